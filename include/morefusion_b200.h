@@ -1,0 +1,184 @@
+/*
+ * morefusion_b200.h -- C ABI of libmorefusion_sm100a.so
+ *
+ * Drop-in boundary for the volumetric-pose hot path of wkentaro/morefusion
+ * (SURVEY.md section 8).  The reference has no native library: each entry point
+ * below replaces one chainer.Function / Link method (cited per function, paths
+ * relative to the reference checkout).  A binding only needs ctypes/cffi: plain
+ * pointers, sizes and scalars -- no torch, chainer or cupy types.
+ *
+ * Conventions
+ *   - every pointer named in/out is a DEVICE pointer unless marked "host";
+ *     tensors are dense, C-contiguous, float32 / int32 as in the reference.
+ *   - grids are [X,Y,Z] (z fastest), batched [B,C,X,Y,Z]; flat voxel index
+ *     ix*Y*Z + iy*Z + iz (average_voxelization_3d.py:92-96).
+ *   - quaternions are (w,x,y,z); transforms are row-major 4x4.
+ *   - the caller owns all memory including `workspace`; kernels never allocate,
+ *     never retain pointers past the call, never synchronise the host, and are
+ *     safe under CUDA-graph capture.  Work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*).
+ *   - return value: 0 = ok; <0 = invalid argument (MF_E_*); >0 = cudaError_t.
+ *   - `flags` (device int32, may be NULL) receives OR-ed MF_FLAG_* bits so the
+ *     host binding can raise the reference's ValueError lazily.
+ */
+#ifndef MOREFUSION_B200_H_
+#define MOREFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_OK 0
+#define MF_E_BADARG (-1)      /* null pointer / negative size */
+#define MF_E_TOOLARGE (-2)    /* B*X*Y*Z (or P*K) does not fit in int32 keys */
+#define MF_E_WORKSPACE (-3)   /* workspace smaller than *_workspace_bytes() */
+#define MF_E_UNSUPPORTED (-4) /* shape outside what the kernel family covers */
+
+#define MF_FLAG_NAN_POINTS 1      /* "points include nan" (average_voxelization_3d.py:13-14,47-48) */
+#define MF_FLAG_UNSORTED_BATCH 2  /* batch_indices not non-decreasing (informational) */
+#define MF_FLAG_BAD_BATCH_INDEX 4 /* batch index outside [0,B): point dropped */
+
+int mf_abi_version(void);
+/* number of SMs / device name the library sees (diagnostics for the binding) */
+int mf_device_sm_count(int device);
+
+/* ------------------------------------------------------------------------
+ * a1  average_voxelization_3d
+ *     replaces AverageVoxelization3D.forward_gpu / backward_gpu
+ *     (morefusion/functions/geometry/average_voxelization_3d.py:43-118, :147-220)
+ * values [N,C] points [N,3] batch_indices [N] -> matrix [B,C,X,Y,Z], counts [B,X,Y,Z]
+ * One pass: every output voxel is written exactly once (no memset, no atomics
+ * on HBM); per-voxel sums are taken in ascending point order (deterministic).
+ * ------------------------------------------------------------------------ */
+size_t mf_average_voxelization_3d_workspace_bytes(int64_t n_points);
+int mf_average_voxelization_3d_fwd(
+    const float* values, const float* points, const int32_t* batch_indices,
+    int64_t n_points, int channels, int batch_size,
+    float origin_x, float origin_y, float origin_z, float pitch,
+    int X, int Y, int Z,
+    float* matrix, int32_t* counts,
+    void* workspace, size_t workspace_bytes, int32_t* flags, void* stream);
+int mf_average_voxelization_3d_bwd(
+    const float* gmatrix, const int32_t* counts,
+    const float* points, const int32_t* batch_indices,
+    int64_t n_points, int channels, int batch_size,
+    float origin_x, float origin_y, float origin_z, float pitch,
+    int X, int Y, int Z,
+    float* gvalues, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a6  max_voxelization_3d
+ *     replaces MaxVoxelization3D.forward_gpu / backward_gpu
+ *     (morefusion/functions/geometry/max_voxelization_3d.py:57-143, :145-185)
+ * winner per voxel = max intensity, lowest point id on exact ties.
+ * ------------------------------------------------------------------------ */
+size_t mf_max_voxelization_3d_workspace_bytes(int batch_size, int X, int Y, int Z);
+int mf_max_voxelization_3d_fwd(
+    const float* values, const float* points, const int32_t* batch_indices,
+    const float* intensities,
+    int64_t n_points, int channels, int batch_size,
+    float origin_x, float origin_y, float origin_z, float pitch,
+    int X, int Y, int Z,
+    float* matrix, int32_t* indices,
+    void* workspace, size_t workspace_bytes, int32_t* flags, void* stream);
+int mf_max_voxelization_3d_bwd(
+    const float* gmatrix, const int32_t* indices,
+    int64_t n_points, int channels, int batch_size, int X, int Y, int Z,
+    float* gvalues, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a5  interpolate_voxel_grid
+ *     replaces InterpolateVoxelGrid.forward_gpu / backward_gpu
+ *     (morefusion/functions/geometry/interpolate_voxel_grid.py:159-214, :216-268)
+ * voxelized [B,C,X,Y,Z], points [P,3] (voxel units), batch_indices [P] -> values [P,C]
+ * `channels_last` != 0 reads/writes the grid as [B,X,Y,Z,C] (internal layout of
+ * the 3D-CNN path; same arithmetic).
+ * ------------------------------------------------------------------------ */
+int mf_interpolate_voxel_grid_fwd(
+    const float* voxelized, const float* points, const int32_t* batch_indices,
+    int64_t n_points, int batch_size, int channels, int X, int Y, int Z,
+    int channels_last, float* values, void* stream);
+int mf_interpolate_voxel_grid_bwd(
+    const float* gvalues, const float* points, const int32_t* batch_indices,
+    int64_t n_points, int batch_size, int channels, int X, int Y, int Z,
+    int channels_last, float* gvoxelized /* fully written */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a3  truncated_distance_function
+ *     replaces TruncatedDistanceFunction.forward_gpu / backward_gpu
+ *     (morefusion/functions/geometry/truncated_distance_function.py:21-101, :103-166)
+ * points [P,3] -> tdf [X,Y,Z] (init = truncation), indices [X,Y,Z] (winning
+ * point id, -1 if none; already divided by K as at :177).
+ * Winner = lexicographic min of (distance, point id): deterministic.
+ * ------------------------------------------------------------------------ */
+size_t mf_truncated_distance_function_workspace_bytes(int X, int Y, int Z);
+int mf_truncated_distance_function_fwd(
+    const float* points, int64_t n_points,
+    float pitch, float origin_x, float origin_y, float origin_z,
+    int X, int Y, int Z, float truncation,
+    float* tdf, int32_t* indices,
+    void* workspace, size_t workspace_bytes, void* stream);
+int mf_truncated_distance_function_bwd(
+    const float* gtdf, const float* points, const int32_t* indices, int64_t n_points,
+    float pitch, float origin_x, float origin_y, float origin_z,
+    int X, int Y, int Z, float truncation,
+    float* gpoints, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a4  pseudo_occupancy_voxelization
+ *     replaces the function at truncated_distance_function.py:181-213
+ * Outputs grid/surface/inside [X,Y,Z]; also tdf, indices, w_surface, w_inside
+ * (kept for backward: weights carry no gradient, :196-213).
+ * ------------------------------------------------------------------------ */
+size_t mf_pseudo_occupancy_voxelization_workspace_bytes(int X, int Y, int Z);
+int mf_pseudo_occupancy_voxelization_fwd(
+    const float* points, const float* sdf, int64_t n_points,
+    float pitch, float origin_x, float origin_y, float origin_z,
+    int X, int Y, int Z, float threshold, float sdf_offset,
+    float* grid, float* grid_surface, float* grid_inside,
+    float* tdf, int32_t* indices, float* w_surface, float* w_inside,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a2  occupancy_grid_3d
+ *     replaces OccupancyGrid3D + the chainer op chain at
+ *     morefusion/functions/geometry/occupancy_grid_3d.py:31-85
+ * matrix-free: never materialises the [X,Y,Z,P] distance tensors.
+ * ------------------------------------------------------------------------ */
+int mf_occupancy_grid_3d_fwd(
+    const float* points, int64_t n_points,
+    float pitch, float origin_x, float origin_y, float origin_z,
+    int X, int Y, int Z, float threshold,
+    float* grid, float* dmin /* [X,Y,Z], kept for backward */, void* stream);
+int mf_occupancy_grid_3d_bwd(
+    const float* ggrid, const float* dmin, const float* points, int64_t n_points,
+    float pitch, float origin_x, float origin_y, float origin_z,
+    int X, int Y, int Z, float threshold,
+    float* gpoints /* zero-filled by the call */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a7  rigid-transform operators
+ *     quaternion_matrix.py:6-78, compose_transform.py:5-48,
+ *     translation_matrix.py:5-39, transformation_matrix.py:5-18,
+ *     transform_points.py:6-30
+ * ------------------------------------------------------------------------ */
+int mf_quaternion_matrix_fwd(const float* q /*[N,4]*/, int64_t n, float* R /*[N,4,4]*/, void* stream);
+int mf_quaternion_matrix_bwd(const float* gR /*[N,4,4]*/, const float* q, int64_t n,
+                             float* gq /*[N,4]*/, void* stream);
+int mf_compose_transform_fwd(const float* R /*[N,3,3]*/, const float* t /*[N,3] or NULL*/,
+                             int64_t n, float* T /*[N,4,4]*/, void* stream);
+int mf_transform_points_fwd(const float* points /*[P,3]*/, int64_t n_points,
+                            const float* T /*[M,4,4]*/, int64_t m,
+                            float* out /*[M,P,3]*/, void* stream);
+int mf_transform_points_bwd(const float* gout /*[M,P,3]*/, const float* points, int64_t n_points,
+                            const float* T, int64_t m,
+                            float* gpoints /*[P,3] or NULL*/, float* gT /*[M,4,4] or NULL*/,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOREFUSION_B200_H_ */

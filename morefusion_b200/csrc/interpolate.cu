@@ -1,0 +1,139 @@
+// interpolate_voxel_grid (trilinear gather / scatter) for sm_100a.
+//
+// Replaces the reference's CuPy kernels K7/K8:
+//   morefusion/functions/geometry/interpolate_voxel_grid.py:6-59 (weights),
+//   :170-212 (forward), :224-266 (backward).
+// Semantics kept: (int) truncation of the coordinate, weight order
+// w000,w100,w010,w001,w110,w011,w101,w111, corners outside the grid skipped
+// without renormalisation, accumulation in corner order j=0..7.  Uses the
+// correct (Y*Z, Z, 1) strides (the reference forward's (X*Y, Y, 1) is equal
+// for cubic grids only).
+#include "common.cuh"
+
+namespace mf {
+
+struct Tri {
+  float w[8];
+  int ix[8], iy[8], iz[8];
+};
+
+__device__ __forceinline__ void trilinear(float x, float y, float z, Tri& t) {
+  int x0 = static_cast<int>(x), y0 = static_cast<int>(y), z0 = static_cast<int>(z);
+  float lx = __fsub_rn(x, (float)x0), ly = __fsub_rn(y, (float)y0), lz = __fsub_rn(z, (float)z0);
+  float hx = __fsub_rn(1.f, lx), hy = __fsub_rn(1.f, ly), hz = __fsub_rn(1.f, lz);
+  t.w[0] = __fmul_rn(__fmul_rn(hx, hy), hz);
+  t.w[1] = __fmul_rn(__fmul_rn(lx, hy), hz);
+  t.w[2] = __fmul_rn(__fmul_rn(hx, ly), hz);
+  t.w[3] = __fmul_rn(__fmul_rn(hx, hy), lz);
+  t.w[4] = __fmul_rn(__fmul_rn(lx, ly), hz);
+  t.w[5] = __fmul_rn(__fmul_rn(hx, ly), lz);
+  t.w[6] = __fmul_rn(__fmul_rn(lx, hy), lz);
+  t.w[7] = __fmul_rn(__fmul_rn(lx, ly), lz);
+  const int dx[8] = {0, 1, 0, 0, 1, 0, 1, 1};
+  const int dy[8] = {0, 0, 1, 0, 1, 1, 0, 1};
+  const int dz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    t.ix[j] = x0 + dx[j];
+    t.iy[j] = y0 + dy[j];
+    t.iz[j] = z0 + dz[j];
+  }
+}
+
+// one thread per (point, channel); channel fastest so that the [P,C] output is coalesced
+// and, for channels_last grids, so are the 8 corner reads.
+template <bool kChannelsLast>
+__global__ void k_interp_fwd(const float* __restrict__ vox, const float* __restrict__ points,
+                             const int* __restrict__ bi, long long P, int B, int C, int X, int Y,
+                             int Z, float* __restrict__ values) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * C) return;
+  long long n = i / C;
+  int c = (int)(i - n * C);
+  int b = bi[n];
+  Tri t;
+  trilinear(points[3 * n], points[3 * n + 1], points[3 * n + 2], t);
+  const long long V = (long long)X * Y * Z;
+  float acc = 0.f;
+  if (b >= 0 && b < B) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t.ix[j] >= 0 && t.ix[j] < X && t.iy[j] >= 0 && t.iy[j] < Y && t.iz[j] >= 0 &&
+          t.iz[j] < Z) {
+        long long flat = ((long long)t.ix[j] * Y + t.iy[j]) * Z + t.iz[j];
+        float v = kChannelsLast ? __ldg(vox + ((long long)b * V + flat) * C + c)
+                                : __ldg(vox + ((long long)b * C + c) * V + flat);
+        acc = __fadd_rn(acc, __fmul_rn(t.w[j], v));
+      }
+    }
+  }
+  values[i] = acc;
+}
+
+template <bool kChannelsLast>
+__global__ void k_interp_bwd(const float* __restrict__ gvalues, const float* __restrict__ points,
+                             const int* __restrict__ bi, long long P, int B, int C, int X, int Y,
+                             int Z, float* __restrict__ gvox) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * C) return;
+  long long n = i / C;
+  int c = (int)(i - n * C);
+  int b = bi[n];
+  if (b < 0 || b >= B) return;
+  Tri t;
+  trilinear(points[3 * n], points[3 * n + 1], points[3 * n + 2], t);
+  const long long V = (long long)X * Y * Z;
+  float g = gvalues[i];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (t.ix[j] >= 0 && t.ix[j] < X && t.iy[j] >= 0 && t.iy[j] < Y && t.iz[j] >= 0 &&
+        t.iz[j] < Z) {
+      long long flat = ((long long)t.ix[j] * Y + t.iy[j]) * Z + t.iz[j];
+      float* dst = kChannelsLast ? gvox + ((long long)b * V + flat) * C + c
+                                 : gvox + ((long long)b * C + c) * V + flat;
+      atomicAdd(dst, __fmul_rn(t.w[j], g));
+    }
+  }
+}
+
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" int mf_interpolate_voxel_grid_fwd(const float* voxelized, const float* points,
+                                             const int32_t* batch_indices, int64_t P, int B, int C,
+                                             int X, int Y, int Z, int channels_last, float* values,
+                                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0 || B <= 0 || C <= 0 || X <= 0 || Y <= 0 || Z <= 0) return MF_E_BADARG;
+  if (P == 0) return MF_OK;
+  if (!voxelized || !points || !batch_indices || !values) return MF_E_BADARG;
+  if (channels_last)
+    k_interp_fwd<true><<<div_up(P * C, 256), 256, 0, stream>>>(voxelized, points, batch_indices, P,
+                                                               B, C, X, Y, Z, values);
+  else
+    k_interp_fwd<false><<<div_up(P * C, 256), 256, 0, stream>>>(voxelized, points, batch_indices,
+                                                                P, B, C, X, Y, Z, values);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_interpolate_voxel_grid_bwd(const float* gvalues, const float* points,
+                                             const int32_t* batch_indices, int64_t P, int B, int C,
+                                             int X, int Y, int Z, int channels_last,
+                                             float* gvoxelized, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0 || B <= 0 || C <= 0 || X <= 0 || Y <= 0 || Z <= 0) return MF_E_BADARG;
+  if (!gvoxelized) return MF_E_BADARG;
+  MF_CUDA_TRY(cudaMemsetAsync(gvoxelized, 0, (size_t)B * C * X * Y * Z * 4, stream));
+  if (P == 0) return MF_OK;
+  if (!gvalues || !points || !batch_indices) return MF_E_BADARG;
+  if (channels_last)
+    k_interp_bwd<true><<<div_up(P * C, 256), 256, 0, stream>>>(gvalues, points, batch_indices, P, B,
+                                                               C, X, Y, Z, gvoxelized);
+  else
+    k_interp_bwd<false><<<div_up(P * C, 256), 256, 0, stream>>>(gvalues, points, batch_indices, P,
+                                                                B, C, X, Y, Z, gvoxelized);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}

@@ -1,0 +1,79 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/*.h declares,
+and the ctypes table in morefusion_b200/_lib.py covers exactly that set."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    syms = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if fn.endswith(".h"):
+            text = open(os.path.join(inc, fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            syms |= set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", text))
+    return syms
+
+
+def test_library_exports_header_symbols():
+    from morefusion_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from morefusion_b200 import build
+        build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in sorted(syms) if not hasattr(L, s)]
+    assert not missing, missing
+    assert syms == set(_lib.SIGNATURES), (syms ^ set(_lib.SIGNATURES))
+    assert L.mf_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    import morefusion_b200 as m
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.functions.average_voxelization_3d(
+            torch.zeros(4, 2), torch.zeros(4, 3), torch.zeros(4, dtype=torch.int32),
+            batch_size=1, origin=(0, 0, 0), pitch=1.0, dimensions=(2, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.functions.truncated_distance_function(
+            torch.zeros(4, 3), pitch=1.0, origin=(0, 0, 0), dims=(2, 2, 2), truncation=1.0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "morefusion_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                assert "from .. import oracle" not in text
+
+
+def test_argument_validation_matches_reference():
+    import torch
+    import morefusion_b200 as m
+    f = m.functions
+    v, p, b = torch.zeros(4, 2), torch.zeros(4, 3), torch.zeros(4, dtype=torch.int32)
+    with pytest.raises(ValueError, match="dimensions must be a tuple"):   # voxelization_3d.py:11-16
+        f.average_voxelization_3d(v, p, b, batch_size=1, origin=(0, 0, 0), pitch=1.0,
+                                  dimensions=[2, 2, 2])
+    with pytest.raises(m.InvalidType):                                     # :20-32
+        f.average_voxelization_3d(v.double(), p, b, batch_size=1, origin=(0, 0, 0), pitch=1.0,
+                                  dimensions=(2, 2, 2))
+    with pytest.raises(m.InvalidType):
+        f.average_voxelization_3d(v, p, b.long(), batch_size=1, origin=(0, 0, 0), pitch=1.0,
+                                  dimensions=(2, 2, 2))
+    with pytest.raises(m.InvalidType):
+        f.interpolate_voxel_grid(torch.zeros(1, 2, 4, 4), p, b)
+    with pytest.raises(AssertionError):                                    # transform_points.py:8
+        f.transform_points(torch.zeros(4, 2), torch.eye(4))
+    with pytest.raises(TypeError):                                         # keyword-only args
+        f.average_voxelization_3d(v, p, b, 1, (0, 0, 0), 1.0, (2, 2, 2))
