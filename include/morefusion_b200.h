@@ -178,6 +178,61 @@ int mf_transform_points_bwd(const float* gout /*[M,P,3]*/, const float* points, 
                             float* gpoints /*[P,3] or NULL*/, float* gT /*[M,4,4] or NULL*/,
                             void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * a10 / a11  3D-CNN section of the singleview_3d pose model
+ *     replaces the chainer/cuDNN layers of
+ *     morefusion/contrib/singleview_3d/models/model.py:62-91 (layer defs),
+ *     :93-141 (_extract), :239-273 (heads + pose assembly)
+ * Activations are channels-last bf16, accumulation fp32.  The k4/s2/p1 Conv3Ds run as
+ * implicit GEMMs over a space-to-depth ("s2d") layout of the zero-padded input:
+ *   X[b][jd][jh][jw][r*C + c] = xpad[b][c][2jd+rd][2jh+rh][2jw+rw],  r = rd<<2|rh<<1|rw,
+ * and weights Wg[co][((ad*2+ah)*2+aw)*8C + r*C + ci] = W[co][ci][2ad+rd][2ah+rh][2aw+rw].
+ * ------------------------------------------------------------------------ */
+#define GEMM_LINEAR 0    /* A[m][k] row-major, leading dimension lda */
+#define GEMM_CONV_S2D 1  /* A gathered from an s2d grid: m=(b,od,oh,ow), k=(a, r*C+ci) */
+#define OUT_BF16 0       /* out[m*ldo + col_off + n], bf16 */
+#define OUT_F32 1        /* out[m*ldo + col_off + n], fp32 */
+#define OUT_S2D_BF16 2   /* row m=(b,od,oh,ow) scattered into the s2d layout of the next conv */
+
+typedef struct GemmParams {
+  const void* A;      /* bf16 */
+  const void* W;      /* bf16 [N][ldw], K-major */
+  const float* bias;  /* [N] or NULL */
+  void* out;
+  int M, N, K;
+  int mode;           /* GEMM_* */
+  long long lda;      /* GEMM_LINEAR */
+  long long ldw;
+  int Do;             /* GEMM_CONV_S2D / OUT_S2D_BF16: output grid edge (16 for conv3, 8 for conv4) */
+  int Ci8;            /* GEMM_CONV_S2D: 8 * input channels */
+  int relu;
+  int out_mode;       /* OUT_* */
+  long long ldo;
+  int col_off;
+} GemmParams;
+
+int mf_cnn_point_mlp(const float* values /*[B,32,P]*/, const float* points /*[B,3,P] voxel frame*/,
+                     const float* w1_rgb, const float* b1_rgb, const float* w1_pcd,
+                     const float* b1_pcd, const float* w2_rgb, const float* b2_rgb,
+                     const float* w2_pcd, const float* b2_pcd, int B, int P, float center,
+                     void* feat_bf16 /*[B*P, ldf], cols 0..215*/, int ldf,
+                     float* feat2 /*[B*P,144]*/, void* stream);
+int mf_cnn_occ_convs(const float* grid_nontarget_empty /*[B,D,D,D]*/, const float* w1,
+                     const float* b1, const float* w2, const float* b2, int B, int D,
+                     float* h1 /*[B,V,8] scratch*/, float* h2 /*[B,V,16]*/, void* stream);
+int mf_cnn_pack_s2d(const float* vox /*[B,C,D,D,D]*/, const float* hocc /*[B,V,Cocc] or NULL*/,
+                    int B, int C, int Cocc, int D, void* X /*bf16 s2d, borders pre-zeroed*/,
+                    void* stream);
+int mf_gemm_bf16_simt(const GemmParams* p, void* stream);
+int mf_cnn_interp_cl(const void* grid_bf16, int s2d, const float* points /*[B,3,P]*/, int B,
+                     int P, int C, int D, float divisor, void* feat_bf16, int ldf, int col_off,
+                     void* stream);
+int mf_cnn_pose(const float* out_rot, const float* out_trans, const float* out_conf,
+                const float* points, const int32_t* class_id, const float* pitch,
+                const float* origin, int B, int P, int n_fg_class, float* rot /*[B,P,4]*/,
+                float* trans /*[B,P,3]*/, float* conf /*[B,P]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,3 +16,4 @@ class config:
 
 
 from . import functions  # noqa: E402,F401
+from . import contrib  # noqa: E402,F401

@@ -1,0 +1,268 @@
+"""singleview_3d pose model: the 3D-CNN section on hand-written sm_100a kernels.
+
+Mirrors morefusion/contrib/singleview_3d/models/model.py (class Model :11-481):
+same constructor keywords (:19-27), the same link names for every layer (:62-91) so a
+reference snapshot maps 1:1 onto ``state_dict`` keys, ``_extract`` (:93-141) and the
+heads / pose assembly of ``predict`` (:239-273).
+
+Internal layout is B200-first, not a translation: activations are channels-last bf16 in
+persistent buffers, the two k4/s2 Conv3Ds and all Conv1D heads are GEMMs on one kernel
+family (tcgen05 when the shape qualifies, SIMT otherwise), and the whole forward is a fixed
+launch sequence that can be captured in a CUDA graph.  No cuDNN / cuBLAS / torch ops on the
+path after the 2-D feature extractor.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .... import _lib
+from ....functions.geometry import _util
+from ....functions.geometry.average_voxelization_3d import AverageVoxelization3D
+
+# YCB voxel pitch for a 32^3 grid = bbox diagonal / 32
+# (datasets/ycb_video/models.py:113-115; table ros/.../utils/data.h:12-32), index = class id
+YCB_VOXEL_PITCH_32 = [
+    None, 0.006296589104319322, 0.008705823111730123, 0.006425726070431774,
+    0.004375644727606043, 0.007023497839423789, 0.003923674166124662, 0.006018916012848706,
+    0.004320481778555272, 0.004535342826373148, 0.006631487204390293, 0.009982031658204186,
+    0.008721623259758258, 0.007331656585392745, 0.005318687227615036, 0.008406278399464109,
+    0.0079006960844688, 0.00699458097945295, 0.0038783371057780278, 0.006648125743278138,
+    0.008405508709996566, 0.0033429720217908734,
+]
+
+
+class GemmParams(ctypes.Structure):
+    _fields_ = [
+        ("A", ctypes.c_void_p), ("W", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("mode", ctypes.c_int), ("lda", ctypes.c_longlong), ("ldw", ctypes.c_longlong),
+        ("Do", ctypes.c_int), ("Ci8", ctypes.c_int), ("relu", ctypes.c_int),
+        ("out_mode", ctypes.c_int), ("ldo", ctypes.c_longlong), ("col_off", ctypes.c_int),
+    ]
+
+
+GEMM_LINEAR, GEMM_CONV_S2D = 0, 1
+OUT_BF16, OUT_F32, OUT_S2D_BF16 = 0, 1, 2
+
+
+def pack_conv_k4s2_weight(W):
+    """OIDHW [Co,Ci,4,4,4] fp32 -> [Co, 64*Ci] bf16 in implicit-GEMM K order
+    k = ((ad*2+ah)*2+aw)*8Ci + (rd*4+rh*2+rw)*Ci + ci with kd = 2ad+rd (etc.)."""
+    Co, Ci = W.shape[:2]
+    W = W.reshape(Co, Ci, 2, 2, 2, 2, 2, 2)            # co ci ad rd ah rh aw rw
+    W = W.permute(0, 2, 4, 6, 3, 5, 7, 1)              # co ad ah aw rd rh rw ci
+    return W.reshape(Co, 64 * Ci).to(torch.bfloat16).contiguous()
+
+
+class Model(torch.nn.Module):
+
+    _lambda_confidence = 0.015
+    _n_point = 1000
+    _voxel_dim = 32
+
+    def __init__(self, *, n_fg_class, pretrained_resnet18=False, with_occupancy=False,
+                 loss=None, loss_scale=None):
+        super().__init__()
+        self._n_fg_class = n_fg_class
+        self._with_occupancy = with_occupancy
+        if loss is None:
+            loss = "add/add_s"
+        assert loss in ["add", "add/add_s", "add+occupancy", "add/add_s+occupancy"]
+        self._loss = loss
+        if loss_scale is None:
+            loss_scale = {"occupancy": 1.0}
+        self._loss_scale = loss_scale
+        self._pretrained_resnet18 = pretrained_resnet18
+
+        nn = torch.nn
+        self.conv1_rgb = nn.Conv1d(32, 64, 1)
+        self.conv1_pcd = nn.Conv1d(3, 8, 1)
+        self.conv2_rgb = nn.Conv1d(64, 128, 1)
+        self.conv2_pcd = nn.Conv1d(8, 16, 1)
+        if with_occupancy:
+            self.conv1_occ = nn.Conv3d(1, 8, 3, 1, padding=1)
+            self.conv2_occ = nn.Conv3d(8, 16, 3, 1, padding=2, dilation=2)
+        cin3 = 144 + (16 if with_occupancy else 0)
+        self.conv3 = nn.Conv3d(cin3, 256, 4, 2, padding=1)
+        self.conv4 = nn.Conv3d(256, 512, 4, 2, padding=1)
+        for head, cout in (("rot", n_fg_class * 4), ("trans", n_fg_class * 3),
+                           ("conf", n_fg_class)):
+            setattr(self, f"conv1_{head}", nn.Conv1d(984, 640, 1))
+            setattr(self, f"conv2_{head}", nn.Conv1d(640, 256, 1))
+            setattr(self, f"conv3_{head}", nn.Conv1d(256, 128, 1))
+            setattr(self, f"conv4_{head}", nn.Conv1d(128, cout, 1))
+        self._packed = None
+        self._wbufs = {}
+        self.use_tensor_cores = True
+
+    # ------------------------------------------------------------------ weights
+    def load_reference_weights(self, weights):
+        """weights: {'<link>/W': ndarray, '<link>/b': ndarray} keyed like a chainer npz
+        snapshot of the reference model (model.py:62-91)."""
+        with torch.no_grad():
+            for name, mod in self.named_children():
+                if name + "/W" in weights:
+                    mod.weight.copy_(torch.as_tensor(weights[name + "/W"]).reshape(mod.weight.shape))
+                    mod.bias.copy_(torch.as_tensor(weights[name + "/b"]))
+        self._packed = None
+        return self
+
+    def _pack(self):
+        dev = self.conv3.weight.device
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()      # noqa: E731
+        p = {}
+        for n in ("conv1_rgb", "conv1_pcd", "conv2_rgb", "conv2_pcd"):
+            m = getattr(self, n)
+            p[n + "/W"] = f32(m.weight.reshape(m.weight.shape[0], -1))
+            p[n + "/b"] = f32(m.bias)
+        if self._with_occupancy:
+            for n in ("conv1_occ", "conv2_occ"):
+                m = getattr(self, n)
+                p[n + "/W"] = f32(m.weight)
+                p[n + "/b"] = f32(m.bias)
+        for n in ("conv3", "conv4"):
+            m = getattr(self, n)
+            p[n + "/W"] = pack_conv_k4s2_weight(m.weight.detach().float())
+            p[n + "/b"] = f32(m.bias)
+        # heads: layer 1 of the three heads share their input -> one GEMM with N = 3*640
+        heads = ("rot", "trans", "conf")
+        p["head1/W"] = torch.cat(
+            [getattr(self, f"conv1_{h}").weight.detach().reshape(640, 984) for h in heads], 0
+        ).to(torch.bfloat16).contiguous()
+        p["head1/b"] = torch.cat([f32(getattr(self, f"conv1_{h}").bias) for h in heads])
+        for h in heads:
+            for layer in (2, 3, 4):
+                m = getattr(self, f"conv{layer}_{h}")
+                W = m.weight.detach().reshape(m.weight.shape[0], -1).to(torch.bfloat16)
+                if layer == 4:     # pad N to a multiple of 8 rows? not needed: K-major rows only
+                    pass
+                p[f"conv{layer}_{h}/W"] = W.contiguous()
+                p[f"conv{layer}_{h}/b"] = f32(m.bias)
+        self._packed = p
+        self._packed_dev = dev
+        return p
+
+    def _work_buffers(self, B, P, dev):
+        key = (B, P, dev)
+        if key in self._wbufs:
+            return self._wbufs[key]
+        D = self._voxel_dim
+        Ct = 144 + (16 if self._with_occupancy else 0)
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dt=bf: torch.zeros(*s, dtype=dt, device=dev)     # noqa: E731
+        NP = B * P
+        b = dict(
+            feat=z(NP, 984), feat2=z(NP, 144, dt=f32),
+            x3=z(B, 17, 17, 17, 8 * Ct),          # s2d of the zero-padded 32^3 x Ct grid
+            x4=z(B, 9, 9, 9, 8 * 256),            # s2d of the zero-padded 16^3 x 256 grid (= H3)
+            h4=z(B, 8, 8, 8, 512),
+            hd1=z(NP, 1920), hd2=z(NP, 3 * 256), hd3=z(NP, 3 * 128),
+            out_rot=z(NP, self._n_fg_class * 4, dt=f32),
+            out_trans=z(NP, self._n_fg_class * 3, dt=f32),
+            out_conf=z(NP, self._n_fg_class, dt=f32),
+            bi=torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P),
+        )
+        if self._with_occupancy:
+            b["occ1"] = z(B, D ** 3, 8, dt=f32)
+            b["occ2"] = z(B, D ** 3, 16, dt=f32)
+        self._wbufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------ kernels
+    def _gemm(self, L, A, W, bias, out, M, N, K, *, mode=GEMM_LINEAR, lda=0, Do=0, Ci8=0,
+              relu=1, out_mode=OUT_BF16, ldo=0, col_off=0):
+        gp = GemmParams(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(out), M, N, K, mode,
+                        lda, W.shape[1], Do, Ci8, relu, out_mode, ldo, col_off)
+        fn = L.mf_gemm_bf16_simt
+        if self.use_tensor_cores and hasattr(L, "mf_gemm_bf16_tc"):
+            rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.stream())
+            if rc == 0:
+                return
+            if rc != -4:          # MF_E_UNSUPPORTED -> SIMT kernel handles the shape
+                _lib.check(rc, "gemm_bf16_tc")
+        _lib.check(fn(ctypes.byref(gp), _lib.stream()), "gemm_bf16_simt")
+
+    def forward_features(self, *, class_id, values, points, pitch, origin,
+                         grid_nontarget_empty=None):
+        """The hot path proper: everything after the 2-D extractor (model.py:236-273).
+
+        values [B,32,P] f32 per-point RGB features, points [B,3,P] f32 in the voxel frame,
+        pitch [B], origin [B,3], class_id [B] (int32), grid_nontarget_empty [B,32,32,32].
+        Returns rot [B,P,4], trans [B,P,3], conf [B,P] (fp32)."""
+        L = _lib.lib()
+        _lib.require_cuda(values, points)
+        dev = values.device
+        B, _, P = values.shape
+        D = self._voxel_dim
+        if self._packed is None or self._packed_dev != self.conv3.weight.device:
+            self._pack()
+        w = self._packed
+        buf = self._work_buffers(B, P, dev)
+        NP = B * P
+        nfg = self._n_fg_class
+        values = values.contiguous().float()
+        points = points.contiguous().float()
+        s = _lib.stream
+        with torch.cuda.device(dev):
+            _lib.check(L.mf_cnn_point_mlp(
+                _lib.ptr(values), _lib.ptr(points),
+                _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
+                _lib.ptr(w["conv1_pcd/W"]), _lib.ptr(w["conv1_pcd/b"]),
+                _lib.ptr(w["conv2_rgb/W"]), _lib.ptr(w["conv2_rgb/b"]),
+                _lib.ptr(w["conv2_pcd/W"]), _lib.ptr(w["conv2_pcd/b"]),
+                B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), 984, _lib.ptr(buf["feat2"]), s()),
+                "point_mlp")
+            # _voxelize (model.py:143-164): origin (0,0,0), pitch 1.0, 32^3
+            pts_np = points.permute(0, 2, 1).reshape(NP, 3).contiguous()
+            vox, _ = AverageVoxelization3D.apply(
+                buf["feat2"], pts_np, buf["bi"], B, (0.0, 0.0, 0.0), 1.0, (D, D, D))
+            hocc = None
+            Cocc = 0
+            if self._with_occupancy:
+                g = grid_nontarget_empty.to(torch.float32).contiguous()
+                _lib.check(L.mf_cnn_occ_convs(
+                    _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                    _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                    _lib.ptr(buf["occ1"]), _lib.ptr(buf["occ2"]), s()), "occ_convs")
+                hocc, Cocc = buf["occ2"], 16
+            Ct = 144 + Cocc
+            _lib.check(L.mf_cnn_pack_s2d(_lib.ptr(vox), _lib.ptr(hocc), B, 144, Cocc, D,
+                                         _lib.ptr(buf["x3"]), s()), "pack_s2d")
+            # conv3: 32^3 x Ct -> 16^3 x 256, written straight into conv4's s2d input
+            self._gemm(L, buf["x3"], w["conv3/W"], w["conv3/b"], buf["x4"], B * 4096, 256,
+                       64 * Ct, mode=GEMM_CONV_S2D, Do=16, Ci8=8 * Ct, out_mode=OUT_S2D_BF16)
+            _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["x4"]), 1, _lib.ptr(points), B, P, 256, 16,
+                                          2.0, _lib.ptr(buf["feat"]), 984, 216, s()), "interp3")
+            # conv4: 16^3 x 256 -> 8^3 x 512
+            self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
+                       64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
+                       ldo=512)
+            _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["h4"]), 0, _lib.ptr(points), B, P, 512, 8,
+                                          4.0, _lib.ptr(buf["feat"]), 984, 472, s()), "interp4")
+            # heads (model.py:239-254)
+            self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
+                       lda=984, ldo=1920)
+            for i, h in enumerate(("rot", "trans", "conf")):
+                a1 = buf["hd1"][:, i * 640:]
+                self._gemm(L, a1, w[f"conv2_{h}/W"], w[f"conv2_{h}/b"], buf["hd2"], NP, 256, 640,
+                           lda=1920, ldo=768, col_off=i * 256)
+                a2 = buf["hd2"][:, i * 256:]
+                self._gemm(L, a2, w[f"conv3_{h}/W"], w[f"conv3_{h}/b"], buf["hd3"], NP, 128, 256,
+                           lda=768, ldo=384, col_off=i * 128)
+                a3 = buf["hd3"][:, i * 128:]
+                o = buf["out_" + h]
+                self._gemm(L, a3, w[f"conv4_{h}/W"], w[f"conv4_{h}/b"], o, NP, o.shape[1], 128,
+                           lda=384, relu=0, out_mode=OUT_F32, ldo=o.shape[1])
+            rot = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+            trans = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
+            conf = torch.empty((B, P), dtype=torch.float32, device=dev)
+            cid = class_id.to(device=dev, dtype=torch.int32).contiguous()
+            pt = torch.as_tensor(pitch, dtype=torch.float32, device=dev).contiguous()
+            og = torch.as_tensor(origin, dtype=torch.float32, device=dev).contiguous()
+            _lib.check(L.mf_cnn_pose(
+                _lib.ptr(buf["out_rot"]), _lib.ptr(buf["out_trans"]), _lib.ptr(buf["out_conf"]),
+                _lib.ptr(points), _lib.ptr(cid), _lib.ptr(pt), _lib.ptr(og), B, P, nfg,
+                _lib.ptr(rot), _lib.ptr(trans), _lib.ptr(conf), s()), "pose")
+        return rot, trans, conf

@@ -1,0 +1,471 @@
+// 3D-CNN section of the singleview_3d pose model (sm_100a): SIMT stages.
+//
+// Replaces the chainer/cuDNN layers of
+//   morefusion/contrib/singleview_3d/models/model.py:93-141 (_extract), :239-273 (heads, pose)
+// with channels-last bf16 activations and fp32 accumulation:
+//   * per-point 1x1 "Conv1D" stacks (model.py:62-66,97-108)           -> k_point_mlp
+//   * conv1_occ / conv2_occ thin 3^3 stencils (model.py:69-70,114-125) -> k_occ_conv1/2
+//   * space-to-depth packing of the 32^3 x160 grid for the k4 s2 convs -> k_pack_s2d
+//   * GEMM (implicit-GEMM conv3/conv4 over the s2d layout, and the head Conv1Ds);
+//     this file holds the SIMT version, conv3d_tc.cu the tcgen05 one      -> k_gemm_simt
+//   * trilinear gather from channels-last bf16 grids (model.py:130-139) -> k_interp_cl
+//   * class selection / normalise / voxel->camera frame (model.py:256-273) -> k_pose
+//
+// Space-to-depth: a k=4, stride-2, pad-1 convolution over x equals a k=2, stride-1
+// convolution over y[j, r] = xpad[2j + r] (r = parity bits per axis, xpad = x padded by 1):
+//   out[o] = sum_{a in {0,1}^3} sum_{r, ci} W[2a+r, ci] * y[o + a, (r, ci)]
+// so the A operand of the implicit GEMM for one K block is a dense box of y.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "cnn.cuh"
+
+namespace mf {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------ per-point MLP
+constexpr int kMlpPts = 16;
+
+__global__ void __launch_bounds__(256)
+k_point_mlp(const float* __restrict__ values,  // [B,32,P]
+            const float* __restrict__ points,  // [B,3,P] voxel frame
+            const float* __restrict__ w1r, const float* __restrict__ b1r,   // [64,32]
+            const float* __restrict__ w1p, const float* __restrict__ b1p,   // [8,3]
+            const float* __restrict__ w2r, const float* __restrict__ b2r,   // [128,64]
+            const float* __restrict__ w2p, const float* __restrict__ b2p,   // [16,8]
+            int B, int P, float center, bf16* __restrict__ feat, int ldf,
+            float* __restrict__ feat2) {
+  __shared__ float xin[kMlpPts][36];
+  __shared__ float h1[kMlpPts][73];
+  const long long n0 = (long long)blockIdx.x * kMlpPts;
+  const long long NP = (long long)B * P;
+  for (int e = threadIdx.x; e < kMlpPts * 35; e += blockDim.x) {
+    int pt = e / 35, c = e % 35;
+    long long n = n0 + pt;
+    float v = 0.f;
+    if (n < NP) {
+      long long b = n / P, p = n % P;
+      v = (c < 32) ? values[(b * 32 + c) * P + p] : (center - points[(b * 3 + (c - 32)) * P + p]);
+    }
+    xin[pt][c] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kMlpPts * 72; e += blockDim.x) {
+    int pt = e / 72, oc = e % 72;
+    float acc;
+    if (oc < 64) {
+      acc = b1r[oc];
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(w1r + oc * 32 + k), xin[pt][k], acc);
+    } else {
+      int o = oc - 64;
+      acc = b1p[o];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc = fmaf(__ldg(w1p + o * 3 + k), xin[pt][32 + k], acc);
+    }
+    h1[pt][oc] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kMlpPts * 72; e += blockDim.x) {
+    int pt = e / 72, oc = e % 72;
+    long long n = n0 + pt;
+    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(h1[pt][oc]);
+  }
+  for (int e = threadIdx.x; e < kMlpPts * 144; e += blockDim.x) {
+    int pt = e / 144, oc = e % 144;
+    float acc;
+    if (oc < 128) {
+      acc = b2r[oc];
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) acc = fmaf(__ldg(w2r + oc * 64 + k), h1[pt][k], acc);
+    } else {
+      int o = oc - 128;
+      acc = b2p[o];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(w2p + o * 8 + k), h1[pt][64 + k], acc);
+    }
+    acc = fmaxf(acc, 0.f);
+    long long n = n0 + pt;
+    if (n < NP) {
+      feat[n * ldf + 72 + oc] = __float2bfloat16(acc);
+      feat2[n * 144 + oc] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ occupancy stencils
+// conv1_occ: Conv3D(1->8, k3, s1, p1) + ReLU; channels-last fp32 output [B,V,8]
+__global__ void k_occ_conv1(const float* __restrict__ gne, const float* __restrict__ w,
+                            const float* __restrict__ bias, int B, int D,
+                            float* __restrict__ h1) {
+  __shared__ float sw[8 * 27 + 8];
+  for (int e = threadIdx.x; e < 8 * 27; e += blockDim.x) sw[e] = w[e];
+  if (threadIdx.x < 8) sw[8 * 27 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  long long V = (long long)D * D * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * V) return;
+  long long b = i / V, v = i % V;
+  int z = (int)(v % D), y = (int)((v / D) % D), x = (int)(v / ((long long)D * D));
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = sw[8 * 27 + c];
+  for (int kd = 0; kd < 3; ++kd) {
+    int xx = x + kd - 1;
+    if (xx < 0 || xx >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      int yy = y + kh - 1;
+      if (yy < 0 || yy >= D) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int zz = z + kw - 1;
+        if (zz < 0 || zz >= D) continue;
+        float in = gne[b * V + ((long long)xx * D + yy) * D + zz];
+        int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(sw[c * 27 + tap], in, acc[c]);
+      }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(h1 + i * 8);
+  o[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  o[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+}
+
+// conv2_occ: Conv3D(8->16, k3, s1, p2, dilate 2) + ReLU; output [B,V,16] fp32
+__global__ void k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
+                            const float* __restrict__ bias, int B, int D,
+                            float* __restrict__ h2) {
+  __shared__ float sw[27 * 8 * 16 + 16];   // [tap][ci][co]
+  for (int e = threadIdx.x; e < 16 * 8 * 27; e += blockDim.x) {
+    int co = e / (8 * 27), r = e % (8 * 27), ci = r / 27, tap = r % 27;   // OIDHW
+    sw[(tap * 8 + ci) * 16 + co] = w[e];
+  }
+  if (threadIdx.x < 16) sw[27 * 8 * 16 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  long long V = (long long)D * D * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * V) return;
+  long long b = i / V, v = i % V;
+  int z = (int)(v % D), y = (int)((v / D) % D), x = (int)(v / ((long long)D * D));
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = sw[27 * 8 * 16 + c];
+  for (int kd = 0; kd < 3; ++kd) {
+    int xx = x + 2 * (kd - 1);
+    if (xx < 0 || xx >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      int yy = y + 2 * (kh - 1);
+      if (yy < 0 || yy >= D) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int zz = z + 2 * (kw - 1);
+        if (zz < 0 || zz >= D) continue;
+        const float4* src =
+            reinterpret_cast<const float4*>(h1 + (b * V + ((long long)xx * D + yy) * D + zz) * 8);
+        float4 lo = __ldg(src), hi = __ldg(src + 1);
+        float in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+          for (int co = 0; co < 16; ++co)
+            acc[co] = fmaf(sw[(tap * 8 + ci) * 16 + co], in[ci], acc[co]);
+      }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(h2 + i * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    o[q] = make_float4(fmaxf(acc[4 * q], 0.f), fmaxf(acc[4 * q + 1], 0.f),
+                       fmaxf(acc[4 * q + 2], 0.f), fmaxf(acc[4 * q + 3], 0.f));
+}
+
+// ------------------------------------------------------------------ s2d packing
+// X[b][jd][jh][jw][r*Ct + c] = xpad[b][c][2jd+rd][2jh+rh][2jw+rw]  (bf16), Ct = C + Cocc.
+// One CTA per (b, id, ih) row of D voxels: coalesced reads along iw, transpose in smem,
+// coalesced channel-contiguous writes.  Border entries (xpad == 0) are never written: the
+// buffer is zeroed once at allocation.
+__global__ void __launch_bounds__(256)
+k_pack_s2d(const float* __restrict__ vox,   // [B,C,D,D,D]
+           const float* __restrict__ hocc,  // [B,V,Cocc] or null
+           int B, int C, int Cocc, int D, bf16* __restrict__ X) {
+  extern __shared__ float tile[];            // [Ct][D+1]
+  const int Ct = C + Cocc, J = D / 2 + 1;
+  int ih = blockIdx.x % D, id = (blockIdx.x / D) % D, b = blockIdx.x / (D * D);
+  const long long V = (long long)D * D * D;
+  const long long rowv = ((long long)id * D + ih) * D;
+  for (int e = threadIdx.x; e < C * D; e += blockDim.x) {
+    int c = e / D, iw = e % D;
+    tile[c * (D + 1) + iw] = vox[((long long)b * C + c) * V + rowv + iw];
+  }
+  for (int e = threadIdx.x; e < Cocc * D; e += blockDim.x) {
+    int iw = e / Cocc, c = e % Cocc;
+    tile[(C + c) * (D + 1) + iw] = hocc[((long long)b * V + rowv + iw) * Cocc + c];
+  }
+  __syncthreads();
+  int pd = id + 1, ph = ih + 1;
+  int jd = pd >> 1, rd = pd & 1, jh = ph >> 1, rh = ph & 1;
+  for (int e = threadIdx.x; e < D * Ct; e += blockDim.x) {
+    int iw = e / Ct, c = e % Ct;
+    int pw = iw + 1, jw = pw >> 1, rw = pw & 1;
+    int r = (rd << 2) | (rh << 1) | rw;
+    long long dst = ((((long long)b * J + jd) * J + jh) * J + jw) * (8LL * Ct) + (long long)r * Ct + c;
+    X[dst] = __float2bfloat16(tile[c * (D + 1) + iw]);
+  }
+}
+
+// ------------------------------------------------------------------ SIMT GEMM
+// out[m, n] = act( sum_k A(m,k) * W[n,k] + bias[n] ),  bf16 operands, fp32 accumulate.
+constexpr int BM = 64, BN = 64, BK = 32;
+
+__device__ __forceinline__ long long a_offset(const GemmParams& p, int m, int k) {
+  if (p.mode == GEMM_LINEAR) return (long long)m * p.lda + k;
+  int Do = p.Do, Js = Do + 1;
+  int ow = m % Do, oh = (m / Do) % Do, od = (m / (Do * Do)) % Do, b = m / (Do * Do * Do);
+  int a = k / p.Ci8, kc = k - a * p.Ci8;
+  int ad = (a >> 2) & 1, ah = (a >> 1) & 1, aw = a & 1;
+  return ((((long long)b * Js + od + ad) * Js + oh + ah) * Js + ow + aw) * p.Ci8 + kc;
+}
+
+__device__ __forceinline__ void store_out(const GemmParams& p, int m, int n, float v) {
+  if (p.relu) v = fmaxf(v, 0.f);
+  if (p.out_mode == OUT_F32) {
+    reinterpret_cast<float*>(p.out)[(long long)m * p.ldo + p.col_off + n] = v;
+  } else if (p.out_mode == OUT_BF16) {
+    reinterpret_cast<bf16*>(p.out)[(long long)m * p.ldo + p.col_off + n] = __float2bfloat16(v);
+  } else {  // OUT_S2D_BF16: row m = (b,od,oh,ow) of a Do^3 grid -> s2d-padded layout of the next conv
+    int Do = p.Do, J = Do / 2 + 1;
+    int ow = m % Do, oh = (m / Do) % Do, od = (m / (Do * Do)) % Do, b = m / (Do * Do * Do);
+    int pd = od + 1, ph = oh + 1, pw = ow + 1;
+    int r = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+    long long dst = ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * p.N) +
+                    (long long)r * p.N + n;
+    reinterpret_cast<bf16*>(p.out)[dst] = __float2bfloat16(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_gemm_simt(GemmParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = tid % 16, ty = tid / 16;       // 16x16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid / 4, lk = (tid % 4) * 8;   // loader: row 0..63, k offset 0,8,16,24
+  const bf16* A = reinterpret_cast<const bf16*>(p.A);
+  const bf16* W = reinterpret_cast<const bf16*>(p.W);
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    {
+      int m = m0 + lr, k = k0 + lk;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < p.M && k < p.K) v = __ldg(reinterpret_cast<const uint4*>(A + a_offset(p, m, k)));
+      const bf16* h = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[lk + j][lr] = __bfloat162float(h[j]);
+    }
+    {
+      int n = n0 + lr, k = k0 + lk;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (n < p.N && k < p.K) v = __ldg(reinterpret_cast<const uint4*>(W + (long long)n * p.ldw + k));
+      const bf16* h = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Ws[lk + j][lr] = __bfloat162float(h[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      store_out(p, m, n, acc[i][j] + (p.bias ? p.bias[n] : 0.f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ trilinear gather (bf16, channels-last)
+// same arithmetic as interpolate.cu (reference interpolate_voxel_grid.py:6-59,176-208) on the
+// model's internal layouts; `scale` = 1/2 or 1/4 applied as points / (1/scale) like model.py:131,137.
+template <bool kS2D>
+__global__ void k_interp_cl(const bf16* __restrict__ grid, const float* __restrict__ points,  // [B,3,P]
+                            int B, int P, int C, int D, float divisor, bf16* __restrict__ feat,
+                            int ldf, int col_off) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long NP = (long long)B * P;
+  if (i >= NP * C) return;
+  long long n = i / C;
+  int c = (int)(i - n * C);
+  long long b = n / P, pp = n % P;
+  float x = __fdiv_rn(points[(b * 3 + 0) * P + pp], divisor);
+  float y = __fdiv_rn(points[(b * 3 + 1) * P + pp], divisor);
+  float z = __fdiv_rn(points[(b * 3 + 2) * P + pp], divisor);
+  int x0 = static_cast<int>(x), y0 = static_cast<int>(y), z0 = static_cast<int>(z);
+  float lx = x - (float)x0, ly = y - (float)y0, lz = z - (float)z0;
+  float hx = 1.f - lx, hy = 1.f - ly, hz = 1.f - lz;
+  const float w[8] = {hx * hy * hz, lx * hy * hz, hx * ly * hz, hx * hy * lz,
+                      lx * ly * hz, hx * ly * lz, lx * hy * lz, lx * ly * lz};
+  const int dx[8] = {0, 1, 0, 0, 1, 0, 1, 1};
+  const int dy[8] = {0, 0, 1, 0, 1, 1, 0, 1};
+  const int dz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+  float acc = 0.f;
+  const int J = D / 2 + 1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ix = x0 + dx[j], iy = y0 + dy[j], iz = z0 + dz[j];
+    if (ix < 0 || ix >= D || iy < 0 || iy >= D || iz < 0 || iz >= D) continue;
+    long long src;
+    if (kS2D) {
+      int pd = ix + 1, ph = iy + 1, pw = iz + 1;
+      int r = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+      src = ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * C) +
+            (long long)r * C + c;
+    } else {
+      src = (((b * D + ix) * D + iy) * D + iz) * (long long)C + c;
+    }
+    acc = fmaf(w[j], __bfloat162float(grid[src]), acc);
+  }
+  feat[n * ldf + col_off + c] = __float2bfloat16(acc);
+}
+
+// ------------------------------------------------------------------ pose epilogue (model.py:256-273)
+__global__ void k_pose(const float* __restrict__ out_rot,    // [B*P, nfg*4]
+                       const float* __restrict__ out_trans,  // [B*P, nfg*3]
+                       const float* __restrict__ out_conf,   // [B*P, nfg]
+                       const float* __restrict__ points,     // [B,3,P] voxel frame
+                       const int* __restrict__ class_id, const float* __restrict__ pitch,
+                       const float* __restrict__ origin, int B, int P, int nfg,
+                       float* __restrict__ rot, float* __restrict__ trans,
+                       float* __restrict__ conf) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)B * P) return;
+  long long b = n / P, p = n % P;
+  int fg = class_id[b] - 1;
+  const float* q = out_rot + n * (nfg * 4) + fg * 4;
+  float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + 1e-5f;  // F.normalize
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rot[n * 4 + k] = q[k] / nrm;
+  float pt = pitch[b];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float cam = points[(b * 3 + k) * P + p] * pt + origin[b * 3 + k];
+    trans[n * 3 + k] = cam + out_trans[n * (nfg * 3) + fg * 3 + k] * pt;
+  }
+  float cf = out_conf[n * nfg + fg];
+  conf[n] = 1.f / (1.f + expf(-cf));
+}
+
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const float* w1r,
+                                const float* b1r, const float* w1p, const float* b1p,
+                                const float* w2r, const float* b2r, const float* w2p,
+                                const float* b2p, int B, int P, float center, void* feat, int ldf,
+                                float* feat2, void* stream_) {
+  if (B <= 0 || P <= 0 || ldf < 216) return MF_E_BADARG;
+  if (!values || !points || !w1r || !b1r || !w1p || !b1p || !w2r || !b2r || !w2p || !b2p ||
+      !feat || !feat2)
+    return MF_E_BADARG;
+  long long NP = (long long)B * P;
+  k_point_mlp<<<div_up(NP, kMlpPts), 256, 0, (cudaStream_t)stream_>>>(
+      values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat, ldf,
+      feat2);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_occ_convs(const float* gne, const float* w1, const float* b1,
+                                const float* w2, const float* b2, int B, int D, float* h1,
+                                float* h2, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B <= 0 || D <= 0 || !gne || !w1 || !b1 || !w2 || !b2 || !h1 || !h2) return MF_E_BADARG;
+  long long BV = (long long)B * D * D * D;
+  k_occ_conv1<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, h1);
+  MF_LAUNCH_CHECK();
+  k_occ_conv2<<<div_up(BV, 128), 128, 0, stream>>>(h1, w2, b2, B, D, h2);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_pack_s2d(const float* vox, const float* hocc, int B, int C, int Cocc, int D,
+                               void* X, void* stream_) {
+  if (B <= 0 || C <= 0 || Cocc < 0 || D <= 0 || (D & 1) || !vox || !X) return MF_E_BADARG;
+  if (Cocc > 0 && !hocc) return MF_E_BADARG;
+  size_t smem = (size_t)(C + Cocc) * (D + 1) * 4;
+  static bool attr = false;
+  if (!attr) {
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_pack_s2d, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     96 * 1024));
+    attr = true;
+  }
+  if (smem > 96 * 1024) return MF_E_UNSUPPORTED;
+  k_pack_s2d<<<(unsigned)(B * D * D), 256, smem, (cudaStream_t)stream_>>>(vox, hocc, B, C, Cocc,
+                                                                        D, (bf16*)X);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_gemm_bf16_simt(const GemmParams* hp, void* stream_) {
+  if (!hp) return MF_E_BADARG;
+  GemmParams p = *hp;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
+  if (p.K % 8 != 0 || p.ldw % 8 != 0) return MF_E_UNSUPPORTED;
+  if (p.mode == GEMM_LINEAR && p.lda % 8 != 0) return MF_E_UNSUPPORTED;
+  if (p.mode == GEMM_CONV_S2D && (p.Ci8 % 8 != 0 || p.K != 8 * p.Ci8)) return MF_E_UNSUPPORTED;
+  dim3 grid(div_up(p.N, BN), div_up(p.M, BM));
+  k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream_>>>(p);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_interp_cl(const void* grid, int s2d, const float* points, int B, int P,
+                                int C, int D, float divisor, void* feat, int ldf, int col_off,
+                                void* stream_) {
+  if (B <= 0 || P <= 0 || C <= 0 || D <= 0 || !grid || !points || !feat) return MF_E_BADARG;
+  long long tot = (long long)B * P * C;
+  if (s2d)
+    k_interp_cl<true><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
+        (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
+  else
+    k_interp_cl<false><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
+        (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_pose(const float* out_rot, const float* out_trans, const float* out_conf,
+                           const float* points, const int32_t* class_id, const float* pitch,
+                           const float* origin, int B, int P, int nfg, float* rot, float* trans,
+                           float* conf, void* stream_) {
+  if (B <= 0 || P <= 0 || nfg <= 0) return MF_E_BADARG;
+  if (!out_rot || !out_trans || !out_conf || !points || !class_id || !pitch || !origin || !rot ||
+      !trans || !conf)
+    return MF_E_BADARG;
+  k_pose<<<div_up((long long)B * P, 128), 128, 0, (cudaStream_t)stream_>>>(
+      out_rot, out_trans, out_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}

@@ -1,0 +1,77 @@
+"""GPU parity: 3D-CNN section of singleview_3d.Model (CUDA, bf16 operands / fp32 accumulate)
+vs the torch-CPU oracle.  Tolerances: against the oracle run with bf16-rounded operands at the
+same points (tight) and against the pure fp32 oracle (bf16-level)."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as ocnn
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def make_inputs(B, P=1000, seed=0):
+    rs = np.random.RandomState(seed)
+    values = rs.normal(0, 1, (B, 32, P)).astype(F32)
+    # surface-like cloud in the voxel frame, a few points outside the grid
+    c = rs.uniform(12, 20, (B, 3, 1))
+    d = rs.normal(size=(B, 3, P))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    points = (c + d * rs.uniform(6, 11, (B, 1, P))).astype(F32)
+    points[:, :, :5] = rs.uniform(-3, 35, (B, 3, 5))
+    gne = (rs.uniform(size=(B, 32, 32, 32)) < 0.4)
+    class_id = (np.arange(B) % 21 + 1).astype(np.int32)
+    pitch = np.array([0.0063 + 0.0005 * i for i in range(B)], F32)
+    origin = rs.uniform(-0.2, 0.6, (B, 3)).astype(F32)
+    return dict(values=values, points=points, grid_nontarget_empty=gne, class_id=class_id,
+                pitch=pitch, origin=origin)
+
+
+def run_cuda(w, inp, dev, with_occ=True, tc=True):
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    m = Model(n_fg_class=21, with_occupancy=with_occ).to(dev)
+    m.load_reference_weights(w)
+    m.use_tensor_cores = tc
+    rot, trans, conf = m.forward_features(
+        class_id=torch.as_tensor(inp["class_id"], device=dev),
+        values=torch.as_tensor(inp["values"], device=dev),
+        points=torch.as_tensor(inp["points"], device=dev),
+        pitch=inp["pitch"], origin=inp["origin"],
+        grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=dev))
+    torch.cuda.synchronize()
+    return m, rot.cpu().numpy(), trans.cpu().numpy(), conf.cpu().numpy()
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("with_occ", [True, False])
+def test_cnn_forward_vs_oracle(cuda_device, with_occ, tc):
+    B = 2
+    w = ocnn.init_weights(21, seed=1, with_occupancy=with_occ)
+    inp = make_inputs(B)
+    m, rot, trans, conf = run_cuda(w, inp, cuda_device, with_occ, tc)
+    ref = ocnn.forward(w, n_fg_class=21, bf16=True, **inp)
+    # concat feature [B*P,984] (bf16 storage) vs oracle feat
+    feat = m._wbufs[(B, 1000, cuda_device)]["feat"].float().cpu().numpy()
+    want = ref["feat"].transpose(0, 2, 1).reshape(B * 1000, 984)
+    err = np.abs(feat - want)
+    scale = np.abs(want).max()
+    assert err.max() <= 0.02 * scale, (err.max(), scale)
+    assert np.mean(err) <= 2e-3 * scale
+    # final poses: tight vs bf16-rounded oracle
+    np.testing.assert_allclose(rot, ref["rot"], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(conf, ref["conf"], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(trans, ref["trans"], rtol=0, atol=2e-2 * float(inp["pitch"].max()) * 8)
+    assert np.mean(np.abs(rot - ref["rot"])) < 2e-3
+    # bf16-level vs the reference's fp32 arithmetic
+    ref32 = ocnn.forward(w, n_fg_class=21, bf16=False, **inp)
+    assert np.mean(np.abs(rot - ref32["rot"])) < 1e-2
+    assert np.mean(np.abs(conf - ref32["conf"])) < 1e-2
+    # argmax-confidence pose (what the callers consume, demo.py:85 / evaluate.py:86)
+    k = conf.argmax(1)
+    k32 = ref32["conf"].argmax(1)
+    for b in range(B):
+        q, q32 = rot[b, k[b]], ref32["rot"][b, k[b]]
+        assert abs(abs(float(q @ q32)) - 1) < 5e-3
+        assert ref32["conf"][b, k[b]] >= ref32["conf"][b, k32[b]] - 2e-2
