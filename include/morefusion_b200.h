@@ -225,6 +225,11 @@ int mf_cnn_pack_s2d(const float* vox /*[B,C,D,D,D]*/, const float* hocc /*[B,V,C
                     int B, int C, int Cocc, int D, void* X /*bf16 s2d, borders pre-zeroed*/,
                     void* stream);
 int mf_gemm_bf16_simt(const GemmParams* p, void* stream);
+/* tcgen05/TMEM/TMA kernel; returns MF_E_UNSUPPORTED for shapes it does not cover (N % 32, N < 128,
+ * K < 64, unaligned views) -- the caller then uses mf_gemm_bf16_simt.  `workspace` holds fp32
+ * [M][N] partial sums when the launch splits K (few output tiles, long K). */
+size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N);
+int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes, void* stream);
 int mf_cnn_interp_cl(const void* grid_bf16, int s2d, const float* points /*[B,3,P]*/, int B,
                      int P, int C, int D, float divisor, void* feat_bf16, int ldf, int col_off,
                      void* stream);

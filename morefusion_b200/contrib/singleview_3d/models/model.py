@@ -96,6 +96,7 @@ class Model(torch.nn.Module):
         self._packed = None
         self._wbufs = {}
         self.use_tensor_cores = True
+        self.launch_log = []
 
     # ------------------------------------------------------------------ weights
     def load_reference_weights(self, weights):
@@ -175,14 +176,16 @@ class Model(torch.nn.Module):
               relu=1, out_mode=OUT_BF16, ldo=0, col_off=0):
         gp = GemmParams(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(out), M, N, K, mode,
                         lda, W.shape[1], Do, Ci8, relu, out_mode, ldo, col_off)
-        fn = L.mf_gemm_bf16_simt
-        if self.use_tensor_cores and hasattr(L, "mf_gemm_bf16_tc"):
-            rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.stream())
+        if self.use_tensor_cores:
+            ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(M, N), A.device)
+            rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.ptr(ws), ws.numel(), _lib.stream())
             if rc == 0:
+                self.launch_log.append(("tc", M, N, K))
                 return
-            if rc != -4:          # MF_E_UNSUPPORTED -> SIMT kernel handles the shape
+            if rc != -4:          # MF_E_UNSUPPORTED -> the SIMT kernel covers the shape
                 _lib.check(rc, "gemm_bf16_tc")
-        _lib.check(fn(ctypes.byref(gp), _lib.stream()), "gemm_bf16_simt")
+        self.launch_log.append(("simt", M, N, K))
+        _lib.check(L.mf_gemm_bf16_simt(ctypes.byref(gp), _lib.stream()), "gemm_bf16_simt")
 
     def forward_features(self, *, class_id, values, points, pitch, origin,
                          grid_nontarget_empty=None):

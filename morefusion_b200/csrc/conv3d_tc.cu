@@ -1,0 +1,440 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: the implicit-GEMM k4-s2 Conv3Ds (conv3, conv4) and the
+// Conv1D heads of the singleview_3d pose model.
+//
+// Replaces the cuDNN ConvolutionND calls behind
+//   morefusion/contrib/singleview_3d/models/model.py:73-74 (conv3, conv4), :77-91 (heads).
+//
+// out[m, n] = act( sum_k A(m,k) * W[n,k] + bias[n] )     bf16 operands, fp32 accumulation in TMEM.
+//
+// CTA tile 128 x BLOCK_N x 64.  Warp roles (one CTA per SM, 256 threads):
+//   warp 0  (1 lane)  TMA producer: per K block one box of A and one of W into a
+//                     SWIZZLE_128B smem stage, mbarrier expect_tx / complete_tx
+//   warp 1  (1 lane)  MMA issuer: 4 x tcgen05.mma (M128 x N x K16) per stage, tcgen05.commit
+//                     releases the stage; a final commit signals the epilogue
+//   warp 2            TMEM allocator (BLOCK_N fp32 columns)
+//   warps 4-7         epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias, ReLU, bf16
+//                     pack, 16-byte stores (row-major, or scattered into the space-to-depth
+//                     layout the next convolution's TMA boxes read)
+// For the convolutions the A operand needs no im2col: with the space-to-depth input layout
+// (cnn.cu) the 128 output voxels x 64 channels of one K block are ONE 5-D TMA box.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "cnn.cuh"
+#include "common.cuh"
+
+namespace mf {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KiB
+
+struct TcExtra {
+  int kb_per_a;      // conv: K blocks per kernel-offset a (= Ci8 / 64)
+  int kb_total;      // K blocks overall
+  int kb_per_split;  // K blocks per grid.z slice
+  int splitk;
+  float* ws;         // fp32 [M][N] partial sums when splitk > 1
+  int* err;          // device error word (pipeline time-out), may be null
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline must not hang the GPU (traps after ~2 s)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=1024>>4)
+//  | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ long long out_row_offset(const GemmParams& p, int m) {
+  if (p.out_mode != OUT_S2D_BF16) return (long long)m * p.ldo + p.col_off;
+  int Do = p.Do, J = Do / 2 + 1;
+  int ow = m % Do, oh = (m / Do) % Do, od = (m / (Do * Do)) % Do, b = m / (Do * Do * Do);
+  int pd = od + 1, ph = oh + 1, pw = ow + 1;
+  int r = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+  return ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * p.N) +
+         (long long)r * p.N;
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          const GemmParams p, const TcExtra e) {
+  constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_dyn[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * TC_BLOCK_M;
+  const int kb0 = blockIdx.z * e.kb_per_split;
+  const int kb1 = min(kb0 + e.kb_per_split, e.kb_total);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)BLOCK_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer
+    int cb = 0, cw = 0, ch = 0, cd = 0;
+    if (p.mode == GEMM_CONV_S2D) {
+      int Do = p.Do;
+      cw = m0 % Do;                       // 0 for Do in {8,16}: tiles start at ow = 0
+      ch = (m0 / Do) % Do;
+      cd = (m0 / (Do * Do)) % Do;
+      cb = m0 / (Do * Do * Do);
+    }
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1, e.err, 1);
+      mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+      unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+      unsigned char* sb = sa + TC_A_BYTES;
+      const int kb = kb0 + i;
+      if (p.mode == GEMM_CONV_S2D) {
+        int a = kb / e.kb_per_a, c = (kb - a * e.kb_per_a) * TC_BLOCK_K;
+        tma_load_5d(sa, &tmA, &full_bar[s], c, cw + (a & 1), ch + ((a >> 1) & 1),
+                    cd + ((a >> 2) & 1), cb);
+      } else {
+        tma_load_2d(sa, &tmA, &full_bar[s], kb * TC_BLOCK_K, m0);
+      }
+      tma_load_2d(sb, &tmW, &full_bar[s], kb * TC_BLOCK_K, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1,
+    // b=BF16 [10,13)=1, K-major both (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph, e.err, 2);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+      const uint64_t adesc = make_sw128_desc(sa);
+      const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+      for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+        // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in addr>>4 units
+        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                  (i > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+    }
+    umma_commit(&tmem_full_bar);    // accumulator complete
+  } else if (warp >= 4) {
+    // ===== epilogue
+    mbar_wait(&tmem_full_bar, 0, e.err, 3);
+    tcgen05_fence_after();
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    const long long roff = row_ok ? out_row_offset(p, m) : 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      const int n = n0 + c0;
+      if (!row_ok || n >= p.N) continue;            // N % 32 == 0 is enforced on the host
+      if (e.splitk > 1) {
+        float* dst = e.ws + (long long)m * p.N + n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+        continue;
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+        v[j] = p.relu ? fmaxf(x, 0.f) : x;
+      }
+      if (p.out_mode == OUT_F32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + roff + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          dst[j] = u;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)BLOCK_N)
+                 : "memory");
+  }
+}
+
+// split-K epilogue: bias + activation + layout on the reduced fp32 sums
+__global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.M * p.N) return;
+  int m = (int)(i / p.N), n = (int)(i % p.N);
+  float v = ws[i] + (p.bias ? p.bias[n] : 0.f);
+  if (p.relu) v = fmaxf(v, 0.f);
+  long long off = out_row_offset(p, m) + n;
+  if (p.out_mode == OUT_F32) reinterpret_cast<float*>(p.out)[off] = v;
+  else reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  PFN_encodeTiled fn = get_encode();
+  if (!fn) return MF_E_UNSUPPORTED;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MF_OK : MF_E_BADARG;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p,
+                  const TcExtra& e, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  k_gemm_tc<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(tmA, tmW, p, e);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N) {
+  return (size_t)M * N * 4 + 256;
+}
+
+extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!hp) return MF_E_BADARG;
+  GemmParams p = *hp;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
+  // shapes this kernel family covers; everything else goes to the SIMT kernel
+  if (p.N % 32 != 0 || p.N < 128 || p.K < 64 || p.K % 8 != 0 || p.ldw % 8 != 0)
+    return MF_E_UNSUPPORTED;
+  if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15) || ((uintptr_t)p.out & 15))
+    return MF_E_UNSUPPORTED;
+  if (p.out_mode != OUT_S2D_BF16 && ((p.ldo % 8) || (p.col_off % 8))) return MF_E_UNSUPPORTED;
+  const int BN = (p.N % 256 == 0) ? 256 : 128;
+  TcExtra e{};
+  e.kb_total = (p.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  CUtensorMap tmA, tmW;
+  int rc;
+  if (p.mode == GEMM_CONV_S2D) {
+    const int Do = p.Do, Js = Do + 1;
+    if (!(Do == 8 || Do == 16) || p.Ci8 % 64 != 0 || p.K != 8 * p.Ci8) return MF_E_UNSUPPORTED;
+    if (p.M % (Do * Do * Do) != 0) return MF_E_UNSUPPORTED;
+    const int Bn = p.M / (Do * Do * Do);
+    e.kb_per_a = p.Ci8 / 64;
+    cuuint64_t dims[5] = {(cuuint64_t)p.Ci8, (cuuint64_t)Js, (cuuint64_t)Js, (cuuint64_t)Js,
+                          (cuuint64_t)Bn};
+    cuuint64_t str[4] = {(cuuint64_t)p.Ci8 * 2, (cuuint64_t)Js * p.Ci8 * 2,
+                         (cuuint64_t)Js * Js * p.Ci8 * 2, (cuuint64_t)Js * Js * Js * p.Ci8 * 2};
+    // 128 consecutive output voxels (w fastest): 16x8x1 for Do=16, 8x8x2 for Do=8
+    cuuint32_t box[5] = {64, (cuuint32_t)Do, 8, (cuuint32_t)(Do == 16 ? 1 : 2), 1};
+    rc = encode(&tmA, p.A, 5, dims, str, box);
+  } else {
+    if (p.lda % 8 != 0) return MF_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+    cuuint64_t str[1] = {(cuuint64_t)p.lda * 2};
+    cuuint32_t box[2] = {64, 128};
+    rc = encode(&tmA, p.A, 2, dims, str, box);
+  }
+  if (rc) return rc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
+    cuuint64_t str[1] = {(cuuint64_t)p.ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    rc = encode(&tmW, p.W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  const int m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (p.N + BN - 1) / BN;
+  int splitk = 1;
+  const int tiles = m_tiles * n_tiles;
+  if (tiles <= 74 && e.kb_total >= 64) {
+    splitk = 148 / tiles;
+    if (splitk > 4) splitk = 4;
+    if (splitk < 1) splitk = 1;
+  }
+  e.kb_per_split = (e.kb_total + splitk - 1) / splitk;
+  splitk = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
+  e.splitk = splitk;
+  e.err = nullptr;
+  if (splitk > 1) {
+    if (!workspace || workspace_bytes < (size_t)p.M * p.N * 4) return MF_E_WORKSPACE;
+    e.ws = (float*)workspace;
+    MF_CUDA_TRY(cudaMemsetAsync(e.ws, 0, (size_t)p.M * p.N * 4, stream));
+  }
+  dim3 grid(n_tiles, m_tiles, splitk);
+  if (BN == 256) rc = launch<256, 4>(tmA, tmW, p, e, grid, stream);
+  else rc = launch<128, 6>(tmA, tmW, p, e, grid, stream);
+  if (rc) return rc;
+  if (splitk > 1) {
+    k_splitk_finish<<<div_up((long long)p.M * p.N, 256), 256, 0, stream>>>(e.ws, p);
+    MF_LAUNCH_CHECK();
+  }
+  return MF_OK;
+}

@@ -1,0 +1,84 @@
+"""GPU: tcgen05 GEMM kernel vs torch fp32 reference of the same op (bf16 operands, fp32
+accumulate) and vs the SIMT kernel, for the linear (heads) and implicit-conv (s2d) modes."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _call(kind, A, W, bias, out, M, N, K, **kw):
+    from morefusion_b200 import _lib
+    from morefusion_b200.contrib.singleview_3d.models.model import GemmParams
+    from morefusion_b200.functions.geometry import _util
+    L = _lib.lib()
+    gp = GemmParams(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(out), M, N, K,
+                    kw.get("mode", 0), kw.get("lda", 0), W.shape[1], kw.get("Do", 0),
+                    kw.get("Ci8", 0), kw.get("relu", 1), kw.get("out_mode", 0), kw.get("ldo", N),
+                    kw.get("col_off", 0))
+    if kind == "tc":
+        ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(M, N), A.device)
+        rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.ptr(ws), ws.numel(), _lib.stream())
+    else:
+        rc = L.mf_gemm_bf16_simt(ctypes.byref(gp), _lib.stream())
+    torch.cuda.synchronize()
+    return rc
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (8000, 1920, 984),
+                                   (8000, 256, 640), (1000, 128, 256), (4096, 512, 2048)])
+def test_tc_linear(cuda_device, M, N, K):
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=cuda_device).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=cuda_device) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda_device)
+    out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    rc = _call("tc", A, W, bias, out, M, N, K, lda=K)
+    assert rc == 0
+    ref = torch.relu(A.float() @ W.float().T + bias)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+    # fp32 output, no relu
+    out32 = torch.zeros(M, N, device=cuda_device)
+    rc = _call("tc", A, W, bias, out32, M, N, K, lda=K, relu=0, out_mode=1)
+    assert rc == 0
+    ref = A.float() @ W.float().T + bias
+    torch.testing.assert_close(out32, ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("Do,Ci,Co,B", [(16, 160, 256, 2), (8, 256, 512, 2), (8, 256, 512, 8)])
+def test_tc_conv_s2d(cuda_device, Do, Ci, Co, B):
+    """conv k4 s2 p1 through the s2d implicit GEMM == torch conv3d on the same bf16 operands."""
+    from morefusion_b200.contrib.singleview_3d.models.model import pack_conv_k4s2_weight
+    torch.manual_seed(1)
+    D = 2 * Do
+    x = torch.randn(B, Ci, D, D, D, device=cuda_device).to(torch.bfloat16)
+    Wc = (torch.randn(Co, Ci, 4, 4, 4, device=cuda_device) / (Ci * 64) ** 0.5)
+    bias = torch.randn(Co, device=cuda_device)
+    # s2d layout of the zero-padded input
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1, 1, 1))
+    J = Do + 1
+    X = xp.reshape(B, Ci, J, 2, J, 2, J, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J, J, J, 8 * Ci).contiguous()
+    Wg = pack_conv_k4s2_weight(Wc)
+    M, N, K = B * Do ** 3, Co, 64 * Ci
+    ref = torch.relu(torch.nn.functional.conv3d(x.float(), Wc.to(torch.bfloat16).float(), bias, stride=2, padding=1))
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(M, N)
+    for kind in ("simt", "tc"):
+        out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+        rc = _call(kind, X, Wg, bias, out, M, N, K, mode=1, Do=Do, Ci8=8 * Ci)
+        assert rc == 0, kind
+        err = (out.float() - ref).abs().max().item()
+        assert err <= 2e-2 * max(1.0, ref.abs().max().item()), (kind, err)
+    # s2d output mode (conv3 -> conv4 input): compare with the row-major result re-laid out
+    if Do == 16:
+        J2 = Do // 2 + 1
+        out2 = torch.zeros(B, J2, J2, J2, 8 * N, device=cuda_device, dtype=torch.bfloat16)
+        rc = _call("tc", X, Wg, bias, out2, M, N, K, mode=1, Do=Do, Ci8=8 * Ci, out_mode=2)
+        assert rc == 0
+        h = out.reshape(B, Do, Do, Do, N).permute(0, 4, 1, 2, 3)
+        hp = torch.nn.functional.pad(h, (1, 1, 1, 1, 1, 1))
+        want = hp.reshape(B, N, J2, 2, J2, 2, J2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J2, J2, J2, 8 * N)
+        assert torch.equal(out2, want.contiguous())
