@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MoreFusion volumetric-pose hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU cores
+
+Metric (BASELINE.json): objects/sec, volumetric pose (32^3).  Workload at every N:
+BASELINE config[1] "singleview_3d inference, 32^3 occupancy 3D-CNN, batch=8 objects" -- one
+step = one pass of the hot path (per-point MLP -> average_voxelization_3d 32^3 -> occupancy
+stencils -> conv3/conv4 -> trilinear gathers -> 3 pose heads -> per-point poses) over a batch
+of 8 synthetic YCB-shaped objects x 1000 points per rank (weak scaling: objects are
+independent, no data-path collective).  The 2-D ResNet18/PSPNet extractor is the
+adjacent "next" row: its 32-channel per-point output is the synthetic input.
+
+Printed JSON (one line, rank 0): value = device-resident throughput; e2e = same metric through
+the public Runner API with pinned HOST buffers in and out (H2D + D2H inside the timed region);
+roofline = conv3 tcgen05 implicit GEMM (dense algorithmic FLOPs / CUDA-event duration measured
+inside the timed steps) against the measured bf16 peak; cpu_baseline = the oracle port of the
+same path timed on this box's host cores on a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_PER_RANK = 8
+P = 1000
+METRIC = "objects/sec volumetric pose (32^3)"
+WORKLOAD = "singleview_3d inference hot path: 3D-CNN over 32^3 grid, batch=8 objects x 1000 pts per GPU"
+CONV3_FLOPS_PER_OBJECT = 2.0 * 4096 * 256 * (160 * 64)     # 21.47 GFLOP
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_port_step(weights, batch, n_obj):
+    from oracle import cnn as ocnn
+    sub = {k: v[:n_obj] for k, v in batch.items()}
+    t0 = time.perf_counter()
+    ocnn.forward(weights, n_fg_class=21, bf16=False, **sub)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """The reference's algorithm for this path on the host CPU cores.  The reference's own code
+    cannot run here (chainer/cupy absent) so this is the oracle port
+    (kind="port"): torch-CPU fp32 convs + the NumPy restatements of the reference kernels."""
+    if rank != 0:
+        return
+    from morefusion_b200 import synthetic
+    from oracle import cnn as ocnn
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    weights = ocnn.init_weights(21, seed=1)
+    n_obj = 2                                       # bounded sample per step
+    batch = synthetic.make_cnn_batch(B_PER_RANK, P, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_step(weights, batch, n_obj)
+    ts = [cpu_port_step(weights, batch, n_obj) for _ in range(args.steps)]
+    total = sum(ts)
+    value = n_obj * args.steps / total
+    line = dict(
+        impl="reference", metric=METRIC, value=value, unit="objects/s", n_gpus=args.gpus,
+        steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps,
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=WORKLOAD, sample=f"{n_obj} of the {B_PER_RANK} objects per step"),
+        cpu_baseline=dict(value=value, unit="objects/s", cores=threads, kind="port",
+                          sample=f"{n_obj} objects x {args.steps} steps, torch-CPU fp32 + NumPy oracle"),
+        e2e=dict(value=value, unit="objects/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local):
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; no CPU fallback"
+    import morefusion_b200 as mf
+    from morefusion_b200 import synthetic
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    from oracle import cnn as ocnn          # weights initialiser + cpu_baseline leg only
+    mf.config.check_nan = False
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pk = peaks()
+
+    weights = ocnn.init_weights(21, seed=1)
+    model = Model(n_fg_class=21, with_occupancy=True).to(dev).load_reference_weights(weights)
+    runner = model.make_runner(B_PER_RANK, P, dev, graph=not args.no_graph)
+    n_sets = 4                                       # rotate input batches
+    batches = [synthetic.make_cnn_batch(B_PER_RANK, P, seed=100 * rank + i) for i in range(n_sets)]
+    dev_sets = []
+    for b in batches:
+        runner.load_host(b)
+        torch.cuda.synchronize()
+        dev_sets.append({k: v.clone() for k, v in runner.st.items()})
+    pinned_sets = []
+    for b in batches:
+        runner.load_host(b)
+        pinned_sets.append({k: v.clone().pin_memory() for k, v in runner.host_in.items()})
+    torch.cuda.synchronize()
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def set_inputs(i):
+        for k, v in dev_sets[i % n_sets].items():
+            runner.st[k].copy_(v)
+
+    # ---- device-resident throughput
+    for i in range(max(args.warmup, 3)):
+        set_inputs(i)
+        runner.run()
+    torch.cuda.synchronize()
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    n0 = model.n_launches
+    for i in range(K):
+        set_inputs(i)
+        flush.zero_()                     # L2 flush between timed iterations (untimed)
+        runner.set_events(*cev[i])
+        ev[i][0].record()
+        runner.run()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    barrier(world)
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    conv3_ms = [a.elapsed_time(b) for a, b in cev]
+    total_ms = max_over_ranks(sum(step_ms), world, dev)
+    launches = runner.launches_per_step * K if runner.graphs is not None else model.n_launches - n0
+    runner.ev = None
+    value = world * B_PER_RANK * K / (total_ms * 1e-3)
+
+    # ---- end to end: pinned host buffers in, pinned host poses out, copies inside the timing
+    for i in range(3):
+        for k, v in pinned_sets[i % n_sets].items():
+            runner.host_in[k].copy_(v)
+        runner.upload(); runner.run(); runner.download()
+    torch.cuda.synchronize()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier(world)
+    torch.cuda.synchronize()
+    for i in range(K):
+        src = pinned_sets[i % n_sets]
+        flush.zero_()
+        ev2[i][0].record()
+        for k in runner.st:
+            runner.st[k].copy_(src[k], non_blocking=True)     # H2D from pinned memory
+        runner.run()
+        runner.download()                                      # D2H of rot/trans/conf
+        ev2[i][1].record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev2), world, dev)
+    e2e_value = world * B_PER_RANK * K / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (conv3 tcgen05 implicit GEMM)
+    conv3_avg_ms = float(np.mean(conv3_ms))
+    flops = CONV3_FLOPS_PER_OBJECT * B_PER_RANK
+    achieved = flops / (conv3_avg_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_conv3_ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = dict(bound="tensor", kernel="k_gemm_tc<256,4> (conv3 160->256 k4 s2, implicit GEMM M=32768 N=256 K=10240)",
+                achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                frac=achieved / pk["bf16_sustained"], frac_of_burst_peak=achieved / pk["bf16"],
+                peak_source=pk["source"] + ", sustained figure (kernel timed inside the step)",
+                avg_launch_us=conv3_avg_ms * 1e3, share_of_step=conv3_avg_ms / float(np.mean(step_ms)),
+                traffic=traffic)
+    # ---- CPU baseline: oracle port on the host cores, bounded sample
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_obj = 2
+    cpu_port_step(weights, batches[0], 1)
+    reps, t_cpu = 0, 0.0
+    while t_cpu < 8.0 and reps < 6:
+        t_cpu += cpu_port_step(weights, batches[0], n_obj)
+        reps += 1
+    cpu = dict(value=n_obj * reps / t_cpu, unit="objects/s", cores=threads, kind="port",
+               sample=f"{n_obj} objects x {reps} passes of the oracle port (torch-CPU fp32 convs + NumPy kernels)")
+    line = dict(
+        metric=METRIC, value=value, unit="objects/s", n_gpus=world, steps=K, warmup=max(args.warmup, 3),
+        ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="bf16", data="synthetic",
+        config=dict(workload=WORKLOAD, objects_per_gpu_per_step=B_PER_RANK, points_per_object=P,
+                    voxel_dim=32, n_fg_class=21, parallelism=f"objects sharded over {world} GPU(s), no collective",
+                    cuda_graph=runner.graphs is not None,
+                    l2="192 MiB buffer written between timed iterations (untimed); 4 rotating input sets"),
+        e2e=dict(value=e2e_value, unit="objects/s", h2d_bytes_per_step=runner.h2d_bytes,
+                 d2h_bytes_per_step=runner.d2h_bytes, ms_per_step=e2e_ms / K),
+        gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # host-CPU arm: rank 0 alone works; other ranks exit 0 without joining any group
+        run_reference(args, int(os.environ.get("RANK", "0")), 1)
+        return
+    rank, world, local = dist_setup(args.gpus)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,10 @@ namespace mf {
 using bf16 = __nv_bfloat16;
 
 // ------------------------------------------------------------------ per-point MLP
-constexpr int kMlpPts = 16;
+// 64 points per CTA; weights staged transposed in shared memory ([k][oc]) so that lanes
+// (consecutive oc) read consecutive words and the activations are warp broadcasts.
+constexpr int kMlpPts = 64;
+constexpr int kMlpSmemFloats = 32 * 64 + 3 * 8 + 64 * 128 + 8 * 16 + 72 + 144 + kMlpPts * 36 + kMlpPts * 73;
 
 __global__ void __launch_bounds__(256)
 k_point_mlp(const float* __restrict__ values,  // [B,32,P]
@@ -36,54 +39,60 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
             const float* __restrict__ w2p, const float* __restrict__ b2p,   // [16,8]
             int B, int P, float center, bf16* __restrict__ feat, int ldf,
             float* __restrict__ feat2) {
-  __shared__ float xin[kMlpPts][36];
-  __shared__ float h1[kMlpPts][73];
+  extern __shared__ float sm[];
+  float* t1r = sm;                 // [32][64]
+  float* t1p = t1r + 32 * 64;      // [3][8]
+  float* t2r = t1p + 3 * 8;        // [64][128]
+  float* t2p = t2r + 64 * 128;     // [8][16]
+  float* bb1 = t2p + 8 * 16;       // [72]
+  float* bb2 = bb1 + 72;           // [144]
+  float* xin = bb2 + 144;          // [kMlpPts][36]
+  float* h1 = xin + kMlpPts * 36;  // [kMlpPts][73]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * 32; e += 256) t1r[(e % 32) * 64 + e / 32] = w1r[e];
+  for (int e = tid; e < 8 * 3; e += 256) t1p[(e % 3) * 8 + e / 3] = w1p[e];
+  for (int e = tid; e < 128 * 64; e += 256) t2r[(e % 64) * 128 + e / 64] = w2r[e];
+  for (int e = tid; e < 16 * 8; e += 256) t2p[(e % 8) * 16 + e / 8] = w2p[e];
+  for (int e = tid; e < 72; e += 256) bb1[e] = e < 64 ? b1r[e] : b1p[e - 64];
+  for (int e = tid; e < 144; e += 256) bb2[e] = e < 128 ? b2r[e] : b2p[e - 128];
   const long long n0 = (long long)blockIdx.x * kMlpPts;
   const long long NP = (long long)B * P;
-  for (int e = threadIdx.x; e < kMlpPts * 35; e += blockDim.x) {
-    int pt = e / 35, c = e % 35;
+  for (int e = tid; e < kMlpPts * 35; e += 256) {
+    int c = e / kMlpPts, pt = e % kMlpPts;      // pt fastest: coalesced along P
     long long n = n0 + pt;
     float v = 0.f;
     if (n < NP) {
       long long b = n / P, p = n % P;
       v = (c < 32) ? values[(b * 32 + c) * P + p] : (center - points[(b * 3 + (c - 32)) * P + p]);
     }
-    xin[pt][c] = v;
+    xin[pt * 36 + c] = v;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < kMlpPts * 72; e += blockDim.x) {
+  for (int e = tid; e < kMlpPts * 72; e += 256) {
     int pt = e / 72, oc = e % 72;
-    float acc;
+    float acc = bb1[oc];
     if (oc < 64) {
-      acc = b1r[oc];
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(w1r + oc * 32 + k), xin[pt][k], acc);
+      for (int k = 0; k < 32; ++k) acc = fmaf(t1r[k * 64 + oc], xin[pt * 36 + k], acc);
     } else {
-      int o = oc - 64;
-      acc = b1p[o];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) acc = fmaf(__ldg(w1p + o * 3 + k), xin[pt][32 + k], acc);
+      for (int k = 0; k < 3; ++k) acc = fmaf(t1p[k * 8 + oc - 64], xin[pt * 36 + 32 + k], acc);
     }
-    h1[pt][oc] = fmaxf(acc, 0.f);
+    acc = fmaxf(acc, 0.f);
+    h1[pt * 73 + oc] = acc;
+    long long n = n0 + pt;
+    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(acc);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < kMlpPts * 72; e += blockDim.x) {
-    int pt = e / 72, oc = e % 72;
-    long long n = n0 + pt;
-    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(h1[pt][oc]);
-  }
-  for (int e = threadIdx.x; e < kMlpPts * 144; e += blockDim.x) {
+  for (int e = tid; e < kMlpPts * 144; e += 256) {
     int pt = e / 144, oc = e % 144;
-    float acc;
+    float acc = bb2[oc];
     if (oc < 128) {
-      acc = b2r[oc];
 #pragma unroll 8
-      for (int k = 0; k < 64; ++k) acc = fmaf(__ldg(w2r + oc * 64 + k), h1[pt][k], acc);
+      for (int k = 0; k < 64; ++k) acc = fmaf(t2r[k * 128 + oc], h1[pt * 73 + k], acc);
     } else {
-      int o = oc - 128;
-      acc = b2p[o];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(w2p + o * 8 + k), h1[pt][64 + k], acc);
+      for (int k = 0; k < 8; ++k) acc = fmaf(t2p[k * 16 + oc - 128], h1[pt * 73 + 64 + k], acc);
     }
     acc = fmaxf(acc, 0.f);
     long long n = n0 + pt;
@@ -137,7 +146,7 @@ __global__ void k_occ_conv1(const float* __restrict__ gne, const float* __restri
 __global__ void k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
                             const float* __restrict__ bias, int B, int D,
                             float* __restrict__ h2) {
-  __shared__ float sw[27 * 8 * 16 + 16];   // [tap][ci][co]
+  __shared__ __align__(16) float sw[27 * 8 * 16 + 16];   // [tap][ci][co]
   for (int e = threadIdx.x; e < 16 * 8 * 27; e += blockDim.x) {
     int co = e / (8 * 27), r = e % (8 * 27), ci = r / 27, tap = r % 27;   // OIDHW
     sw[(tap * 8 + ci) * 16 + co] = w[e];
@@ -167,10 +176,17 @@ __global__ void k_occ_conv2(const float* __restrict__ h1, const float* __restric
         float in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         int tap = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
-        for (int ci = 0; ci < 8; ++ci)
+        for (int ci = 0; ci < 8; ++ci) {
+          const float4* wv = reinterpret_cast<const float4*>(sw + (tap * 8 + ci) * 16);
 #pragma unroll
-          for (int co = 0; co < 16; ++co)
-            acc[co] = fmaf(sw[(tap * 8 + ci) * 16 + co], in[ci], acc[co]);
+          for (int q = 0; q < 4; ++q) {
+            float4 ww = wv[q];            // one LDS.128 broadcast feeds 4 FMAs
+            acc[4 * q + 0] = fmaf(ww.x, in[ci], acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(ww.y, in[ci], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(ww.z, in[ci], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(ww.w, in[ci], acc[4 * q + 3]);
+          }
+        }
       }
     }
   }
@@ -312,11 +328,13 @@ template <bool kS2D>
 __global__ void k_interp_cl(const bf16* __restrict__ grid, const float* __restrict__ points,  // [B,3,P]
                             int B, int P, int C, int D, float divisor, bf16* __restrict__ feat,
                             int ldf, int col_off) {
+  // one thread per (point, 8 consecutive channels): 16-byte corner loads
+  const int C8 = C >> 3;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long NP = (long long)B * P;
-  if (i >= NP * C) return;
-  long long n = i / C;
-  int c = (int)(i - n * C);
+  if (i >= NP * C8) return;
+  long long n = i / C8;
+  int c = (int)(i - n * C8) * 8;
   long long b = n / P, pp = n % P;
   float x = __fdiv_rn(points[(b * 3 + 0) * P + pp], divisor);
   float y = __fdiv_rn(points[(b * 3 + 1) * P + pp], divisor);
@@ -329,7 +347,9 @@ __global__ void k_interp_cl(const bf16* __restrict__ grid, const float* __restri
   const int dx[8] = {0, 1, 0, 0, 1, 0, 1, 1};
   const int dy[8] = {0, 0, 1, 0, 1, 1, 0, 1};
   const int dz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
-  float acc = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   const int J = D / 2 + 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -344,9 +364,17 @@ __global__ void k_interp_cl(const bf16* __restrict__ grid, const float* __restri
     } else {
       src = (((b * D + ix) * D + iy) * D + iz) * (long long)C + c;
     }
-    acc = fmaf(w[j], __bfloat162float(grid[src]), acc);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(grid + src));
+    const bf16* h = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[j], __bfloat162float(h[k]), acc[k]);
   }
-  feat[n * ldf + col_off + c] = __float2bfloat16(acc);
+  uint4 o;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  *reinterpret_cast<uint4*>(feat + n * ldf + col_off + c) = o;
 }
 
 // ------------------------------------------------------------------ pose epilogue (model.py:256-273)
@@ -390,7 +418,13 @@ extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const 
       !feat || !feat2)
     return MF_E_BADARG;
   long long NP = (long long)B * P;
-  k_point_mlp<<<div_up(NP, kMlpPts), 256, 0, (cudaStream_t)stream_>>>(
+  static bool attr = false;
+  if (!attr) {
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_point_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kMlpSmemFloats * 4));
+    attr = true;
+  }
+  k_point_mlp<<<div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(
       values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat, ldf,
       feat2);
   MF_LAUNCH_CHECK();
@@ -445,7 +479,8 @@ extern "C" int mf_cnn_interp_cl(const void* grid, int s2d, const float* points, 
                                 int C, int D, float divisor, void* feat, int ldf, int col_off,
                                 void* stream_) {
   if (B <= 0 || P <= 0 || C <= 0 || D <= 0 || !grid || !points || !feat) return MF_E_BADARG;
-  long long tot = (long long)B * P * C;
+  if ((C & 7) || (ldf & 7) || (col_off & 7)) return MF_E_UNSUPPORTED;
+  long long tot = (long long)B * P * (C / 8);
   if (s2d)
     k_interp_cl<true><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
         (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);

@@ -1,0 +1,125 @@
+"""Synthetic YCB-shaped inputs for the volumetric-pose hot path (no datasets offline).
+
+Shapes and conventions follow the reference's data pipeline:
+  * 21 YCB classes, voxel pitch = bbox diagonal / 32 (datasets/ycb_video/models.py:113-115;
+    table ros/src/morefusion_ros/include/morefusion_ros/utils/data.h:12-32)
+  * origin = median(points) - pitch * 15.5 (model.py:197-205, rgbd_pose_estimation/base.py:153-156)
+  * 1000 points per object, voxel-frame points = (cam - origin) / pitch (model.py:236)
+  * grid_nontarget_empty: free space + other objects as seen from the camera (train.py:50-54)
+Objects are boxes / cylinders / spheres whose bbox diagonal is 32 * pitch(class).
+"""
+
+import numpy as np
+
+from .contrib.singleview_3d.models.model import YCB_VOXEL_PITCH_32
+
+F32 = np.float32
+
+
+def _rot(rs):
+    q = rs.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _primitive(class_id):
+    """kind, half-extents (metres) with bbox diagonal = 32 * pitch."""
+    diag = 32.0 * YCB_VOXEL_PITCH_32[class_id]
+    kind = ("box", "cylinder", "sphere")[class_id % 3]
+    if kind == "box":
+        ratio = np.array([1.0, 0.7, 0.45])
+    elif kind == "cylinder":
+        ratio = np.array([0.6, 0.6, 1.0])
+    else:
+        ratio = np.array([1.0, 1.0, 1.0])
+    half = ratio / np.linalg.norm(2 * ratio) * diag
+    return kind, half
+
+
+def sdf_primitive(kind, half, p):
+    """Signed distance, POSITIVE INSIDE (trimesh convention, datasets/ycb_video/models.py:77)."""
+    if kind == "sphere":
+        return half[0] - np.linalg.norm(p, axis=-1)
+    if kind == "box":
+        q = np.abs(p) - half
+        outside = np.linalg.norm(np.maximum(q, 0), axis=-1)
+        inside = np.minimum(q.max(axis=-1), 0)
+        return -(outside + inside)
+    # cylinder along z
+    dr = np.linalg.norm(p[..., :2], axis=-1) - half[0]
+    dz = np.abs(p[..., 2]) - half[2]
+    outside = np.linalg.norm(np.maximum(np.stack([dr, dz], -1), 0), axis=-1)
+    inside = np.minimum(np.maximum(dr, dz), 0)
+    return -(outside + inside)
+
+
+def surface_points(kind, half, n, rs):
+    """Uniform-ish points on the primitive's surface (object frame)."""
+    if kind == "sphere":
+        d = rs.normal(size=(n, 3))
+        return d / np.linalg.norm(d, axis=1, keepdims=True) * half[0]
+    if kind == "box":
+        p = rs.uniform(-1, 1, (n, 3)) * half
+        ax = rs.randint(0, 3, n)
+        p[np.arange(n), ax] = np.sign(rs.uniform(-1, 1, n)) * half[ax]
+        return p
+    th = rs.uniform(0, 2 * np.pi, n)
+    z = rs.uniform(-1, 1, n) * half[2]
+    p = np.stack([np.cos(th) * half[0], np.sin(th) * half[0], z], 1)
+    cap = rs.uniform(size=n) < 0.25
+    r = np.sqrt(rs.uniform(size=n)) * half[0]
+    p[cap] = np.stack([np.cos(th) * r, np.sin(th) * r, np.sign(rs.uniform(-1, 1, n)) * half[2]], 1)[cap]
+    return p
+
+
+def sdf_lattice(class_id):
+    """Stand-in for YCBVideoModels.get_sdf (models.py:66-79): interior lattice points at the
+    class pitch with their signed distance (positive inside)."""
+    kind, half = _primitive(class_id)
+    pitch = YCB_VOXEL_PITCH_32[class_id]
+    ax = [np.arange(-h, h + 1e-9, pitch) for h in half]
+    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    d = sdf_primitive(kind, half, g)
+    keep = d >= -0.5 * pitch
+    return g[keep].astype(F32), d[keep].astype(F32)
+
+
+def make_cnn_batch(B=8, P=1000, seed=0, D=32):
+    """One batch of objects for the 3D-CNN hot path (BASELINE config 2 shape)."""
+    rs = np.random.RandomState(seed)
+    class_id = ((np.arange(B) + seed) % 21 + 1).astype(np.int32)
+    values = rs.normal(0, 1, (B, 32, P)).astype(F32)      # stands in for PSPNet features
+    points = np.zeros((B, 3, P), F32)
+    pitch = np.zeros(B, F32)
+    origin = np.zeros((B, 3), F32)
+    gne = np.zeros((B, D, D, D), bool)
+    for i in range(B):
+        kind, half = _primitive(int(class_id[i]))
+        pitch[i] = YCB_VOXEL_PITCH_32[int(class_id[i])]
+        R = _rot(rs)
+        t = np.array([rs.uniform(-0.2, 0.2), rs.uniform(-0.15, 0.15), rs.uniform(0.5, 0.8)])
+        sp = surface_points(kind, half, 6 * P, rs)
+        cam = sp @ R.T + t
+        # visible side only: surface normal ~ (p - centre) facing the camera at the origin
+        vis = ((cam - t) * (-cam)).sum(1) > 0
+        cam = cam[vis]
+        cam = cam + rs.normal(0, 0.003, cam.shape) * (cam / np.linalg.norm(cam, axis=1, keepdims=True))
+        keep = rs.permutation(cam.shape[0])[:P]
+        if keep.shape[0] < P:
+            keep = np.r_[keep, rs.randint(0, cam.shape[0], P - keep.shape[0])]
+        cam = cam[keep].astype(F32)
+        origin[i] = (np.median(cam, axis=0) - pitch[i] * (D / 2.0 - 0.5)).astype(F32)
+        points[i] = ((cam - origin[i]) / pitch[i]).T
+        # free space in front of the surface along the viewing rays + a random occluder slab
+        ijk = np.stack(np.meshgrid(*(np.arange(D),) * 3, indexing="ij"), -1).astype(F32)
+        centres = ijk * pitch[i] + origin[i]
+        obj = (centres - t) @ R
+        inside = sdf_primitive(kind, half, obj) > 0
+        front = np.linalg.norm(centres, axis=-1) < np.linalg.norm(t) - 0.3 * half.max()
+        slab = np.abs(centres[..., 0] - (t[0] + half.max() * 1.2)) < 2 * pitch[i]
+        gne[i] = (front | slab) & ~inside
+    return dict(class_id=class_id, values=values, points=points, pitch=pitch, origin=origin,
+                grid_nontarget_empty=gne)
