@@ -238,6 +238,38 @@ int mf_cnn_pose(const float* out_rot, const float* out_trans, const float* out_c
                 const float* origin, int B, int P, int n_fg_class, float* rot /*[B,P,4]*/,
                 float* trans /*[B,P,3]*/, float* conf /*[B,P]*/, void* stream);
 
+/* ------------------------------------------------------------------------
+ * a8 / a9  IterativeCollisionCheckLink + its Adam loop, fused
+ *     replaces IterativeCollisionCheckLink.forward
+ *       (morefusion/contrib/iterative_collision_check_link.py:31-99), chainer's reverse pass
+ *       through it and chainer.optimizers.Adam.update as driven by
+ *       examples/ycb_video/pose_refinement/check_iterative_collision_check_link.py:44-79
+ * One persistent cooperative kernel runs all `n_iter` (<= 128 per call) iterations for a BATCH of
+ * independent scenes; scene s owns objects [scene_obj_off[s], scene_obj_off[s+1]) (<= 32 per
+ * scene) and `group_size` CTAs.  Points/sdf are concatenated over all objects (obj_pt_off);
+ * work tables: 256-point chunks (chunk_obj / chunk_start, grouped by scene via scene_chunk_off),
+ * scene_slot_off = prefix sums of N_s * C_s.  All tables are DEVICE int32 arrays.
+ *   update == 0 : one forward/backward, parameters untouched (loss_history, grads written)
+ *   update == 1 : Chainer-form Adam, m += (1-b1)(g-m); v += (1-b2)(g*g-v);
+ *                 p -= eta * alpha_t[it] * m / (sqrt(v) + eps); alpha_t given per iteration by the
+ *                 caller (HOST float arrays) for quaternion and translation separately.
+ * adam_state: device [m_q(N,4) | m_t(N,3) | v_q(N,4) | v_t(N,3)].  grads: device [N,7] = gq | gt
+ * of the last iteration.  loss_history: device [n_scenes, n_iter].
+ * ------------------------------------------------------------------------ */
+int mf_icc_max_group_size(int n_scenes);
+size_t mf_icc_workspace_bytes(int n_objects_total, int voxel_dim, int n_scenes, int group_size,
+                              int n_slots);
+int mf_icc_run(int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold,
+               float sdf_offset, const int32_t* scene_obj_off, const int32_t* obj_pt_off,
+               const int32_t* scene_chunk_off, const int32_t* chunk_obj,
+               const int32_t* chunk_start, const int32_t* scene_slot_off, int n_slots,
+               const float* points, const float* sdf, const float* pitch, const float* origin,
+               const float* grid_target, const float* grid_nontarget_empty, float* quaternion,
+               float* translation, float* adam_state, int n_iter, int update,
+               const float* alpha_q_host, const float* alpha_t_host, float beta1, float beta2,
+               float eps, float eta, float* loss_history, float* grads, int group_size,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,10 +25,10 @@ def _rot(rs):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
-def _primitive(class_id):
+def _primitive(class_id, kinds=("box", "cylinder", "sphere")):
     """kind, half-extents (metres) with bbox diagonal = 32 * pitch."""
     diag = 32.0 * YCB_VOXEL_PITCH_32[class_id]
-    kind = ("box", "cylinder", "sphere")[class_id % 3]
+    kind = kinds[class_id % len(kinds)]
     if kind == "box":
         ratio = np.array([1.0, 0.7, 0.45])
     elif kind == "cylinder":
@@ -75,10 +75,10 @@ def surface_points(kind, half, n, rs):
     return p
 
 
-def sdf_lattice(class_id):
+def sdf_lattice(class_id, kinds=("box", "cylinder", "sphere")):
     """Stand-in for YCBVideoModels.get_sdf (models.py:66-79): interior lattice points at the
     class pitch with their signed distance (positive inside)."""
-    kind, half = _primitive(class_id)
+    kind, half = _primitive(class_id, kinds)
     pitch = YCB_VOXEL_PITCH_32[class_id]
     ax = [np.arange(-h, h + 1e-9, pitch) for h in half]
     g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
@@ -123,3 +123,70 @@ def make_cnn_batch(B=8, P=1000, seed=0, D=32):
         gne[i] = (front | slab) & ~inside
     return dict(class_id=class_id, values=values, points=points, pitch=pitch, origin=origin,
                 grid_nontarget_empty=gne)
+
+
+def make_icc_scene(N=8, seed=0, D=32, t_noise=0.01, rot_noise_deg=10.0,
+                   kinds=("box", "cylinder", "sphere")):
+    """Synthetic stand-in for examples/ycb_video/pose_refinement/data (BASELINE config 4):
+    N YCB-shaped primitives resting in contact in a bin, SDF lattice points per object
+    (models.get_sdf stand-in), ground-truth poses, perturbed initial poses
+    (t ~ N(0, 1 cm), rotation ~ U(0, 10 deg)), per-object 32^3 target / non-target+empty grids."""
+    rs = np.random.RandomState(seed)
+    class_id = ((np.arange(N) * 5 + seed) % 21 + 1).astype(np.int32)
+    prims = [_primitive(int(c), kinds) for c in class_id]
+    # place objects on a jittered lattice so that neighbours touch
+    T_true = []
+    cols = int(np.ceil(np.sqrt(N)))
+    for i, (kind, half) in enumerate(prims):
+        R = _rot(rs)
+        r = float(np.linalg.norm(half))
+        cx = (i % cols - (cols - 1) / 2.0) * 0.085 + rs.uniform(-0.01, 0.01)
+        cy = (i // cols - (cols - 1) / 2.0) * 0.085 + rs.uniform(-0.01, 0.01)
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = [cx, cy, 0.7 + rs.uniform(-0.02, 0.02) + 0.0 * r]
+        T_true.append(T)
+    T_true = np.stack(T_true)
+    points, sdf, pitch, origin = [], [], [], []
+    for i, c in enumerate(class_id):
+        p, s = sdf_lattice(int(c), kinds)
+        points.append(p)
+        sdf.append(s)
+        pitch.append(YCB_VOXEL_PITCH_32[int(c)])
+        origin.append(T_true[i, :3, 3] - pitch[-1] * (D / 2.0 - 0.5))
+    pitch = np.array(pitch, F32)
+    origin = np.array(origin, F32)
+    gt_grid = np.zeros((N, D, D, D), F32)
+    gne = np.zeros((N, D, D, D), F32)
+    ijk = np.stack(np.meshgrid(*(np.arange(D),) * 3, indexing="ij"), -1).astype(np.float64)
+    for i in range(N):
+        centres = ijk * pitch[i] + origin[i]
+        d_all = []
+        for j, (kind, half) in enumerate(prims):
+            obj = (centres - T_true[j, :3, 3]) @ T_true[j, :3, :3]
+            d_all.append(sdf_primitive(kind, half, obj))
+        d_all = np.stack(d_all)
+        d_self = d_all[i]
+        # visible (camera-facing) surface shell of object i
+        normal_out = centres - T_true[i, :3, 3]
+        facing = (normal_out * (-centres)).sum(-1) > 0
+        gt_grid[i] = ((np.abs(d_self) < 0.75 * pitch[i]) & facing)
+        others = np.delete(d_all, i, 0).max(0) > 0 if N > 1 else np.zeros_like(d_self, bool)
+        free = (d_all.max(0) < -1.5 * pitch[i]) & (centres[..., 2] < T_true[i, 2, 3])
+        gne[i] = (others | free) & ~(d_self > 0)
+    # perturbed initial poses
+    T_init = []
+    for i in range(N):
+        ax = rs.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = np.deg2rad(rs.uniform(0, rot_noise_deg))
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        dR = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        T = T_true[i].copy()
+        T[:3, :3] = T[:3, :3] @ dR
+        T[:3, 3] += rs.normal(0, t_noise, 3)
+        T_init.append(T)
+    return dict(class_id=class_id, points=points, sdf=sdf, pitch=pitch, origin=origin,
+                grid_target=gt_grid, grid_nontarget_empty=gne,
+                transform_init=np.stack(T_init).astype(F32), transform_true=T_true.astype(F32),
+                primitives=prims)
