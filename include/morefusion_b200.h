@@ -212,15 +212,24 @@ typedef struct GemmParams {
   int col_off;
 } GemmParams;
 
+/* weights are passed TRANSPOSED ([in][out], k-major): w1_rgb [32,64], w1_pcd [3,8], ... */
 int mf_cnn_point_mlp(const float* values /*[B,32,P]*/, const float* points /*[B,3,P] voxel frame*/,
                      const float* w1_rgb, const float* b1_rgb, const float* w1_pcd,
                      const float* b1_pcd, const float* w2_rgb, const float* b2_rgb,
                      const float* w2_pcd, const float* b2_pcd, int B, int P, float center,
                      void* feat_bf16 /*[B*P, ldf], cols 0..215*/, int ldf,
                      float* feat2 /*[B*P,144]*/, void* stream);
+/* conv2's output goes to h2 (fp32 [B,V,16]) or, when X != NULL, as bf16 into channels
+ * [c_off, c_off+16) of the s2d conv3 input X (row length 8*Ct). */
 int mf_cnn_occ_convs(const float* grid_nontarget_empty /*[B,D,D,D]*/, const float* w1,
                      const float* b1, const float* w2, const float* b2, int B, int D,
-                     float* h1 /*[B,V,8] scratch*/, float* h2 /*[B,V,16]*/, void* stream);
+                     float* h1 /*[B,V,8] scratch*/, float* h2 /*[B,V,16] or NULL*/,
+                     void* X /*bf16 s2d or NULL*/, int Ct, int c_off, void* stream);
+/* average_voxelization_3d of model.py:143-164 (origin 0, pitch 1, D^3) fused with the s2d/bf16
+ * packing: writes channels [0,C) of X.  prev_keys [B*P] int32 (in/out, initialise to -1) holds
+ * the voxel keys of the previous call so that only those voxels are re-zeroed. */
+int mf_cnn_voxelize_s2d(const float* feat2 /*[B*P,C]*/, const float* points /*[B,3,P]*/, int B,
+                        int P, int C, int D, int Ct, int32_t* prev_keys, void* X, void* stream);
 int mf_cnn_pack_s2d(const float* vox /*[B,C,D,D,D]*/, const float* hocc /*[B,V,Cocc] or NULL*/,
                     int B, int C, int Cocc, int D, void* X /*bf16 s2d, borders pre-zeroed*/,
                     void* stream);

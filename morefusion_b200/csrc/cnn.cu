@@ -33,10 +33,10 @@ constexpr int kMlpSmemFloats = 32 * 64 + 3 * 8 + 64 * 128 + 8 * 16 + 72 + 144 + 
 __global__ void __launch_bounds__(256)
 k_point_mlp(const float* __restrict__ values,  // [B,32,P]
             const float* __restrict__ points,  // [B,3,P] voxel frame
-            const float* __restrict__ w1r, const float* __restrict__ b1r,   // [64,32]
-            const float* __restrict__ w1p, const float* __restrict__ b1p,   // [8,3]
-            const float* __restrict__ w2r, const float* __restrict__ b2r,   // [128,64]
-            const float* __restrict__ w2p, const float* __restrict__ b2p,   // [16,8]
+            const float* __restrict__ w1r, const float* __restrict__ b1r,   // [32,64] (k-major)
+            const float* __restrict__ w1p, const float* __restrict__ b1p,   // [3,8]
+            const float* __restrict__ w2r, const float* __restrict__ b2r,   // [64,128]
+            const float* __restrict__ w2p, const float* __restrict__ b2p,   // [8,16]
             int B, int P, float center, bf16* __restrict__ feat, int ldf,
             float* __restrict__ feat2) {
   extern __shared__ float sm[];
@@ -49,10 +49,13 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
   float* xin = bb2 + 144;          // [kMlpPts][36]
   float* h1 = xin + kMlpPts * 36;  // [kMlpPts][73]
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * 32; e += 256) t1r[(e % 32) * 64 + e / 32] = w1r[e];
-  for (int e = tid; e < 8 * 3; e += 256) t1p[(e % 3) * 8 + e / 3] = w1p[e];
-  for (int e = tid; e < 128 * 64; e += 256) t2r[(e % 64) * 128 + e / 64] = w2r[e];
-  for (int e = tid; e < 16 * 8; e += 256) t2p[(e % 8) * 16 + e / 8] = w2p[e];
+  // weights arrive pre-transposed ([k][oc], done once when the model packs its weights)
+  for (int e = tid; e < 64 * 32 / 4; e += 256)
+    reinterpret_cast<float4*>(t1r)[e] = __ldg(reinterpret_cast<const float4*>(w1r) + e);
+  for (int e = tid; e < 8 * 3; e += 256) t1p[e] = w1p[e];
+  for (int e = tid; e < 128 * 64 / 4; e += 256)
+    reinterpret_cast<float4*>(t2r)[e] = __ldg(reinterpret_cast<const float4*>(w2r) + e);
+  for (int e = tid; e < 16 * 8; e += 256) t2p[e] = w2p[e];
   for (int e = tid; e < 72; e += 256) bb1[e] = e < 64 ? b1r[e] : b1p[e - 64];
   for (int e = tid; e < 144; e += 256) bb2[e] = e < 128 ? b2r[e] : b2p[e - 128];
   const long long n0 = (long long)blockIdx.x * kMlpPts;
@@ -142,10 +145,15 @@ __global__ void k_occ_conv1(const float* __restrict__ gne, const float* __restri
   o[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
 }
 
-// conv2_occ: Conv3D(8->16, k3, s1, p2, dilate 2) + ReLU; output [B,V,16] fp32
-__global__ void k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
-                            const float* __restrict__ bias, int B, int D,
-                            float* __restrict__ h2) {
+// conv2_occ: Conv3D(8->16, k3, s1, p2, dilate 2) + ReLU.
+// One thread = 4 consecutive z voxels x 16 output channels (64 accumulators): every LDS.128 of
+// weights (4 output channels, warp broadcast) feeds 16 FMAs; inputs are 16-byte channel vectors.
+// Output: fp32 [B,V,16] (h2) or, if X != null, bf16 straight into channels [c_off, c_off+16) of
+// the s2d conv3 input.
+__global__ void __launch_bounds__(128)
+k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
+            const float* __restrict__ bias, int B, int D, float* __restrict__ h2,
+            bf16* __restrict__ X, int Ct, int c_off) {
   __shared__ __align__(16) float sw[27 * 8 * 16 + 16];   // [tap][ci][co]
   for (int e = threadIdx.x; e < 16 * 8 * 27; e += blockDim.x) {
     int co = e / (8 * 27), r = e % (8 * 27), ci = r / 27, tap = r % 27;   // OIDHW
@@ -153,48 +161,177 @@ __global__ void k_occ_conv2(const float* __restrict__ h1, const float* __restric
   }
   if (threadIdx.x < 16) sw[27 * 8 * 16 + threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
+  const int Dz4 = D / 4;
   long long V = (long long)D * D * D;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * V) return;
-  long long b = i / V, v = i % V;
-  int z = (int)(v % D), y = (int)((v / D) % D), x = (int)(v / ((long long)D * D));
-  float acc[16];
+  if (i >= (long long)B * D * D * Dz4) return;
+  int z0 = (int)(i % Dz4) * 4;
+  long long t = i / Dz4;
+  int y = (int)(t % D), x = (int)((t / D) % D);
+  long long b = t / ((long long)D * D);
+  float acc[4][16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = sw[27 * 8 * 16 + c];
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[v][c] = sw[27 * 8 * 16 + c];
   for (int kd = 0; kd < 3; ++kd) {
     int xx = x + 2 * (kd - 1);
     if (xx < 0 || xx >= D) continue;
     for (int kh = 0; kh < 3; ++kh) {
       int yy = y + 2 * (kh - 1);
       if (yy < 0 || yy >= D) continue;
+      const float* row = h1 + (b * V + ((long long)xx * D + yy) * D) * 8;
+      // z positions z0-2 .. z0+5 (8 of them) cover the 3 dilated taps of the 4 voxels
+      float in[8][8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        int zz = z0 - 2 + q;
+        if (zz >= 0 && zz < D) {
+          const float4* src = reinterpret_cast<const float4*>(row + (long long)zz * 8);
+          float4 lo = __ldg(src), hi = __ldg(src + 1);
+          in[q][0] = lo.x; in[q][1] = lo.y; in[q][2] = lo.z; in[q][3] = lo.w;
+          in[q][4] = hi.x; in[q][5] = hi.y; in[q][6] = hi.z; in[q][7] = hi.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) in[q][c] = 0.f;
+        }
+      }
+#pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        int zz = z + 2 * (kw - 1);
-        if (zz < 0 || zz >= D) continue;
-        const float4* src =
-            reinterpret_cast<const float4*>(h1 + (b * V + ((long long)xx * D + yy) * D + zz) * 8);
-        float4 lo = __ldg(src), hi = __ldg(src + 1);
-        float in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        int tap = (kd * 3 + kh) * 3 + kw;
+        const int tap = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
           const float4* wv = reinterpret_cast<const float4*>(sw + (tap * 8 + ci) * 16);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 ww = wv[q];            // one LDS.128 broadcast feeds 4 FMAs
-            acc[4 * q + 0] = fmaf(ww.x, in[ci], acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(ww.y, in[ci], acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(ww.z, in[ci], acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(ww.w, in[ci], acc[4 * q + 3]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float4 ww = wv[q4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              float a = in[v + 2 * kw][ci];          // voxel z0+v, tap offset 2*(kw-1)
+              acc[v][4 * q4 + 0] = fmaf(ww.x, a, acc[v][4 * q4 + 0]);
+              acc[v][4 * q4 + 1] = fmaf(ww.y, a, acc[v][4 * q4 + 1]);
+              acc[v][4 * q4 + 2] = fmaf(ww.z, a, acc[v][4 * q4 + 2]);
+              acc[v][4 * q4 + 3] = fmaf(ww.w, a, acc[v][4 * q4 + 3]);
+            }
           }
         }
       }
     }
   }
-  float4* o = reinterpret_cast<float4*>(h2 + i * 16);
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    o[q] = make_float4(fmaxf(acc[4 * q], 0.f), fmaxf(acc[4 * q + 1], 0.f),
-                       fmaxf(acc[4 * q + 2], 0.f), fmaxf(acc[4 * q + 3], 0.f));
+  for (int v = 0; v < 4; ++v) {
+    int z = z0 + v;
+    if (z >= D) break;
+    if (X) {
+      const int J = D / 2 + 1;
+      int pd = x + 1, ph = y + 1, pw = z + 1;
+      int r = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+      long long dst = ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * Ct) +
+                      (long long)r * Ct + c_off;
+      uint4 o[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        h[c] = __floats2bfloat162_rn(fmaxf(acc[v][2 * c], 0.f), fmaxf(acc[v][2 * c + 1], 0.f));
+      uint4* d4 = reinterpret_cast<uint4*>(X + dst);
+      d4[0] = o[0];
+      d4[1] = o[1];
+    } else {
+      float4* o = reinterpret_cast<float4*>(h2 + (b * V + ((long long)x * D + y) * D + z) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o[q] = make_float4(fmaxf(acc[v][4 * q], 0.f), fmaxf(acc[v][4 * q + 1], 0.f),
+                           fmaxf(acc[v][4 * q + 2], 0.f), fmaxf(acc[v][4 * q + 3], 0.f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused voxelise -> s2d
+// Model path of average_voxelization_3d (model.py:143-164: origin 0, pitch 1, 32^3): the 144
+// averaged feature channels go straight into the bf16 s2d conv3 input.  The grid is >= 97 %
+// empty, so instead of rewriting 100 MB per call the kernel zeroes only the voxels the PREVIOUS
+// call wrote (keys kept in `prev_keys`) and then writes the new ones.  Same arithmetic as
+// k_avg_tiles: per-voxel fp32 sums in ascending point order, IEEE divide, then bf16 rounding.
+__device__ __forceinline__ long long s2d_voxel_offset(int b, int flat, int D, int Ct) {
+  const int J = D / 2 + 1;
+  int iz = flat % D, iy = (flat / D) % D, ix = flat / (D * D);
+  int pd = ix + 1, ph = iy + 1, pw = iz + 1;
+  int r = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+  return ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * Ct) +
+         (long long)r * Ct;
+}
+
+// one warp per point of the previous call: zero its voxel's C channels
+__global__ void k_s2d_clear(const int* __restrict__ prev_keys, int N, int C, int D, int Ct,
+                            bf16* __restrict__ X) {
+  int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  int key = prev_keys[n];
+  if (key < 0) return;
+  const int V = D * D * D;
+  bf16* dst = X + s2d_voxel_offset(key / V, key % V, D, Ct);
+  for (int c = lane * 2; c < C; c += 64)
+    *reinterpret_cast<uint32_t*>(dst + c) = 0u;
+}
+
+__global__ void k_s2d_keys(const float* __restrict__ points /*[B,3,P]*/, int B, int P, int D,
+                           int* __restrict__ keys) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B * P) return;
+  int b = n / P, p = n % P;
+  int ix = static_cast<int>(roundf(points[(b * 3 + 0) * P + p]));   // (p - 0) / 1.0
+  int iy = static_cast<int>(roundf(points[(b * 3 + 1) * P + p]));
+  int iz = static_cast<int>(roundf(points[(b * 3 + 2) * P + p]));
+  bool ok = ix >= 0 && ix < D && iy >= 0 && iy < D && iz >= 0 && iz < D;
+  keys[n] = ok ? b * D * D * D + (ix * D + iy) * D + iz : -1;
+}
+
+// one warp per point: the lowest-index point of a voxel ("leader") sums the voxel's points in
+// ascending order, lanes over channels, and writes the averaged bf16 row
+__global__ void __launch_bounds__(256)
+k_s2d_scatter(const float* __restrict__ feat2 /*[N,C]*/, const int* __restrict__ keys, int B,
+              int P, int C, int D, int Ct, bf16* __restrict__ X) {
+  int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (n >= B * P) return;
+  const int key = keys[n];
+  if (key < 0) return;
+  const int b = n / P, lo = b * P, hi = lo + P;
+  // leader test: any earlier point of this object with the same key?
+  bool earlier = false;
+  for (int j0 = lo; j0 < n && !earlier; j0 += 32) {
+    int j = j0 + lane;
+    bool m = (j < n) && (keys[j] == key);
+    earlier = __any_sync(0xffffffffu, m);
+  }
+  if (earlier) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  int count = 0;
+  for (int j0 = n - (n - lo) % 32; j0 < hi; j0 += 32) {     // chunks aligned so that j ascends
+    int j = j0 + lane;
+    bool m = (j >= n) && (j < hi) && (keys[j] == key);
+    unsigned mask = __ballot_sync(0xffffffffu, m);
+    while (mask) {
+      int l = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float* src = feat2 + (long long)(j0 + l) * C;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = lane + 32 * k;
+        if (c < C) acc[k] = __fadd_rn(acc[k], __ldg(src + c));
+      }
+      ++count;
+    }
+  }
+  const int V = D * D * D;
+  bf16* dst = X + s2d_voxel_offset(b, key % V, D, Ct);
+  const float cf = (float)count;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = lane + 32 * k;
+    if (c < C) dst[c] = __float2bfloat16(__fdiv_rn(acc[k], cf));
+  }
 }
 
 // ------------------------------------------------------------------ s2d packing
@@ -433,13 +570,33 @@ extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const 
 
 extern "C" int mf_cnn_occ_convs(const float* gne, const float* w1, const float* b1,
                                 const float* w2, const float* b2, int B, int D, float* h1,
-                                float* h2, void* stream_) {
+                                float* h2, void* X, int Ct, int c_off, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (B <= 0 || D <= 0 || !gne || !w1 || !b1 || !w2 || !b2 || !h1 || !h2) return MF_E_BADARG;
+  if (B <= 0 || D <= 0 || (D & 3) || !gne || !w1 || !b1 || !w2 || !b2 || !h1) return MF_E_BADARG;
+  if (!h2 && !X) return MF_E_BADARG;
+  if (X && ((Ct & 7) || (c_off & 7) || c_off + 16 > Ct)) return MF_E_BADARG;
   long long BV = (long long)B * D * D * D;
   k_occ_conv1<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, h1);
   MF_LAUNCH_CHECK();
-  k_occ_conv2<<<div_up(BV, 128), 128, 0, stream>>>(h1, w2, b2, B, D, h2);
+  k_occ_conv2<<<div_up(BV / 4, 128), 128, 0, stream>>>(h1, w2, b2, B, D, h2, (bf16*)X, Ct, c_off);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_voxelize_s2d(const float* feat2, const float* points, int B, int P, int C,
+                                   int D, int Ct, int32_t* prev_keys, void* X, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B <= 0 || P <= 0 || C <= 0 || C > 256 || (C & 1) || D <= 0 || (D & 1) || Ct < C)
+    return MF_E_BADARG;
+  if (!feat2 || !points || !prev_keys || !X) return MF_E_BADARG;
+  if ((long long)B * D * D * D >= (1LL << 31)) return MF_E_TOOLARGE;
+  const int N = B * P;
+  k_s2d_clear<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(prev_keys, N, C, D, Ct, (bf16*)X);
+  MF_LAUNCH_CHECK();
+  k_s2d_keys<<<div_up(N, 256), 256, 0, stream>>>(points, B, P, D, prev_keys);
+  MF_LAUNCH_CHECK();
+  k_s2d_scatter<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(feat2, prev_keys, B, P, C, D, Ct,
+                                                                   (bf16*)X);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

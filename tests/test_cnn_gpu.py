@@ -78,3 +78,33 @@ def test_cnn_forward_vs_oracle(cuda_device, with_occ, tc):
         q, q32 = rot[b, k[b]], ref32["rot"][b, k[b]]
         assert abs(abs(float(q @ q32)) - 1) < 5e-3
         assert ref32["conf"][b, k[b]] >= ref32["conf"][b, k32[b]] - 2e-2
+
+
+def test_fused_voxelize_equals_operator_composition(cuda_device):
+    """The fused voxelise->s2d path (sparse clear + leader scatter + occupancy stencil writing
+    in place) produces bit-identical conv3 input to average_voxelization_3d + occ convs + pack,
+    across consecutive calls with different inputs (exercises the sparse re-zeroing)."""
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    import morefusion_b200 as mf
+    mf.config.check_nan = False
+    B = 3
+    w = ocnn.init_weights(21, seed=2)
+    m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)
+
+    def x3_of(inp, fused):
+        m.fused_voxelize = fused
+        m.forward_features(
+            class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+            values=torch.as_tensor(inp["values"], device=cuda_device),
+            points=torch.as_tensor(inp["points"], device=cuda_device),
+            pitch=inp["pitch"], origin=inp["origin"],
+            grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device))
+        torch.cuda.synchronize()
+        return m._wbufs[(B, 1000, cuda_device)]["x3"].clone()
+
+    a, b, c = make_inputs(B, seed=5), make_inputs(B, seed=6), make_inputs(B, seed=7)
+    ref_a, ref_b, ref_c = x3_of(a, False), x3_of(b, False), x3_of(c, False)
+    assert torch.equal(x3_of(a, True), ref_a)     # dense -> fused transition (full clear)
+    assert torch.equal(x3_of(b, True), ref_b)     # sparse clear of a's voxels
+    assert torch.equal(x3_of(c, True), ref_c)
+    assert torch.equal(x3_of(a, False), ref_a)    # and back
