@@ -234,6 +234,10 @@ int mf_cnn_pack_s2d(const float* vox /*[B,C,D,D,D]*/, const float* hocc /*[B,V,C
                     int B, int C, int Cocc, int D, void* X /*bf16 s2d, borders pre-zeroed*/,
                     void* stream);
 int mf_gemm_bf16_simt(const GemmParams* p, void* stream);
+/* up to 3 GEMMs in one launch (the three pose heads); tc variant needs identical M,N,K,mode */
+int mf_gemm_bf16_simt_grouped(const GemmParams* p, int n_groups, void* stream);
+int mf_gemm_bf16_tc_grouped(const GemmParams* p, int n_groups, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* tcgen05/TMEM/TMA kernel; returns MF_E_UNSUPPORTED for shapes it does not cover (N % 32, N < 128,
  * K < 64, unaligned views) -- the caller then uses mf_gemm_bf16_simt.  `workspace` holds fp32
  * [M][N] partial sums when the launch splits K (few output tiles, long K). */

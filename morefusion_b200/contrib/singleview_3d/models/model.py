@@ -193,6 +193,30 @@ class Model(torch.nn.Module):
         self.n_launches += 1
         _lib.check(L.mf_gemm_bf16_simt(ctypes.byref(gp), _lib.stream()), "gemm_bf16_simt")
 
+    def _gemm_grouped(self, L, specs):
+        """Up to 3 GEMMs in one launch; tcgen05 when the shapes match and qualify, else SIMT."""
+        n = len(specs)
+        arr = (GemmParams * n)()
+        keep = []
+        for i, sp in enumerate(specs):
+            keep.append(sp)
+            arr[i] = GemmParams(
+                _lib.ptr(sp["A"]), _lib.ptr(sp["W"]), _lib.ptr(sp["bias"]), _lib.ptr(sp["out"]),
+                sp["M"], sp["N"], sp["K"], sp.get("mode", GEMM_LINEAR), sp.get("lda", 0),
+                sp["W"].shape[1], sp.get("Do", 0), sp.get("Ci8", 0), sp.get("relu", 1),
+                sp.get("out_mode", OUT_BF16), sp.get("ldo", 0), sp.get("col_off", 0))
+        if self.use_tensor_cores:
+            dev = specs[0]["A"].device
+            ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(specs[0]["M"], specs[0]["N"]), dev)
+            rc = L.mf_gemm_bf16_tc_grouped(arr, n, _lib.ptr(ws), ws.numel(), _lib.stream())
+            if rc == 0:
+                self.n_launches += 1
+                return
+            if rc != -4:
+                _lib.check(rc, "gemm_bf16_tc_grouped")
+        _lib.check(L.mf_gemm_bf16_simt_grouped(arr, n, _lib.stream()), "gemm_bf16_simt_grouped")
+        self.n_launches += 1
+
     def forward_features(self, *, class_id, values, points, pitch, origin,
                          grid_nontarget_empty=None):
         """The hot path proper: everything after the 2-D extractor (model.py:236-273).
@@ -309,17 +333,21 @@ class Model(torch.nn.Module):
             # heads (model.py:239-254)
             self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
                        lda=984, ldo=1920)
-            for i, h in enumerate(("rot", "trans", "conf")):
-                a1 = buf["hd1"][:, i * 640:]
-                self._gemm(L, a1, w[f"conv2_{h}/W"], w[f"conv2_{h}/b"], buf["hd2"], NP, 256, 640,
-                           lda=1920, ldo=768, col_off=i * 256)
-                a2 = buf["hd2"][:, i * 256:]
-                self._gemm(L, a2, w[f"conv3_{h}/W"], w[f"conv3_{h}/b"], buf["hd3"], NP, 128, 256,
-                           lda=768, ldo=384, col_off=i * 128)
-                a3 = buf["hd3"][:, i * 128:]
-                o = buf["out_" + h]
-                self._gemm(L, a3, w[f"conv4_{h}/W"], w[f"conv4_{h}/b"], o, NP, o.shape[1], 128,
-                           lda=384, relu=0, out_mode=OUT_F32, ldo=o.shape[1])
+            heads = ("rot", "trans", "conf")
+            # layers 2-4 of the three heads: one grouped launch per layer (grid.z = head)
+            self._gemm_grouped(L, [dict(
+                A=buf["hd1"][:, i * 640:], W=w[f"conv2_{h}/W"], bias=w[f"conv2_{h}/b"],
+                out=buf["hd2"], M=NP, N=256, K=640, lda=1920, ldo=768, col_off=i * 256)
+                for i, h in enumerate(heads)])
+            self._gemm_grouped(L, [dict(
+                A=buf["hd2"][:, i * 256:], W=w[f"conv3_{h}/W"], bias=w[f"conv3_{h}/b"],
+                out=buf["hd3"], M=NP, N=128, K=256, lda=768, ldo=384, col_off=i * 128)
+                for i, h in enumerate(heads)])
+            self._gemm_grouped(L, [dict(
+                A=buf["hd3"][:, i * 128:], W=w[f"conv4_{h}/W"], bias=w[f"conv4_{h}/b"],
+                out=buf["out_" + h], M=NP, N=buf["out_" + h].shape[1], K=128, lda=384, relu=0,
+                out_mode=OUT_F32, ldo=buf["out_" + h].shape[1])
+                for i, h in enumerate(heads)])
             _lib.check(L.mf_cnn_pose(
                 _lib.ptr(buf["out_rot"]), _lib.ptr(buf["out_trans"]), _lib.ptr(buf["out_conf"]),
                 _lib.ptr(points), _lib.ptr(st["class_id"]), _lib.ptr(st["pitch"]),

@@ -398,8 +398,14 @@ __device__ __forceinline__ void store_out(const GemmParams& p, int m, int n, flo
   }
 }
 
+struct SimtGroup {
+  GemmParams p[3];
+};
+
 __global__ void __launch_bounds__(256)
-k_gemm_simt(GemmParams p) {
+k_gemm_simt(const __grid_constant__ SimtGroup grp) {
+  const GemmParams& p = grp.p[blockIdx.z];
+  if ((int)(blockIdx.x * BN) >= p.N || (int)(blockIdx.y * BM) >= p.M) return;
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -619,17 +625,29 @@ extern "C" int mf_cnn_pack_s2d(const float* vox, const float* hocc, int B, int C
   return MF_OK;
 }
 
-extern "C" int mf_gemm_bf16_simt(const GemmParams* hp, void* stream_) {
-  if (!hp) return MF_E_BADARG;
-  GemmParams p = *hp;
-  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
-  if (p.K % 8 != 0 || p.ldw % 8 != 0) return MF_E_UNSUPPORTED;
-  if (p.mode == GEMM_LINEAR && p.lda % 8 != 0) return MF_E_UNSUPPORTED;
-  if (p.mode == GEMM_CONV_S2D && (p.Ci8 % 8 != 0 || p.K != 8 * p.Ci8)) return MF_E_UNSUPPORTED;
-  dim3 grid(div_up(p.N, BN), div_up(p.M, BM));
-  k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream_>>>(p);
+extern "C" int mf_gemm_bf16_simt_grouped(const GemmParams* hp, int n_groups, void* stream_) {
+  if (!hp || n_groups < 1 || n_groups > 3) return MF_E_BADARG;
+  SimtGroup grp;
+  int maxM = 0, maxN = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const GemmParams& p = hp[g];
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
+    if (p.K % 8 != 0 || p.ldw % 8 != 0) return MF_E_UNSUPPORTED;
+    if (p.mode == GEMM_LINEAR && p.lda % 8 != 0) return MF_E_UNSUPPORTED;
+    if (p.mode == GEMM_CONV_S2D && (p.Ci8 % 8 != 0 || p.K != 8 * p.Ci8)) return MF_E_UNSUPPORTED;
+    grp.p[g] = p;
+    maxM = p.M > maxM ? p.M : maxM;
+    maxN = p.N > maxN ? p.N : maxN;
+  }
+  for (int g = n_groups; g < 3; ++g) grp.p[g] = hp[0];
+  dim3 grid(div_up(maxN, BN), div_up(maxM, BM), n_groups);
+  k_gemm_simt<<<grid, 256, 0, (cudaStream_t)stream_>>>(grp);
   MF_LAUNCH_CHECK();
   return MF_OK;
+}
+
+extern "C" int mf_gemm_bf16_simt(const GemmParams* hp, void* stream_) {
+  return mf_gemm_bf16_simt_grouped(hp, 1, stream_);
 }
 
 extern "C" int mf_cnn_interp_cl(const void* grid, int s2d, const float* points, int B, int P,

@@ -19,6 +19,7 @@
 // (cnn.cu) the 128 output voxels x 64 channels of one K block are ONE 5-D TMA box.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "cnn.cuh"
 #include "common.cuh"
@@ -34,10 +35,19 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KiB
 struct TcExtra {
   int kb_per_a;      // conv: K blocks per kernel-offset a (= Ci8 / 64)
   int kb_total;      // K blocks overall
-  int kb_per_split;  // K blocks per grid.z slice
+  int kb_per_split;  // K blocks per split-K slice
   int splitk;
-  float* ws;         // fp32 [M][N] partial sums when splitk > 1
+  float* ws;         // fp32 [splitk][M][N] partial sums when splitk > 1 (plain stores, no atomics)
   int* err;          // device error word (pipeline time-out), may be null
+};
+
+constexpr int TC_MAX_GROUPS = 3;
+// up to 3 same-shape GEMMs in one launch (the three pose heads): grid.z = group * splitk + split
+struct TcArgs {
+  CUtensorMap tmA[TC_MAX_GROUPS];
+  CUtensorMap tmW[TC_MAX_GROUPS];
+  GemmParams p[TC_MAX_GROUPS];
+  TcExtra e;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -152,8 +162,12 @@ __device__ __forceinline__ long long out_row_offset(const GemmParams& p, int m) 
 // ------------------------------------------------------------------ kernel
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(256, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-          const GemmParams p, const TcExtra e) {
+k_gemm_tc(const __grid_constant__ TcArgs args) {
+  const int group = blockIdx.z / args.e.splitk, split = blockIdx.z - group * args.e.splitk;
+  const CUtensorMap& tmA = args.tmA[group];
+  const CUtensorMap& tmW = args.tmW[group];
+  const GemmParams& p = args.p[group];
+  const TcExtra& e = args.e;
   constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_dyn[];
@@ -167,7 +181,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * TC_BLOCK_M;
-  const int kb0 = blockIdx.z * e.kb_per_split;
+  const int kb0 = split * e.kb_per_split;
   const int kb1 = min(kb0 + e.kb_per_split, e.kb_total);
   const int nkb = kb1 - kb0;
 
@@ -259,9 +273,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int n = n0 + c0;
       if (!row_ok || n >= p.N) continue;            // N % 32 == 0 is enforced on the host
       if (e.splitk > 1) {
-        float* dst = e.ws + (long long)m * p.N + n;
+        float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         continue;
       }
       float v[32];
@@ -302,11 +318,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // split-K epilogue: bias + activation + layout on the reduced fp32 sums
-__global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p) {
+__global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p, int splitk) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)p.M * p.N) return;
+  const long long MN = (long long)p.M * p.N;
+  if (i >= MN) return;
   int m = (int)(i / p.N), n = (int)(i % p.N);
-  float v = ws[i] + (p.bias ? p.bias[n] : 0.f);
+  float v = p.bias ? p.bias[n] : 0.f;
+  for (int s = 0; s < splitk; ++s) v += ws[s * MN + i];
   if (p.relu) v = fmaxf(v, 0.f);
   long long off = out_row_offset(p, m) + n;
   if (p.out_mode == OUT_F32) reinterpret_cast<float*>(p.out)[off] = v;
@@ -344,8 +362,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 }
 
 template <int BLOCK_N, int STAGES>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p,
-                  const TcExtra& e, dim3 grid, cudaStream_t stream) {
+static int launch(const TcArgs& args, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -353,24 +370,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmPara
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  k_gemm_tc<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(tmA, tmW, p, e);
+  k_gemm_tc<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(args);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
 
-}  // namespace mf
-
-using namespace mf;
-
-extern "C" size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N) {
-  return (size_t)M * N * 4 + 256;
-}
-
-extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t workspace_bytes,
-                               void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (!hp) return MF_E_BADARG;
-  GemmParams p = *hp;
+static int check_shape(const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
   // shapes this kernel family covers; everything else goes to the SIMT kernel
   if (p.N % 32 != 0 || p.N < 128 || p.K < 64 || p.K % 8 != 0 || p.ldw % 8 != 0)
@@ -378,63 +383,97 @@ extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t wor
   if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15) || ((uintptr_t)p.out & 15))
     return MF_E_UNSUPPORTED;
   if (p.out_mode != OUT_S2D_BF16 && ((p.ldo % 8) || (p.col_off % 8))) return MF_E_UNSUPPORTED;
-  const int BN = (p.N % 256 == 0) ? 256 : 128;
-  TcExtra e{};
-  e.kb_total = (p.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-  CUtensorMap tmA, tmW;
+  return MF_OK;
+}
+
+static int make_maps(const GemmParams& p, int BN, CUtensorMap* tmA, CUtensorMap* tmW, int* kb_per_a) {
   int rc;
+  *kb_per_a = 0;
   if (p.mode == GEMM_CONV_S2D) {
     const int Do = p.Do, Js = Do + 1;
     if (!(Do == 8 || Do == 16) || p.Ci8 % 64 != 0 || p.K != 8 * p.Ci8) return MF_E_UNSUPPORTED;
     if (p.M % (Do * Do * Do) != 0) return MF_E_UNSUPPORTED;
     const int Bn = p.M / (Do * Do * Do);
-    e.kb_per_a = p.Ci8 / 64;
+    *kb_per_a = p.Ci8 / 64;
     cuuint64_t dims[5] = {(cuuint64_t)p.Ci8, (cuuint64_t)Js, (cuuint64_t)Js, (cuuint64_t)Js,
                           (cuuint64_t)Bn};
     cuuint64_t str[4] = {(cuuint64_t)p.Ci8 * 2, (cuuint64_t)Js * p.Ci8 * 2,
                          (cuuint64_t)Js * Js * p.Ci8 * 2, (cuuint64_t)Js * Js * Js * p.Ci8 * 2};
     // 128 consecutive output voxels (w fastest): 16x8x1 for Do=16, 8x8x2 for Do=8
     cuuint32_t box[5] = {64, (cuuint32_t)Do, 8, (cuuint32_t)(Do == 16 ? 1 : 2), 1};
-    rc = encode(&tmA, p.A, 5, dims, str, box);
+    rc = encode(tmA, p.A, 5, dims, str, box);
   } else {
     if (p.lda % 8 != 0) return MF_E_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     cuuint64_t str[1] = {(cuuint64_t)p.lda * 2};
     cuuint32_t box[2] = {64, 128};
-    rc = encode(&tmA, p.A, 2, dims, str, box);
+    rc = encode(tmA, p.A, 2, dims, str, box);
   }
   if (rc) return rc;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
-    cuuint64_t str[1] = {(cuuint64_t)p.ldw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BN};
-    rc = encode(&tmW, p.W, 2, dims, str, box);
+  cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
+  cuuint64_t str[1] = {(cuuint64_t)p.ldw * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  return encode(tmW, p.W, 2, dims, str, box);
+}
+
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N) {
+  return (size_t)M * N * 4 * 4 + 256;      // up to 4 split-K slices
+}
+
+extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!hp || n_groups < 1 || n_groups > TC_MAX_GROUPS) return MF_E_BADARG;
+  TcArgs args;
+  memset(&args, 0, sizeof(args));
+  const GemmParams& p0 = hp[0];
+  for (int g = 0; g < n_groups; ++g) {
+    int rc = check_shape(hp[g]);
+    if (rc) return rc;
+    if (hp[g].M != p0.M || hp[g].N != p0.N || hp[g].K != p0.K || hp[g].mode != p0.mode ||
+        hp[g].Do != p0.Do || hp[g].Ci8 != p0.Ci8)
+      return MF_E_UNSUPPORTED;
+    args.p[g] = hp[g];
+  }
+  const int BN = (p0.N >= 256) ? 256 : 128;
+  args.e.kb_total = (p0.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  for (int g = 0; g < n_groups; ++g) {
+    int rc = make_maps(hp[g], BN, &args.tmA[g], &args.tmW[g], &args.e.kb_per_a);
     if (rc) return rc;
   }
-  const int m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p0.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (p0.N + BN - 1) / BN;
   int splitk = 1;
-  const int tiles = m_tiles * n_tiles;
-  if (tiles <= 74 && e.kb_total >= 64) {
+  const int tiles = m_tiles * n_tiles * n_groups;
+  if (n_groups == 1 && tiles <= 74 && args.e.kb_total >= 64) {
     splitk = 148 / tiles;
     if (splitk > 4) splitk = 4;
     if (splitk < 1) splitk = 1;
   }
-  e.kb_per_split = (e.kb_total + splitk - 1) / splitk;
-  splitk = (e.kb_total + e.kb_per_split - 1) / e.kb_per_split;
-  e.splitk = splitk;
-  e.err = nullptr;
+  args.e.kb_per_split = (args.e.kb_total + splitk - 1) / splitk;
+  splitk = (args.e.kb_total + args.e.kb_per_split - 1) / args.e.kb_per_split;
+  args.e.splitk = splitk;
+  args.e.err = nullptr;
   if (splitk > 1) {
-    if (!workspace || workspace_bytes < (size_t)p.M * p.N * 4) return MF_E_WORKSPACE;
-    e.ws = (float*)workspace;
-    MF_CUDA_TRY(cudaMemsetAsync(e.ws, 0, (size_t)p.M * p.N * 4, stream));
+    if (!workspace || workspace_bytes < (size_t)splitk * p0.M * p0.N * 4) return MF_E_WORKSPACE;
+    args.e.ws = (float*)workspace;
   }
-  dim3 grid(n_tiles, m_tiles, splitk);
-  if (BN == 256) rc = launch<256, 4>(tmA, tmW, p, e, grid, stream);
-  else rc = launch<128, 6>(tmA, tmW, p, e, grid, stream);
+  dim3 grid(n_tiles, m_tiles, splitk * n_groups);
+  int rc;
+  if (BN == 256) rc = launch<256, 4>(args, grid, stream);
+  else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;
   if (splitk > 1) {
-    k_splitk_finish<<<div_up((long long)p.M * p.N, 256), 256, 0, stream>>>(e.ws, p);
+    k_splitk_finish<<<div_up((long long)p0.M * p0.N, 256), 256, 0, stream>>>(args.e.ws, p0, splitk);
     MF_LAUNCH_CHECK();
   }
   return MF_OK;
+}
+
+extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  return mf_gemm_bf16_tc_grouped(hp, 1, workspace, workspace_bytes, stream_);
 }
