@@ -42,7 +42,7 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
   extern __shared__ float sm[];
   float* t1r = sm;                 // [32][64]
   float* t1p = t1r + 32 * 64;      // [3][8]
-  float* t2r = t1p + 3 * 8;        // [64][128]
+  float* t2r = t1p + 3 * 8;        // [64][128]  (16-byte aligned: 2048 + 24 floats before it)
   float* t2p = t2r + 64 * 128;     // [8][16]
   float* bb1 = t2p + 8 * 16;       // [72]
   float* bb2 = bb1 + 72;           // [144]
@@ -71,37 +71,83 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
     xin[pt * 36 + c] = v;
   }
   __syncthreads();
-  for (int e = tid; e < kMlpPts * 72; e += 256) {
-    int pt = e / 72, oc = e % 72;
-    float acc = bb1[oc];
-    if (oc < 64) {
+  // stage 1: 64 points x 72 channels; thread = 4 points x 1 channel column group
+  //   rgb: 64 oc x 64 pts -> (16 pt-groups of 4) x 64 oc = 1024 work items, 4 per thread
+  for (int e = tid; e < 16 * 64; e += 256) {
+    int oc = e % 64, pg = e / 64;
+    float a0 = bb1[oc], a1 = a0, a2 = a0, a3 = a0;
+    const float* x0 = xin + (pg * 4) * 36;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(t1r[k * 64 + oc], xin[pt * 36 + k], acc);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) acc = fmaf(t1p[k * 8 + oc - 64], xin[pt * 36 + 32 + k], acc);
+    for (int k = 0; k < 32; ++k) {
+      float wv = t1r[k * 64 + oc];
+      a0 = fmaf(wv, x0[k], a0);
+      a1 = fmaf(wv, x0[36 + k], a1);
+      a2 = fmaf(wv, x0[72 + k], a2);
+      a3 = fmaf(wv, x0[108 + k], a3);
     }
-    acc = fmaxf(acc, 0.f);
-    h1[pt * 73 + oc] = acc;
-    long long n = n0 + pt;
-    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(acc);
+    h1[(pg * 4 + 0) * 73 + oc] = fmaxf(a0, 0.f);
+    h1[(pg * 4 + 1) * 73 + oc] = fmaxf(a1, 0.f);
+    h1[(pg * 4 + 2) * 73 + oc] = fmaxf(a2, 0.f);
+    h1[(pg * 4 + 3) * 73 + oc] = fmaxf(a3, 0.f);
+  }
+  for (int e = tid; e < kMlpPts * 8; e += 256) {
+    int pt = e / 8, o = e % 8;
+    float acc = bb1[64 + o];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc = fmaf(t1p[k * 8 + o], xin[pt * 36 + 32 + k], acc);
+    h1[pt * 73 + 64 + o] = fmaxf(acc, 0.f);
   }
   __syncthreads();
-  for (int e = tid; e < kMlpPts * 144; e += 256) {
-    int pt = e / 144, oc = e % 144;
-    float acc = bb2[oc];
-    if (oc < 128) {
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) acc = fmaf(t2r[k * 128 + oc], h1[pt * 73 + k], acc);
-    } else {
+  for (int e = tid; e < kMlpPts * 72; e += 256) {
+    int pt = e / 72, oc = e % 72;
+    long long n = n0 + pt;
+    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(h1[pt * 73 + oc]);
+  }
+  // stage 2 rgb: 128 oc x 64 pts; thread = 4 points x 4 consecutive oc (one LDS.128 of weights
+  // feeds 16 FMAs): 32 oc-quads x 16 point-groups = 512 items, 2 per thread
+  for (int e = tid; e < 32 * 16; e += 256) {
+    int oq = e % 32, pg = e / 32;
+    float4 bq = *reinterpret_cast<const float4*>(bb2 + oq * 4);
+    float acc[4][4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(t2p[k * 16 + oc - 128], h1[pt * 73 + 64 + k], acc);
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bq.x; acc[i][1] = bq.y; acc[i][2] = bq.z; acc[i][3] = bq.w; }
+    const float* hp = h1 + (pg * 4) * 73;
+#pragma unroll 4
+    for (int k = 0; k < 64; ++k) {
+      float4 wv = *reinterpret_cast<const float4*>(t2r + k * 128 + oq * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x = hp[i * 73 + k];
+        acc[i][0] = fmaf(wv.x, x, acc[i][0]);
+        acc[i][1] = fmaf(wv.y, x, acc[i][1]);
+        acc[i][2] = fmaf(wv.z, x, acc[i][2]);
+        acc[i][3] = fmaf(wv.w, x, acc[i][3]);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long n = n0 + pg * 4 + i;
+      if (n >= NP) continue;
+      float v0 = fmaxf(acc[i][0], 0.f), v1 = fmaxf(acc[i][1], 0.f), v2 = fmaxf(acc[i][2], 0.f),
+            v3 = fmaxf(acc[i][3], 0.f);
+      *reinterpret_cast<float4*>(feat2 + n * 144 + oq * 4) = make_float4(v0, v1, v2, v3);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1b = __floats2bfloat162_rn(v2, v3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1b);
+      *reinterpret_cast<uint2*>(feat + n * ldf + 72 + oq * 4) = u;
+    }
+  }
+  for (int e = tid; e < kMlpPts * 16; e += 256) {
+    int pt = e / 16, o = e % 16;
+    float acc = bb2[128 + o];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(t2p[k * 16 + o], h1[pt * 73 + 64 + k], acc);
     acc = fmaxf(acc, 0.f);
     long long n = n0 + pt;
     if (n < NP) {
-      feat[n * ldf + 72 + oc] = __float2bfloat16(acc);
-      feat2[n * 144 + oc] = acc;
+      feat[n * ldf + 72 + 128 + o] = __float2bfloat16(acc);
+      feat2[n * 144 + 128 + o] = acc;
     }
   }
 }
@@ -150,7 +196,7 @@ __global__ void k_occ_conv1(const float* __restrict__ gne, const float* __restri
 // weights (4 output channels, warp broadcast) feeds 16 FMAs; inputs are 16-byte channel vectors.
 // Output: fp32 [B,V,16] (h2) or, if X != null, bf16 straight into channels [c_off, c_off+16) of
 // the s2d conv3 input.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
             const float* __restrict__ bias, int B, int D, float* __restrict__ h2,
             bf16* __restrict__ X, int Ct, int c_off) {
@@ -584,7 +630,7 @@ extern "C" int mf_cnn_occ_convs(const float* gne, const float* w1, const float* 
   long long BV = (long long)B * D * D * D;
   k_occ_conv1<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, h1);
   MF_LAUNCH_CHECK();
-  k_occ_conv2<<<div_up(BV / 4, 128), 128, 0, stream>>>(h1, w2, b2, B, D, h2, (bf16*)X, Ct, c_off);
+  k_occ_conv2<<<div_up(BV / 4, 64), 64, 0, stream>>>(h1, w2, b2, B, D, h2, (bf16*)X, Ct, c_off);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

@@ -271,7 +271,18 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int n = n0 + c0;
-      if (!row_ok || n >= p.N) continue;            // N % 32 == 0 is enforced on the host
+      if (!row_ok || n >= p.N) continue;
+      if (p.N & 31) {
+        // ragged N (small-N heads, fp32 row-major output only; enforced on the host): rows are
+        // not 16-byte aligned, scalar stores
+        float* dst = reinterpret_cast<float*>(p.out) + roff + n;
+        const int nj = min(32, p.N - n);
+        for (int j = 0; j < nj; ++j) {
+          float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+          dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+        }
+        continue;
+      }
       if (e.splitk > 1) {
         float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
 #pragma unroll
@@ -317,18 +328,28 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
   }
 }
 
-// split-K epilogue: bias + activation + layout on the reduced fp32 sums
+// split-K epilogue: sum the slices, bias + activation + layout; 4 columns per thread
 __global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p, int splitk) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long MN = (long long)p.M * p.N;
-  if (i >= MN) return;
-  int m = (int)(i / p.N), n = (int)(i % p.N);
-  float v = p.bias ? p.bias[n] : 0.f;
-  for (int s = 0; s < splitk; ++s) v += ws[s * MN + i];
-  if (p.relu) v = fmaxf(v, 0.f);
+  if (i * 4 >= MN) return;
+  int m = (int)((i * 4) / p.N), n = (int)((i * 4) % p.N);   // N % 32 == 0
+  float4 v = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0, 0, 0, 0);
+  for (int s = 0; s < splitk; ++s) {
+    float4 a = __ldcs(reinterpret_cast<const float4*>(ws + s * MN) + i);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
   long long off = out_row_offset(p, m) + n;
-  if (p.out_mode == OUT_F32) reinterpret_cast<float*>(p.out)[off] = v;
-  else reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16(v);
+  if (p.out_mode == OUT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
+  } else {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = u;
+  }
 }
 
 // ------------------------------------------------------------------ host: tensor maps
@@ -378,11 +399,15 @@ static int launch(const TcArgs& args, dim3 grid, cudaStream_t stream) {
 static int check_shape(const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || !p.A || !p.W || !p.out) return MF_E_BADARG;
   // shapes this kernel family covers; everything else goes to the SIMT kernel
-  if (p.N % 32 != 0 || p.N < 128 || p.K < 64 || p.K % 8 != 0 || p.ldw % 8 != 0)
-    return MF_E_UNSUPPORTED;
+  if (p.K < 64 || p.K % 8 != 0 || p.ldw % 8 != 0) return MF_E_UNSUPPORTED;
+  if (p.N % 32 != 0 || p.N < 128) {
+    // ragged / small N: only fp32 row-major outputs, a single N tile, no split-K
+    if (p.out_mode != OUT_F32 || p.N > 128 || p.N < 8) return MF_E_UNSUPPORTED;
+  }
   if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15) || ((uintptr_t)p.out & 15))
     return MF_E_UNSUPPORTED;
-  if (p.out_mode != OUT_S2D_BF16 && ((p.ldo % 8) || (p.col_off % 8))) return MF_E_UNSUPPORTED;
+  if (p.N % 32 == 0 && p.out_mode != OUT_S2D_BF16 && ((p.ldo % 8) || (p.col_off % 8)))
+    return MF_E_UNSUPPORTED;
   return MF_OK;
 }
 
@@ -434,8 +459,10 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   for (int g = 0; g < n_groups; ++g) {
     int rc = check_shape(hp[g]);
     if (rc) return rc;
-    if (hp[g].M != p0.M || hp[g].N != p0.N || hp[g].K != p0.K || hp[g].mode != p0.mode ||
-        hp[g].Do != p0.Do || hp[g].Ci8 != p0.Ci8)
+    const bool small_n = p0.N <= 128 && hp[g].N <= 128 && hp[g].out_mode == OUT_F32 &&
+                         p0.out_mode == OUT_F32;
+    if (hp[g].M != p0.M || (hp[g].N != p0.N && !small_n) || hp[g].K != p0.K ||
+        hp[g].mode != p0.mode || hp[g].Do != p0.Do || hp[g].Ci8 != p0.Ci8)
       return MF_E_UNSUPPORTED;
     args.p[g] = hp[g];
   }
@@ -445,10 +472,12 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
     int rc = make_maps(hp[g], BN, &args.tmA[g], &args.tmW[g], &args.e.kb_per_a);
     if (rc) return rc;
   }
-  const int m_tiles = (p0.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (p0.N + BN - 1) / BN;
+  int maxN = p0.N;
+  for (int g = 1; g < n_groups; ++g) maxN = hp[g].N > maxN ? hp[g].N : maxN;
+  const int m_tiles = (p0.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (maxN + BN - 1) / BN;
   int splitk = 1;
   const int tiles = m_tiles * n_tiles * n_groups;
-  if (n_groups == 1 && tiles <= 74 && args.e.kb_total >= 64) {
+  if (n_groups == 1 && tiles <= 74 && args.e.kb_total >= 64 && p0.N % 32 == 0) {
     splitk = 148 / tiles;
     if (splitk > 4) splitk = 4;
     if (splitk < 1) splitk = 1;
@@ -467,7 +496,7 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;
   if (splitk > 1) {
-    k_splitk_finish<<<div_up((long long)p0.M * p0.N, 256), 256, 0, stream>>>(args.e.ws, p0, splitk);
+    k_splitk_finish<<<div_up((long long)p0.M * p0.N / 4, 256), 256, 0, stream>>>(args.e.ws, p0, splitk);
     MF_LAUNCH_CHECK();
   }
   return MF_OK;
