@@ -225,6 +225,11 @@ int mf_cnn_occ_convs(const float* grid_nontarget_empty /*[B,D,D,D]*/, const floa
                      const float* b1, const float* w2, const float* b2, int B, int D,
                      float* h1 /*[B,V,8] scratch*/, float* h2 /*[B,V,16] or NULL*/,
                      void* X /*bf16 s2d or NULL*/, int Ct, int c_off, void* stream);
+/* tensor-core variant (D == 32): conv1_occ -> bf16 [B,V,8] scratch, conv2_occ as warp-level
+ * mma.sync m16n8k16 (bf16 operands, fp32 accumulate) writing bf16 into X. */
+int mf_cnn_occ_convs_tc(const float* grid_nontarget_empty, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int B, int D, void* h1_bf16 /*[B,V,8]*/,
+                        void* X, int Ct, int c_off, void* stream);
 /* average_voxelization_3d of model.py:143-164 (origin 0, pitch 1, D^3) fused with the s2d/bf16
  * packing: writes channels [0,C) of X.  prev_keys [B*P] int32 (in/out, initialise to -1) holds
  * the voxel keys of the previous call so that only those voxels are re-zeroed. */

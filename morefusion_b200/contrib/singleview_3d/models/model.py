@@ -171,6 +171,7 @@ class Model(torch.nn.Module):
         )
         if self._with_occupancy:
             b["occ1"] = z(B, D ** 3, 8, dt=f32)
+            b["occ1_bf16"] = z(B, D ** 3, 8)
             b["occ2"] = z(B, D ** 3, 16, dt=f32)
         self._wbufs[key] = b
         return b
@@ -280,7 +281,13 @@ class Model(torch.nn.Module):
                     _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
                     _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "voxelize_s2d")
                 self.n_launches += 3
-                if self._with_occupancy:
+                if self._with_occupancy and self.use_tensor_cores and D == 32:
+                    _lib.check(L.mf_cnn_occ_convs_tc(
+                        _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                        _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                        _lib.ptr(buf["occ1_bf16"]), _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs_tc")
+                    self.n_launches += 2
+                elif self._with_occupancy:
                     _lib.check(L.mf_cnn_occ_convs(
                         _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
                         _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,

@@ -292,6 +292,162 @@ k_occ_conv2(const float* __restrict__ h1, const float* __restrict__ w,
   }
 }
 
+// ------------------------------------------------------------------ conv2_occ on tensor cores
+// FP32 FFMA with three register operands issues at half rate on this SM, so even a perfectly
+// tiled SIMT stencil needs ~55 us for the 0.9 GMAC of conv2_occ.  Warp-level mma.sync
+// (m16n8k16, bf16 in, fp32 accumulate) fits this thin layer (N = 16 output channels, K = 27
+// taps x 8 channels): tcgen05's 128-row tiles + TMA boxes cannot express the dilated gather.
+//   A (16 voxels x 16 k): gathered straight from a shared-memory tile of conv1's bf16 output
+//   B (16 k x 8 co): all 14 k-steps x 2 n-tiles live in 56 registers per lane for the whole CTA
+// One CTA = one x-slab (32 x 32 voxels) of one object; smem tile = slabs x-2, x, x+2 with a
+// 2-voxel zero halo in y and z.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4],
+                                               const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int kOccT = 36;                       // 32 + 2*2 halo
+constexpr int kOccTileBytes = 3 * kOccT * kOccT * 16;
+
+__global__ void __launch_bounds__(256)
+k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __restrict__ w /*OIDHW*/,
+                const float* __restrict__ bias, int B, bf16* __restrict__ X, int Ct, int c_off) {
+  constexpr int D = 32;
+  extern __shared__ __align__(16) unsigned char occ_smem[];
+  uint4* tile = reinterpret_cast<uint4*>(occ_smem);          // [3][36][36] x 16 B
+  const int x = blockIdx.x % D, b = blockIdx.x / D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- stage the three input slabs (zero outside the grid)
+  for (int e = tid; e < 3 * kOccT * kOccT; e += 256) {
+    int zz = e % kOccT - 2, yy = (e / kOccT) % kOccT - 2, s = e / (kOccT * kOccT);
+    int xx = x + 2 * (s - 1);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (xx >= 0 && xx < D && yy >= 0 && yy < D && zz >= 0 && zz < D)
+      v = __ldg(reinterpret_cast<const uint4*>(h1) + ((long long)b * D * D * D + (xx * D + yy) * D + zz));
+    tile[e] = v;
+  }
+  // ---- B fragments: k = tap_in_step*8 + ci, step s covers taps 2s, 2s+1 (tap 27 = zero pad)
+  uint32_t bf[14][2][2];
+#pragma unroll
+  for (int s = 0; s < 14; ++s)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int tap = 2 * s + h, co = nt * 8 + g, ci = 2 * t;
+        float w0 = 0.f, w1 = 0.f;
+        if (tap < 27) {
+          w0 = w[(co * 8 + ci) * 27 + tap];
+          w1 = w[(co * 8 + ci + 1) * 27 + tap];
+        }
+        __nv_bfloat162 p = __floats2bfloat162_rn(w0, w1);
+        bf[s][nt][h] = *reinterpret_cast<uint32_t*>(&p);
+      }
+  float bias_r[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    bias_r[nt][0] = bias[nt * 8 + 2 * t];
+    bias_r[nt][1] = bias[nt * 8 + 2 * t + 1];
+  }
+  __syncthreads();
+  const uint32_t* tw = reinterpret_cast<const uint32_t*>(occ_smem);
+  // 64 groups of 16 consecutive-z voxels (y = grp/2, z0 = (grp&1)*16); 8 per warp
+  for (int grp = warp; grp < 64; grp += 8) {
+    const int y = grp >> 1, z0 = (grp & 1) * 16;
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      acc[nt][0] = bias_r[nt][0]; acc[nt][1] = bias_r[nt][1];
+      acc[nt][2] = bias_r[nt][0]; acc[nt][3] = bias_r[nt][1];
+    }
+#pragma unroll
+    for (int s = 0; s < 14; ++s) {
+      uint32_t a[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int tap = 2 * s + h;
+        if (tap < 27) {
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          // tile coords: slab kd, y + 2*(kh-1) + 2, z + 2*(kw-1) + 2
+          const int base = (kd * kOccT + (y + 2 * kh)) * kOccT + (z0 + 2 * kw);
+          a[2 * h + 0] = tw[(base + g) * 4 + t];          // voxel z0+g   : ci 2t, 2t+1
+          a[2 * h + 1] = tw[(base + g + 8) * 4 + t];      // voxel z0+g+8
+        } else {
+          a[2 * h + 0] = 0u;
+          a[2 * h + 1] = 0u;
+        }
+      }
+      // register order of the m16n8k16 A fragment: (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi)
+      uint32_t af[4] = {a[0], a[1], a[2], a[3]};
+      mma_bf16_16816(acc[0], af, bf[s][0]);
+      mma_bf16_16816(acc[1], af, bf[s][1]);
+    }
+    // ---- epilogue: ReLU, bf16, into channels [c_off, c_off+16) of the s2d conv3 input
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int z = z0 + g + 8 * r;
+      const int J = D / 2 + 1;
+      int pd = x + 1, ph = y + 1, pw = z + 1;
+      int rr = ((pd & 1) << 2) | ((ph & 1) << 1) | (pw & 1);
+      long long dst = ((((long long)b * J + (pd >> 1)) * J + (ph >> 1)) * J + (pw >> 1)) * (8LL * Ct) +
+                      (long long)rr * Ct + c_off;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(acc[nt][2 * r], 0.f), fmaxf(acc[nt][2 * r + 1], 0.f));
+        *reinterpret_cast<__nv_bfloat162*>(X + dst + nt * 8 + 2 * t) = o;
+      }
+    }
+  }
+}
+
+// conv1_occ variant writing bf16 channels-last (input of k_occ_conv2_mma)
+__global__ void k_occ_conv1_bf16(const float* __restrict__ gne, const float* __restrict__ w,
+                                 const float* __restrict__ bias, int B, int D,
+                                 bf16* __restrict__ h1) {
+  __shared__ float sw[8 * 27 + 8];
+  for (int e = threadIdx.x; e < 8 * 27; e += blockDim.x) sw[e] = w[e];
+  if (threadIdx.x < 8) sw[8 * 27 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  long long V = (long long)D * D * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * V) return;
+  long long b = i / V, v = i % V;
+  int z = (int)(v % D), y = (int)((v / D) % D), x = (int)(v / ((long long)D * D));
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = sw[8 * 27 + c];
+  for (int kd = 0; kd < 3; ++kd) {
+    int xx = x + kd - 1;
+    if (xx < 0 || xx >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      int yy = y + kh - 1;
+      if (yy < 0 || yy >= D) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int zz = z + kw - 1;
+        if (zz < 0 || zz >= D) continue;
+        float in = gne[b * V + ((long long)xx * D + yy) * D + zz];
+        int tap = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(sw[c * 27 + tap], in, acc[c]);
+      }
+    }
+  }
+  uint4 o;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+  __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+  o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+  reinterpret_cast<uint4*>(h1)[i] = o;
+}
+
 // ------------------------------------------------------------------ fused voxelise -> s2d
 // Model path of average_voxelization_3d (model.py:143-164: origin 0, pitch 1, 32^3): the 144
 // averaged feature channels go straight into the bf16 s2d conv3 input.  The grid is >= 97 %
@@ -631,6 +787,28 @@ extern "C" int mf_cnn_occ_convs(const float* gne, const float* w1, const float* 
   k_occ_conv1<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, h1);
   MF_LAUNCH_CHECK();
   k_occ_conv2<<<div_up(BV / 4, 64), 64, 0, stream>>>(h1, w2, b2, B, D, h2, (bf16*)X, Ct, c_off);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_occ_convs_tc(const float* gne, const float* w1, const float* b1,
+                                   const float* w2, const float* b2, int B, int D,
+                                   void* h1_bf16, void* X, int Ct, int c_off, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (B <= 0 || !gne || !w1 || !b1 || !w2 || !b2 || !h1_bf16 || !X) return MF_E_BADARG;
+  if (D != 32) return MF_E_UNSUPPORTED;
+  if ((Ct & 7) || (c_off & 7) || c_off + 16 > Ct) return MF_E_BADARG;
+  long long BV = (long long)B * D * D * D;
+  k_occ_conv1_bf16<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, (bf16*)h1_bf16);
+  MF_LAUNCH_CHECK();
+  static bool attr = false;
+  if (!attr) {
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_occ_conv2_mma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kOccTileBytes));
+    attr = true;
+  }
+  k_occ_conv2_mma<<<(unsigned)(B * D), 256, kOccTileBytes, stream>>>(
+      (const bf16*)h1_bf16, w2, b2, B, (bf16*)X, Ct, c_off);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

@@ -102,7 +102,8 @@ def forward(w, *, class_id, values, points, pitch, origin, grid_nontarget_empty=
         g = torch.as_tensor(np.asarray(grid_nontarget_empty).astype(np.float32))[:, None]
         h_occ = F.relu(F.conv3d(g, torch.from_numpy(w["conv1_occ/W"]),
                                 torch.from_numpy(w["conv1_occ/b"]), stride=1, padding=1))
-        h_occ = F.relu(F.conv3d(h_occ, torch.from_numpy(w["conv2_occ/W"]),
+        # the CUDA path runs conv2_occ on tensor cores: bf16 operands, fp32 accumulation
+        h_occ = F.relu(F.conv3d(_r(h_occ, bf16), _r(torch.from_numpy(w["conv2_occ/W"]), bf16),
                                 torch.from_numpy(w["conv2_occ/b"]), stride=1, padding=2, dilation=2))
         voxelized = torch.cat([voxelized, h_occ], 1)                      # [B,160,32^3]
     W3 = _r(torch.from_numpy(w["conv3/W"]), bf16)

@@ -102,9 +102,18 @@ def test_fused_voxelize_equals_operator_composition(cuda_device):
         torch.cuda.synchronize()
         return m._wbufs[(B, 1000, cuda_device)]["x3"].clone()
 
+    def same(x, ref):
+        x = x.reshape(B, 17, 17, 17, 8, 160).float()
+        ref = ref.reshape(B, 17, 17, 17, 8, 160).float()
+        # 144 averaged feature channels: bit-identical
+        assert torch.equal(x[..., :144], ref[..., :144])
+        # 16 occupancy channels: tensor-core (bf16 operand) stencil vs the fp32 SIMT stencil
+        torch.testing.assert_close(x[..., 144:], ref[..., 144:], rtol=0,
+                                   atol=0.02 * float(ref[..., 144:].abs().max()))
+
     a, b, c = make_inputs(B, seed=5), make_inputs(B, seed=6), make_inputs(B, seed=7)
     ref_a, ref_b, ref_c = x3_of(a, False), x3_of(b, False), x3_of(c, False)
-    assert torch.equal(x3_of(a, True), ref_a)     # dense -> fused transition (full clear)
-    assert torch.equal(x3_of(b, True), ref_b)     # sparse clear of a's voxels
-    assert torch.equal(x3_of(c, True), ref_c)
+    same(x3_of(a, True), ref_a)     # dense -> fused transition (full clear)
+    same(x3_of(b, True), ref_b)     # sparse clear of a's voxels
+    same(x3_of(c, True), ref_c)
     assert torch.equal(x3_of(a, False), ref_a)    # and back
