@@ -54,6 +54,9 @@ int mf_device_sm_count(int device);
  * on HBM); per-voxel sums are taken in ascending point order (deterministic).
  * ------------------------------------------------------------------------ */
 size_t mf_average_voxelization_3d_workspace_bytes(int64_t n_points);
+/* byte offset inside `workspace` of an int32 copy of the MF_FLAG_* word of the last call (so a
+ * binding needs no separate flags allocation; `flags` below may then be NULL) */
+size_t mf_average_voxelization_3d_flags_offset(void);
 int mf_average_voxelization_3d_fwd(
     const float* values, const float* points, const int32_t* batch_indices,
     int64_t n_points, int channels, int batch_size,

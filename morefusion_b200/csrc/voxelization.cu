@@ -17,6 +17,7 @@ namespace mf {
 
 constexpr int kThreads = 256;
 constexpr int kListCap = 1024;           // keys scanned per round = 4 per thread
+constexpr int kStage = 64;               // list entries whose values are staged in smem at once
 constexpr int kHdrSortedBit = 2;         // hdr[0] bit: set = batch_indices non-decreasing
 
 struct VoxGeom {
@@ -24,15 +25,55 @@ struct VoxGeom {
   int X, Y, Z, B;
 };
 
+constexpr int kLeaderMaxSeg = 4096;      // longest batch segment the per-point leader path scans
+
+__device__ __forceinline__ void vox_keys_point(
+    const float* __restrict__ points, const int* __restrict__ bi, long long N, VoxGeom g,
+    int* __restrict__ keys, int* __restrict__ hdr, int* __restrict__ seg_start,
+    int* __restrict__ seg_end, int* __restrict__ flags, int* __restrict__ tile_count, int VT,
+    int* __restrict__ flags2, int* __restrict__ tile_list, int* __restrict__ tile_list_n,
+    unsigned int* __restrict__ occ_bits, long long n);
+
 // ---------------------------------------------------------------- prepass
 // key[n] = b*V + flat voxel index, or -1 if out of bounds.  Also: NaN flag,
 // sortedness, per-batch [seg_start, seg_end) when sorted.
 __global__ void k_vox_keys(const float* __restrict__ points, const int* __restrict__ bi,
                            long long N, VoxGeom g, int* __restrict__ keys,
                            int* __restrict__ hdr, int* __restrict__ seg_start,
-                           int* __restrict__ seg_end, int* __restrict__ flags) {
+                           int* __restrict__ seg_end, int* __restrict__ flags,
+                           int* __restrict__ tile_count, int VT, int* __restrict__ flags2,
+                           int* __restrict__ tile_list, int* __restrict__ tile_list_n,
+                           unsigned int* __restrict__ occ_bits, int* __restrict__ done,
+                           int* __restrict__ mode) {
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  if (n < N) vox_keys_point(points, bi, N, g, keys, hdr, seg_start, seg_end, flags, tile_count, VT,
+                            flags2, tile_list, tile_list_n, occ_bits, n);
+  // ---- the last block to finish decides the forward mode: "fast" (per-point leader scatter)
+  // needs sorted batch indices and short segments; anything else takes the general tile kernel
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  __threadfence();
+  int maxlen = 0;
+  for (int b = threadIdx.x; b < g.B; b += 32) {
+    int s0 = __ldcg(seg_start + b), s1 = __ldcg(seg_end + b);
+    if (s0 >= 0) maxlen = max(maxlen, s1 - s0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  if (threadIdx.x == 0)
+    *mode = ((__ldcg(hdr) & kHdrSortedBit) && maxlen <= kLeaderMaxSeg) ? 1 : 0;
+}
+
+__device__ __forceinline__ void vox_keys_point(
+    const float* __restrict__ points, const int* __restrict__ bi, long long N, VoxGeom g,
+    int* __restrict__ keys, int* __restrict__ hdr, int* __restrict__ seg_start,
+    int* __restrict__ seg_end, int* __restrict__ flags, int* __restrict__ tile_count, int VT,
+    int* __restrict__ flags2, int* __restrict__ tile_list, int* __restrict__ tile_list_n,
+    unsigned int* __restrict__ occ_bits, long long n) {
   float x = points[3 * n], y = points[3 * n + 1], z = points[3 * n + 2];
   int b = bi[n];
   int f = 0;
@@ -43,7 +84,16 @@ __global__ void k_vox_keys(const float* __restrict__ points, const int* __restri
   bool okb = (b >= 0) && (b < g.B);
   if (!okb) f |= MF_FLAG_BAD_BATCH_INDEX;
   bool ok = okb && ix >= 0 && ix < g.X && iy >= 0 && iy < g.Y && iz >= 0 && iz < g.Z;
-  keys[n] = ok ? (b * (g.X * g.Y * g.Z) + (ix * g.Y + iy) * g.Z + iz) : -1;
+  const int V = g.X * g.Y * g.Z;
+  const int flat = (ix * g.Y + iy) * g.Z + iz;
+  keys[n] = ok ? (b * V + flat) : -1;
+  if (ok) {
+    const int tile = b * ((V + VT - 1) / VT) + flat / VT;
+    // the first point to hit a tile appends it to the list of occupied tiles
+    if (atomicAdd(&tile_count[tile], 1) == 0) tile_list[atomicAdd(tile_list_n, 1)] = tile;
+    const int key = b * V + flat;
+    if (occ_bits) atomicOr(&occ_bits[key >> 5], 1u << (key & 31));
+  }
   int prev = (n > 0) ? bi[n - 1] : b;
   if (prev > b) {
     atomicAnd(&hdr[0], ~kHdrSortedBit);
@@ -54,6 +104,7 @@ __global__ void k_vox_keys(const float* __restrict__ points, const int* __restri
     if (n == N - 1 || bi[n + 1] != b) seg_end[b] = (int)(n + 1);
   }
   if (f && flags) atomicOr(flags, f);
+  if (f && flags2) atomicOr(flags2, f);
 }
 
 // ---------------------------------------------------------------- forward tiles
@@ -71,8 +122,100 @@ struct AvgParams {
   int G;        // thread groups per CTA (each owns voxels v % G == g)
   float* matrix;
   int* counts;
+  const int* tile_count;   // [B][tiles_per_batch] points per voxel tile (from the prepass)
+  const int* tile_list;    // occupied tiles (unordered) and their number
+  const int* tile_list_n;
+  const unsigned int* occ_bits;   // one bit per (b, voxel): some point falls into it
+  const int* mode;         // 1 = fast (leader scatter), 0 = general (tile kernel)
+  int n_fill_ctas, zero_groups;
+  int tiles_per_batch, n_chunks, n_items;
 };
 
+// Kernel A (fused): CTAs [0, n_fill_ctas) stream zeros, the rest run the per-point leader
+// scatter.  The two roles never touch the same output element: in fast mode the fill skips
+// exactly the voxels whose occupancy bit is set and the leaders write exactly those.
+//   fill role   : no shared memory, no integer division in the loop, 16-byte streaming stores
+//   leader role : one warp per point; the lowest-index point of a voxel sums the voxel's
+//                 points in ascending order (lanes over channels), divides, writes C values+count
+constexpr int kZeroRowsPerCta = 32;
+__global__ void __launch_bounds__(256)
+k_avg_fill_scatter(AvgParams p) {
+  const int fast = __ldg(p.mode);
+  if ((int)blockIdx.x < p.n_fill_ctas) {
+    const int tile = blockIdx.x / p.zero_groups, grp = blockIdx.x - tile * p.zero_groups;
+    const int npts = __ldg(p.tile_count + tile);
+    if (!fast && npts != 0) return;                        // general mode: the tile kernel owns it
+    const int b = tile / p.tiles_per_batch, ti = tile - b * p.tiles_per_batch;
+    const int vt4 = p.VT >> 2;
+    const int r0 = grp * kZeroRowsPerCta;
+    const int r1 = min(r0 + kZeroRowsPerCta, p.C + 1);     // C channel planes + the counts plane
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long voff = (long long)ti * p.VT;
+    const unsigned int* bits = p.occ_bits + (((long long)b * p.V + voff) >> 5);
+    for (int e = threadIdx.x; e < (r1 - r0) * vt4; e += 256) {
+      int r = r0 + e / vt4, v4 = e % vt4;
+      float* dst = (r < p.C) ? p.matrix + ((long long)b * p.C + r) * p.V + voff
+                             : reinterpret_cast<float*>(p.counts) + (long long)b * p.V + voff;
+      unsigned int m = 0;
+      if (npts != 0) m = (__ldg(bits + (v4 >> 3)) >> ((v4 & 7) * 4)) & 0xFu;
+      if (m == 0) {
+        __stcs(reinterpret_cast<float4*>(dst) + v4, z4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (!((m >> j) & 1)) dst[4 * v4 + j] = 0.f;
+      }
+    }
+    return;
+  }
+  if (!fast) return;
+  // ---- leader role
+  const long long n = ((long long)(blockIdx.x - p.n_fill_ctas) * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= p.N) return;
+  const int key = __ldg(p.keys + n);
+  if (key < 0) return;
+  const int b = key / p.V;
+  const int lo = __ldg(p.seg_start + b), hi = __ldg(p.seg_end + b);
+  bool earlier = false;
+  for (int j0 = lo; j0 < n && !earlier; j0 += 32) {
+    int j = j0 + lane;
+    bool m = (j < n) && (__ldg(p.keys + j) == key);
+    earlier = __any_sync(0xffffffffu, m);
+  }
+  if (earlier) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  int count = 0;
+  const int nn = (int)n;
+  for (int j0 = nn - (nn - lo) % 32; j0 < hi; j0 += 32) {   // aligned chunks: j ascends
+    int j = j0 + lane;
+    bool m = (j >= nn) && (j < hi) && (__ldg(p.keys + j) == key);
+    unsigned mask = __ballot_sync(0xffffffffu, m);
+    while (mask) {
+      int l = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float* src = p.values + (long long)(j0 + l) * p.C;
+      for (int k = 0; k * 32 < p.C && k < 8; ++k) {
+        int c = lane + 32 * k;
+        if (c < p.C) acc[k] = __fadd_rn(acc[k], __ldg(src + c));
+      }
+      ++count;
+    }
+  }
+  const int flat = key - b * p.V;
+  const float cf = (float)count;
+  float* dst = p.matrix + (long long)b * p.C * p.V + flat;
+  for (int k = 0; k * 32 < p.C && k < 8; ++k) {
+    int c = lane + 32 * k;
+    if (c < p.C) dst[(long long)c * p.V] = __fdiv_rn(acc[k], cf);
+  }
+  if (lane == 0) p.counts[(long long)b * p.V + flat] = count;
+}
+
+// Kernel B: one CTA per (occupied tile, channel chunk): ordered compaction of the point keys in
+// its voxel range, per-voxel sums in ascending point order in shared memory, divide, write.
 __global__ void __launch_bounds__(kThreads)
 k_avg_tiles(AvgParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -80,21 +223,29 @@ k_avg_tiles(AvgParams p) {
   int* cnt = reinterpret_cast<int*>(tile + (size_t)p.VT * p.CCp);  // [VT]
   int* list_n = cnt + p.VT;                                   // [kListCap]
   int* list_v = list_n + kListCap;                            // [kListCap]
+  float* stage = reinterpret_cast<float*>(list_v + kListCap); // [kStage][CCp]
   __shared__ int s_warp[kThreads / 32];
   __shared__ int s_total;
-  __shared__ int s_any;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.z, chunk = blockIdx.y;
-  const int vbase = blockIdx.x * p.VT;
+  const int chunk = blockIdx.y;
+  int tb;
+  if (p.mode && __ldg(p.mode)) return;                       // fast mode already wrote everything
+  if (p.tile_list) {
+    if ((int)blockIdx.x >= __ldg(p.tile_list_n)) return;     // fewer occupied tiles than CTAs
+    tb = __ldg(p.tile_list + blockIdx.x);
+  } else {
+    tb = blockIdx.x;                                          // dense mode (ragged shapes)
+  }
+  const int ti = tb % p.tiles_per_batch, b = tb / p.tiles_per_batch;
+  const int vbase = ti * p.VT;
   const int vt = min(p.VT, p.V - vbase);
   const int c0 = chunk * p.CC;
   const int cc = min(p.CC, p.C - c0);
+  float* out = p.matrix + ((long long)b * p.C + c0) * p.V + vbase;
 
   for (int e = tid; e < p.VT * p.CCp; e += kThreads) tile[e] = 0.f;
   for (int e = tid; e < p.VT; e += kThreads) cnt[e] = 0;
-  if (tid == 0) s_any = 0;
-
   long long lo = 0, hi = p.N;
   if (p.hdr[0] & kHdrSortedBit) {
     int s = p.seg_start[b];
@@ -130,59 +281,51 @@ k_avg_tiles(AvgParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (k[j] >= klo && k[j] < khi) {
-        list_n[pos] = (int)(i0 + j - 0);  // point id (fits int: N < 2^31 checked on host)
+        list_n[pos] = (int)(i0 + j);  // point id (N < 2^31 checked on host)
         list_v[pos] = k[j] - klo;
         ++pos;
       }
     __syncthreads();
     const int L = s_total;
-    if (L > 0) {
-      if (tid == 0) s_any = 1;
+    // values of the listed points are staged through shared memory in batches of kStage rows
+    // (independent, coalesced loads), then added per voxel in ascending point order
+    for (int l0 = 0; l0 < L; l0 += kStage) {
+      const int nl = min(kStage, L - l0);
+      for (int e = tid; e < nl * cc; e += kThreads) {
+        int l = e / cc, ch = e - l * cc;
+        stage[l * p.CCp + ch] = __ldg(p.values + (long long)list_n[l0 + l] * p.C + c0 + ch);
+      }
+      __syncthreads();
       if (acc_thread) {
-        const float* vsrc = p.values + c0 + c;
-        for (int l = 0; l < L; ++l) {
-          int v = list_v[l];
+        for (int l = 0; l < nl; ++l) {
+          int v = list_v[l0 + l];
           if ((v % p.G) == g) {
-            int n = list_n[l];
-            float val = __ldg(vsrc + (long long)n * p.C);
-            tile[v * p.CCp + c] = __fadd_rn(tile[v * p.CCp + c], val);
+            tile[v * p.CCp + c] = __fadd_rn(tile[v * p.CCp + c], stage[l * p.CCp + c]);
             if (c == 0) cnt[v] += 1;
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
-  // ---- write the tile: every output element exactly once, coalesced along v
-  const bool any = s_any != 0;
-  float* out = p.matrix + ((long long)b * p.C + c0) * p.V + vbase;
-  if (!any) {
-    const bool vec = ((p.V & 3) == 0) && ((vt & 3) == 0) && ((vbase & 3) == 0);
-    if (vec) {
-      const int vt4 = vt >> 2;
-      for (int e = tid; e < cc * vt4; e += kThreads) {
-        int ch = e / vt4, v4 = e - ch * vt4;
-        __stcs(reinterpret_cast<float4*>(out + (long long)ch * p.V) + v4,
-               make_float4(0.f, 0.f, 0.f, 0.f));
-      }
+  // ---- write the tile: every output element exactly once, coalesced along v.
+  // thread <-> voxel (no integer division in the loop; the count is read once)
+  for (int v = tid; v < vt; v += kThreads) {
+    const int n = cnt[v];
+    const float fn = (float)n;
+    const float* row = tile + v * p.CCp;
+    float* o = out + v;
+    if (n > 0) {
+      for (int ch = 0; ch < cc; ++ch) __stcs(o + (long long)ch * p.V, __fdiv_rn(row[ch], fn));
     } else {
-      for (int e = tid; e < cc * vt; e += kThreads) {
-        int ch = e / vt, v = e - ch * vt;
-        out[(long long)ch * p.V + v] = 0.f;
-      }
-    }
-  } else {
-    for (int e = tid; e < cc * vt; e += kThreads) {
-      int ch = e / vt, v = e - ch * vt;
-      int n = cnt[v];
-      float s = tile[v * p.CCp + ch];
-      __stcs(out + (long long)ch * p.V + v, n > 0 ? __fdiv_rn(s, (float)n) : 0.f);
+#pragma unroll 8
+      for (int ch = 0; ch < cc; ++ch) __stcs(o + (long long)ch * p.V, 0.f);
     }
   }
   if (chunk == 0) {
     int* oc = p.counts + (long long)b * p.V + vbase;
-    for (int v = tid; v < vt; v += kThreads) oc[v] = any ? cnt[v] : 0;
+    for (int v = tid; v < vt; v += kThreads) oc[v] = cnt[v];
   }
 }
 
@@ -273,10 +416,21 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 using namespace mf;
 
+// workspace layout (T = voxel tiles of this call, W = B*V/32 bitmap words):
+//   region A, memset 0xFF : hdr[4] | seg_start[B] | seg_end[B]          (reserved: 4 + 2*65536 ints)
+//   region B, memset 0x00 : flags | tile_list_n | done | mode | tile_count[T] | occ_bits[W]
+//                                                           (reserved: 4 + 2^20 + 2^21 ints)
+//   tile_list[2^20] | keys[N]
+constexpr size_t kWsA = (4 + 2 * 65536) * sizeof(int);
+constexpr size_t kMaxTiles = 1 << 20;
+constexpr size_t kMaxBitWords = 1 << 21;                     // B*V <= 2^26 voxels
+constexpr size_t kWsListOff = kWsA + (4 + kMaxTiles + kMaxBitWords) * sizeof(int);
+constexpr size_t kWsKeysOff = kWsListOff + kMaxTiles * sizeof(int);
+
+extern "C" size_t mf_average_voxelization_3d_flags_offset(void) { return kWsA; }
+
 extern "C" size_t mf_average_voxelization_3d_workspace_bytes(int64_t n_points) {
-  // hdr[4] + seg_start/end for up to 65536 batches are carved from a fixed 512 KiB
-  // header so the size depends on n_points only.
-  return (size_t)(512 * 1024) + align_up((size_t)(n_points > 0 ? n_points : 1) * 4, 256);
+  return kWsKeysOff + align_up((size_t)(n_points > 0 ? n_points : 1) * 4, 256);
 }
 
 extern "C" int mf_average_voxelization_3d_fwd(
@@ -293,20 +447,38 @@ extern "C" int mf_average_voxelization_3d_fwd(
   if (B > 65535) return MF_E_TOOLARGE;
   if (workspace_bytes < mf_average_voxelization_3d_workspace_bytes(N)) return MF_E_WORKSPACE;
 
+  AvgParams p;
+  p.VT = 256;
+  if (V < 256) p.VT = (int)V;
+  p.tiles_per_batch = (int)((V + p.VT - 1) / p.VT);
+  if ((long long)p.tiles_per_batch * B > (1 << 20)) return MF_E_TOOLARGE;
+
   int* hdr = (int*)workspace;
   int* seg_start = hdr + 4;
-  int* seg_end = seg_start + 65536;
-  int* keys = (int*)((char*)workspace + 512 * 1024);
-  // hdr = all ones (sorted bit set), seg_* = -1 (empty)
-  MF_CUDA_TRY(cudaMemsetAsync(hdr, 0xFF, (4 + (size_t)B) * sizeof(int), stream));
-  MF_CUDA_TRY(cudaMemsetAsync(seg_end, 0xFF, (size_t)B * sizeof(int), stream));
+  int* seg_end = seg_start + B;
+  int* regB = (int*)((char*)workspace + kWsA);
+  int* flags2 = regB;            // internal copy of the flag word (workspace-resident)
+  int* tile_list_n = regB + 1;
+  int* done = regB + 2;
+  int* mode = regB + 3;
+  int* tile_count = regB + 4;
+  const long long n_tiles_ws = (long long)p.tiles_per_batch * B;
+  const bool bitmap_ok = (V * B <= (1LL << 26)) && (V % 256 == 0);
+  unsigned int* occ_bits = bitmap_ok ? (unsigned int*)(tile_count + n_tiles_ws) : nullptr;
+  const size_t bits_words = bitmap_ok ? (size_t)(V * B / 32) : 0;
+  int* tile_list = (int*)((char*)workspace + kWsListOff);
+  int* keys = (int*)((char*)workspace + kWsKeysOff);
+  // hdr = all ones (sorted bit set), seg_* = -1 (empty); flags/counter/tile counts = 0
+  MF_CUDA_TRY(cudaMemsetAsync(hdr, 0xFF, (4 + 2 * (size_t)B) * sizeof(int), stream));
+  MF_CUDA_TRY(cudaMemsetAsync(regB, 0, (4 + (size_t)n_tiles_ws + bits_words) * sizeof(int), stream));
   VoxGeom g{ox, oy, oz, pitch, X, Y, Z, B};
   if (N > 0) {
     k_vox_keys<<<div_up(N, 256), 256, 0, stream>>>(points, batch_indices, N, g, keys, hdr,
-                                                   seg_start, seg_end, flags);
+                                                   seg_start, seg_end, flags, tile_count, p.VT,
+                                                   flags2, tile_list, tile_list_n, occ_bits, done,
+                                                   mode);
     MF_LAUNCH_CHECK();
   }
-  AvgParams p;
   p.values = values; p.keys = keys; p.hdr = hdr; p.seg_start = seg_start; p.seg_end = seg_end;
   p.N = N; p.C = C; p.B = B; p.V = (int)V;
   int nChunks = (C + 63) / 64;
@@ -316,19 +488,44 @@ extern "C" int mf_average_voxelization_3d_fwd(
   p.G = kThreads / p.CC;
   if (p.G < 1) p.G = 1;
   if (p.G > 32) p.G = 32;
-  p.VT = 256;
-  if (V < 256) p.VT = (int)V;
   p.matrix = matrix; p.counts = counts;
-  size_t smem = (size_t)p.VT * p.CCp * 4 + (size_t)p.VT * 4 + (size_t)kListCap * 8;
+  p.tile_count = tile_count; p.tile_list = tile_list; p.tile_list_n = tile_list_n;
+  p.n_chunks = nChunks;
+  const long long n_tiles = (long long)p.tiles_per_batch * B;
+  p.n_items = (int)n_tiles;
+  size_t smem = (size_t)p.VT * p.CCp * 4 + (size_t)p.VT * 4 + (size_t)kListCap * 8 +
+                (size_t)kStage * p.CCp * 4;
   static bool attr_set = false;
   if (!attr_set) {
     MF_CUDA_TRY(cudaFuncSetAttribute(k_avg_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      100 * 1024));
     attr_set = true;
   }
-  dim3 grid(div_up(V, p.VT), nChunks, B);
-  k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
-  MF_LAUNCH_CHECK();
+  p.occ_bits = occ_bits; p.mode = mode;
+  const bool sparse_ok = bitmap_ok && (p.VT == 256) && C <= 256 && N > 0;
+  if (sparse_ok) {
+    // A: fused zero stream + (fast mode) per-point leader scatter; B: occupied tiles (general mode)
+    p.zero_groups = (C + 1 + kZeroRowsPerCta - 1) / kZeroRowsPerCta;
+    const long long n_fill = n_tiles * p.zero_groups;
+    const long long n_lead = (N * 32 + 255) / 256;
+    if (n_fill + n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
+    p.n_fill_ctas = (int)n_fill;
+    k_avg_fill_scatter<<<(unsigned)(n_fill + n_lead), 256, 0, stream>>>(p);
+    MF_LAUNCH_CHECK();
+    long long occ_max = n_tiles < N ? n_tiles : N;             // at most one new tile per point
+    if (occ_max > 0) {
+      dim3 grid((unsigned)occ_max, nChunks, 1);
+      k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
+      MF_LAUNCH_CHECK();
+    }
+  } else {
+    // ragged shapes: every tile through the shared-memory path
+    p.tile_list = nullptr;
+    p.mode = nullptr;
+    dim3 grid((unsigned)n_tiles, nChunks, 1);
+    k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
+    MF_LAUNCH_CHECK();
+  }
   return MF_OK;
 }
 

@@ -26,15 +26,15 @@ class AverageVoxelization3D(torch.autograd.Function):
         with torch.cuda.device(dev):
             matrix = torch.empty((B, C, X, Y, Z), dtype=torch.float32, device=dev)
             counts = torch.empty((B, X, Y, Z), dtype=torch.int32, device=dev)
-            flags = torch.zeros(1, dtype=torch.int32, device=dev)
             nws = L.mf_average_voxelization_3d_workspace_bytes(N)
             ws = _util.workspace(nws, dev)
             rc = L.mf_average_voxelization_3d_fwd(
                 _lib.ptr(values), _lib.ptr(points), _lib.ptr(batch_indices), N, C, B,
                 *origin, pitch, X, Y, Z, _lib.ptr(matrix), _lib.ptr(counts),
-                _lib.ptr(ws), ws.numel(), _lib.ptr(flags), _lib.stream())
+                _lib.ptr(ws), ws.numel(), None, _lib.stream())
         _lib.check(rc, "average_voxelization_3d")
-        _util.raise_on_flags(flags)
+        off = L.mf_average_voxelization_3d_flags_offset()
+        _util.raise_on_flags(ws[off:off + 4].view(torch.int32))
         ctx.save_for_backward(points, batch_indices, counts)
         ctx.geom = (B, origin, pitch, dimensions)
         ctx.mark_non_differentiable(counts)
