@@ -283,7 +283,8 @@ size_t mf_icc_workspace_bytes(int n_objects_total, int voxel_dim, int n_scenes, 
 int mf_icc_run(int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold,
                float sdf_offset, const int32_t* scene_obj_off, const int32_t* obj_pt_off,
                const int32_t* scene_chunk_off, const int32_t* chunk_obj,
-               const int32_t* chunk_start, const int32_t* scene_slot_off, int n_slots,
+               const int32_t* chunk_start, const int32_t* scene_slot_off,
+               const int32_t* obj_chunk_off /*[N+1] first chunk of each object*/, int n_slots,
                const float* points, const float* sdf, const float* pitch, const float* origin,
                const float* grid_target, const float* grid_nontarget_empty, float* quaternion,
                float* translation, float* adam_state, int n_iter, int update,

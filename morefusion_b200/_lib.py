@@ -58,7 +58,7 @@ SIGNATURES = {
     "mf_cnn_pose": (c_i, [c_p] * 7 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "mf_icc_max_group_size": (c_i, [c_i]),
     "mf_icc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
-    "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 6 + [c_i] + [c_p] * 9
+    "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
                    + [c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_p, c_sz, c_p]),
 }
 

@@ -41,6 +41,7 @@ class _Problem:
         pts, sdf, pitch, origin, gt, gne = [], [], [], [], [], []
         scene_obj_off, obj_pt_off = [0], [0]
         scene_chunk_off, chunk_obj, chunk_start, scene_slot_off = [0], [], [], [0]
+        obj_chunk_off = [0]
         V = voxel_dim ** 3
         for sc in scenes:
             n = len(sc["points"])
@@ -61,6 +62,7 @@ class _Problem:
                     chunk_start.append(start + c * CHUNK)
                     n_chunks += 1
                 obj_pt_off.append(start + P)
+                obj_chunk_off.append(len(chunk_obj))
             scene_obj_off.append(o0 + n)
             scene_chunk_off.append(scene_chunk_off[-1] + n_chunks)
             scene_slot_off.append(scene_slot_off[-1] + n * n_chunks)
@@ -76,6 +78,7 @@ class _Problem:
         self.scene_obj_off, self.obj_pt_off = i32(scene_obj_off), i32(obj_pt_off)
         self.scene_chunk_off, self.chunk_obj = i32(scene_chunk_off), i32(chunk_obj)
         self.chunk_start, self.scene_slot_off = i32(chunk_start), i32(scene_slot_off)
+        self.obj_chunk_off = i32(obj_chunk_off)
         self.points = torch.cat(pts).contiguous()
         self.sdf = torch.cat(sdf).contiguous()
         self.pitch = torch.cat(pitch).contiguous()
@@ -107,7 +110,7 @@ def _run(prob, quaternion, translation, adam_state, *, n_iter, update, alpha_q, 
             prob.S, prob.Ntot, prob.voxel_dim, float(voxel_threshold), float(sdf_offset),
             _lib.ptr(prob.scene_obj_off), _lib.ptr(prob.obj_pt_off), _lib.ptr(prob.scene_chunk_off),
             _lib.ptr(prob.chunk_obj), _lib.ptr(prob.chunk_start), _lib.ptr(prob.scene_slot_off),
-            prob.n_slots, _lib.ptr(prob.points), _lib.ptr(prob.sdf), _lib.ptr(prob.pitch),
+            _lib.ptr(prob.obj_chunk_off), prob.n_slots, _lib.ptr(prob.points), _lib.ptr(prob.sdf), _lib.ptr(prob.pitch),
             _lib.ptr(prob.origin), _lib.ptr(prob.grid_target), _lib.ptr(prob.gne),
             _lib.ptr(quaternion), _lib.ptr(translation), _lib.ptr(adam_state), n_iter,
             int(update), ctypes.cast(aq, ctypes.c_void_p), ctypes.cast(at, ctypes.c_void_p),

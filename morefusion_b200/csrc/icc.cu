@@ -40,6 +40,7 @@ struct IccParams {
   const int* chunk_obj;        // [Ctot] global object id of each 256-point chunk
   const int* chunk_start;      // [Ctot] global index of the chunk's first point
   const int* scene_slot_off;   // [S+1] prefix of N_s * C_s
+  const int* obj_chunk_off;    // [Ntot+1] first chunk of every object (chunks of an object are contiguous)
   const float* points;         // [Ptot,3] CAD frame
   const float* sdf;            // [Ptot]
   const float* pitch;          // [Ntot]
@@ -414,16 +415,12 @@ k_icc_run(IccParams p, IccAlpha alpha) {
       if (tid < 32) {
         int gj = sc.o0 + jl;
         // chunks of object j are contiguous in the chunk table
-        int cj0 = -1, cj1 = -1;
-        for (int c = 0; c < sc.C; ++c) {
-          int o = p.chunk_obj[sc.c0 + c];
-          if (o == gj) { if (cj0 < 0) cj0 = c; cj1 = c + 1; }
-        }
+        const int cj0 = p.obj_chunk_off[gj] - sc.c0, cj1 = p.obj_chunk_off[gj + 1] - sc.c0;
         float a[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = 0.f;
         int nc = cj1 - cj0;
-        if (cj0 >= 0)
+        if (nc > 0)
           for (int e = tid; e < sc.N * nc; e += 32) {
             int il = e / nc, cl = cj0 + (e - il * nc);
             const float* slot = p.slots + ((size_t)sc.slot0 + (size_t)il * sc.C + cl) * 12;
@@ -528,7 +525,8 @@ extern "C" size_t mf_icc_workspace_bytes(int n_objects_total, int voxel_dim, int
 extern "C" int mf_icc_run(
     int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold, float sdf_offset,
     const int32_t* scene_obj_off, const int32_t* obj_pt_off, const int32_t* scene_chunk_off,
-    const int32_t* chunk_obj, const int32_t* chunk_start, const int32_t* scene_slot_off, int n_slots,
+    const int32_t* chunk_obj, const int32_t* chunk_start, const int32_t* scene_slot_off,
+    const int32_t* obj_chunk_off, int n_slots,
     const float* points, const float* sdf, const float* pitch, const float* origin,
     const float* grid_target, const float* grid_nontarget_empty,
     float* quaternion, float* translation, float* adam_state,
@@ -540,7 +538,7 @@ extern "C" int mf_icc_run(
   if (n_scenes <= 0 || n_objects_total <= 0 || voxel_dim <= 0 || n_iter <= 0 || n_iter > 128)
     return MF_E_BADARG;
   if (!scene_obj_off || !obj_pt_off || !scene_chunk_off || !chunk_obj || !chunk_start ||
-      !scene_slot_off || !points || !sdf || !pitch || !origin || !grid_target ||
+      !scene_slot_off || !obj_chunk_off || !points || !sdf || !pitch || !origin || !grid_target ||
       !grid_nontarget_empty || !quaternion || !translation || !loss_history || !grads || !workspace)
     return MF_E_BADARG;
   if (update && (!adam_state || !alpha_q_host || !alpha_t_host)) return MF_E_BADARG;
@@ -555,6 +553,7 @@ extern "C" int mf_icc_run(
   p.S = n_scenes; p.D = voxel_dim; p.threshold = voxel_threshold; p.sdf_offset = sdf_offset;
   p.scene_obj_off = scene_obj_off; p.obj_pt_off = obj_pt_off; p.scene_chunk_off = scene_chunk_off;
   p.chunk_obj = chunk_obj; p.chunk_start = chunk_start; p.scene_slot_off = scene_slot_off;
+  p.obj_chunk_off = obj_chunk_off;
   p.points = points; p.sdf = sdf; p.pitch = pitch; p.origin = origin;
   p.grid_target = grid_target; p.gne = grid_nontarget_empty;
   p.q = quaternion; p.t = translation; p.adam = adam_state;

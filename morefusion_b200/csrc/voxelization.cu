@@ -26,6 +26,7 @@ struct VoxGeom {
 };
 
 constexpr int kLeaderMaxSeg = 4096;      // longest batch segment the per-point leader path scans
+constexpr int kLeaderSmemKeys = 8192;    // keys a leader CTA can stage in shared memory
 
 __device__ __forceinline__ void vox_keys_point(
     const float* __restrict__ points, const int* __restrict__ bi, long long N, VoxGeom g,
@@ -127,7 +128,7 @@ struct AvgParams {
   const int* tile_list_n;
   const unsigned int* occ_bits;   // one bit per (b, voxel): some point falls into it
   const int* mode;         // 1 = fast (leader scatter), 0 = general (tile kernel)
-  int n_fill_ctas, zero_groups;
+  int n_fill_ctas, n_lead_ctas, zero_groups;
   int tiles_per_batch, n_chunks, n_items;
 };
 
@@ -137,50 +138,72 @@ struct AvgParams {
 //   fill role   : no shared memory, no integer division in the loop, 16-byte streaming stores
 //   leader role : one warp per point; the lowest-index point of a voxel sums the voxel's
 //                 points in ascending order (lanes over channels), divides, writes C values+count
-constexpr int kZeroRowsPerCta = 32;
 __global__ void __launch_bounds__(256)
 k_avg_fill_scatter(AvgParams p) {
   const int fast = __ldg(p.mode);
-  if ((int)blockIdx.x < p.n_fill_ctas) {
-    const int tile = blockIdx.x / p.zero_groups, grp = blockIdx.x - tile * p.zero_groups;
-    const int npts = __ldg(p.tile_count + tile);
-    if (!fast && npts != 0) return;                        // general mode: the tile kernel owns it
-    const int b = tile / p.tiles_per_batch, ti = tile - b * p.tiles_per_batch;
-    const int vt4 = p.VT >> 2;
-    const int r0 = grp * kZeroRowsPerCta;
-    const int r1 = min(r0 + kZeroRowsPerCta, p.C + 1);     // C channel planes + the counts plane
+  __shared__ int skeys[kLeaderSmemKeys];
+  if ((int)blockIdx.x >= p.n_lead_ctas) {
+    // fill role: the output is walked LINEARLY (plane by plane, 16 KiB per CTA) so that L2
+    // write-back sees long contiguous runs, like a plain fill kernel
+    const int fid = blockIdx.x - p.n_lead_ctas;
+    const int plane = fid / p.zero_groups, seg = fid - plane * p.zero_groups;
+    const int b = plane / (p.C + 1), c = plane - b * (p.C + 1);
+    float* base = (c < p.C) ? p.matrix + ((long long)b * p.C + c) * p.V
+                            : reinterpret_cast<float*>(p.counts) + (long long)b * p.V;
+    const unsigned int* bits = p.occ_bits + (((long long)b * p.V) >> 5);
+    const int* tcount = p.tile_count + b * p.tiles_per_batch;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long voff = (long long)ti * p.VT;
-    const unsigned int* bits = p.occ_bits + (((long long)b * p.V + voff) >> 5);
-    for (int e = threadIdx.x; e < (r1 - r0) * vt4; e += 256) {
-      int r = r0 + e / vt4, v4 = e % vt4;
-      float* dst = (r < p.C) ? p.matrix + ((long long)b * p.C + r) * p.V + voff
-                             : reinterpret_cast<float*>(p.counts) + (long long)b * p.V + voff;
-      unsigned int m = 0;
-      if (npts != 0) m = (__ldg(bits + (v4 >> 3)) >> ((v4 & 7) * 4)) & 0xFu;
-      if (m == 0) {
-        __stcs(reinterpret_cast<float4*>(dst) + v4, z4);
-      } else {
+    // all lookups first (independent loads in flight together), then the stores
+    int npts[4];
+    unsigned int mm[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx4 = seg * 1024 + k * 256 + threadIdx.x;          // float4 index in the plane
+      npts[k] = __ldg(tcount + (idx4 >> 6));                        // VT == 256: 64 float4 / tile
+      mm[k] = (__ldg(bits + (idx4 >> 3)) >> ((idx4 & 7) * 4)) & 0xFu;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx4 = seg * 1024 + k * 256 + threadIdx.x;
+      if (npts[k] == 0 || (fast && mm[k] == 0)) {
+        __stcs(reinterpret_cast<float4*>(base) + idx4, z4);
+      } else if (fast) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (!((m >> j) & 1)) dst[4 * v4 + j] = 0.f;
-      }
+          if (!((mm[k] >> j) & 1)) base[4 * idx4 + j] = 0.f;
+      }                                                             // general mode: tile kernel owns it
     }
     return;
   }
   if (!fast) return;
-  // ---- leader role
-  const long long n = ((long long)(blockIdx.x - p.n_fill_ctas) * 256 + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  // ---- leader role (these CTAs come FIRST in the grid so that they overlap the zero stream).
+  // The CTA's 8 points lie in at most a few batch segments; their keys are staged in shared
+  // memory once and every warp scans them from there.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_first = (long long)blockIdx.x * 8;
+  const long long n_last = min(n_first + 7, p.N - 1);
+  int k_first = -1, k_last = -1;                            // first / last valid key of the CTA
+  for (long long j = n_first; j <= n_last; ++j) {
+    int kk = __ldg(p.keys + j);
+    if (kk >= 0) { if (k_first < 0) k_first = kk; k_last = kk; }
+  }
+  if (k_first < 0) return;                                  // uniform: all 8 points out of bounds
+  const int s_lo = __ldg(p.seg_start + k_first / p.V), s_hi = __ldg(p.seg_end + k_last / p.V);
+  const bool staged = (s_hi - s_lo) <= kLeaderSmemKeys;
+  if (staged)
+    for (int e = threadIdx.x; e < s_hi - s_lo; e += 256) skeys[e] = __ldg(p.keys + s_lo + e);
+  __syncthreads();
+  const long long n = n_first + warp;
   if (n >= p.N) return;
-  const int key = __ldg(p.keys + n);
+  const int key = staged ? skeys[n - s_lo] : __ldg(p.keys + n);
   if (key < 0) return;
   const int b = key / p.V;
   const int lo = __ldg(p.seg_start + b), hi = __ldg(p.seg_end + b);
+  const int nn = (int)n;
   bool earlier = false;
-  for (int j0 = lo; j0 < n && !earlier; j0 += 32) {
+  for (int j0 = lo; j0 < nn && !earlier; j0 += 32) {
     int j = j0 + lane;
-    bool m = (j < n) && (__ldg(p.keys + j) == key);
+    bool m = (j < nn) && ((staged ? skeys[j - s_lo] : __ldg(p.keys + j)) == key);
     earlier = __any_sync(0xffffffffu, m);
   }
   if (earlier) return;
@@ -188,10 +211,9 @@ k_avg_fill_scatter(AvgParams p) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   int count = 0;
-  const int nn = (int)n;
   for (int j0 = nn - (nn - lo) % 32; j0 < hi; j0 += 32) {   // aligned chunks: j ascends
     int j = j0 + lane;
-    bool m = (j >= nn) && (j < hi) && (__ldg(p.keys + j) == key);
+    bool m = (j >= nn) && (j < hi) && ((staged ? skeys[j - s_lo] : __ldg(p.keys + j)) == key);
     unsigned mask = __ballot_sync(0xffffffffu, m);
     while (mask) {
       int l = __ffs(mask) - 1;
@@ -502,14 +524,15 @@ extern "C" int mf_average_voxelization_3d_fwd(
     attr_set = true;
   }
   p.occ_bits = occ_bits; p.mode = mode;
-  const bool sparse_ok = bitmap_ok && (p.VT == 256) && C <= 256 && N > 0;
+  const bool sparse_ok = bitmap_ok && (p.VT == 256) && (V % 4096 == 0) && C <= 256 && N > 0;
   if (sparse_ok) {
     // A: fused zero stream + (fast mode) per-point leader scatter; B: occupied tiles (general mode)
-    p.zero_groups = (C + 1 + kZeroRowsPerCta - 1) / kZeroRowsPerCta;
-    const long long n_fill = n_tiles * p.zero_groups;
+    p.zero_groups = (int)((V / 4 + 1023) / 1024);            // 16 KiB segments per plane
+    const long long n_fill = (long long)B * (C + 1) * p.zero_groups;
     const long long n_lead = (N * 32 + 255) / 256;
     if (n_fill + n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
     p.n_fill_ctas = (int)n_fill;
+    p.n_lead_ctas = (int)n_lead;
     k_avg_fill_scatter<<<(unsigned)(n_fill + n_lead), 256, 0, stream>>>(p);
     MF_LAUNCH_CHECK();
     long long occ_max = n_tiles < N ? n_tiles : N;             // at most one new tile per point
