@@ -292,6 +292,22 @@ int mf_icc_run(int n_scenes, int n_objects_total, int voxel_dim, float voxel_thr
                float eps, float eta, float* loss_history, float* grads, int group_size,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * a12  average_distance (ADD / ADD-S training loss) + nearest neighbour
+ *     replaces morefusion/functions/loss/average_distance.py:40-85 and, for symmetric=1,
+ *     morefusion/geometry/knn/nn.py:17-48 + cuComputeDistanceGlobal.cu:20-86 (matrix-free here)
+ * points [P,3], transform_true [4,4], transforms_pred [M,4,4] -> out [M];
+ * nn_indices [M,P] int32 (may be NULL when symmetric == 0) is kept for the backward pass.
+ * ------------------------------------------------------------------------ */
+int mf_average_distance_fwd(const float* points, int n_points, const float* transform_true,
+                            const float* transforms_pred, int n_pred, int symmetric, float* out,
+                            int32_t* nn_indices, void* stream);
+int mf_average_distance_bwd(const float* gout, const float* points, int n_points,
+                            const float* transform_true, const float* transforms_pred, int n_pred,
+                            const int32_t* nn_indices /*NULL: identity*/,
+                            float* g_transforms_pred /*[M,4,4]*/, float* g_transform_true /*[4,4]*/,
+                            float* workspace /*[n_pred,12] floats*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ SOURCES = {
     "tdf.cu": ["-fmad=false"],
     "transforms.cu": ["-fmad=false"],
     "icc.cu": ["-fmad=false"],
+    "loss.cu": ["-fmad=false"],
     "cnn.cu": [],
     "conv3d_tc.cu": [],
 }

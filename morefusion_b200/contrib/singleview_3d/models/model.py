@@ -296,8 +296,10 @@ class Model(torch.nn.Module):
             else:
                 # unfused reference composition: the public operator + an explicit pack
                 pts_np = st["points"].permute(0, 2, 1).reshape(B * P, 3).contiguous()
-                vox, _ = AverageVoxelization3D.apply(
-                    buf["feat2"], pts_np, buf["bi"], B, (0.0, 0.0, 0.0), 1.0, (D, D, D))
+                from .... import config
+                with config.no_nan_check():      # inputs are the model's own activations
+                    vox, _ = AverageVoxelization3D.apply(
+                        buf["feat2"], pts_np, buf["bi"], B, (0.0, 0.0, 0.0), 1.0, (D, D, D))
                 self.n_launches += 2
                 hocc = None
                 if self._with_occupancy:
@@ -407,8 +409,6 @@ class Runner:
         self.launches_per_step = m.n_launches - n0
 
     def _capture(self):
-        from .... import config
-        config.check_nan = False
         m = self.model
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

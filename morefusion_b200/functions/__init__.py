@@ -10,3 +10,5 @@ from .geometry import transform_points  # noqa: F401
 from .geometry import transformation_matrix  # noqa: F401
 from .geometry import translation_matrix  # noqa: F401
 from .geometry import truncated_distance_function  # noqa: F401
+
+from .loss import average_distance  # noqa: F401

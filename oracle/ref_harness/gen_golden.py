@@ -276,8 +276,38 @@ def gen_icc():
         _save("icc_forward_" + name, **out)
 
 
+# ---------------------------------------------------------------- average_distance loss
+def gen_average_distance():
+    shim.load_functions_namespace()
+    shim.set_mode("cpu")
+    m = shim.ref_module("functions.loss.average_distance")
+    rs = np.random.RandomState(11)
+    # mirrors tests/functions_tests/loss_tests/test_average_distance.py:13-21 (128 points, 5 preds)
+    P, M = 128, 5
+
+    def rand_T():
+        q = rs.normal(size=4); q /= np.linalg.norm(q)
+        w, x, y, z = q
+        T = np.eye(4)
+        T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        T[:3, 3] = rs.uniform(-1, 1, 3)
+        return T.astype(F32)
+    points = rs.uniform(-1, 1, (P, 3)).astype(F32)
+    T1 = rand_T()
+    T2 = np.stack([rand_T() for _ in range(M)])
+    T2[0] = T1                       # identical pose: distance exactly 0
+    T2[1, :3, 3] = T1[:3, 3]; T2[1, :3, :3] = T1[:3, :3] @ np.diag([1, -1, -1]).astype(F32)  # 180 deg flip
+    out = dict(points=points, T1=T1, T2=T2)
+    out["ref_add"] = np.asarray(m.average_distance(points, T1, T2, symmetric=False))
+    out["ref_add_s"] = np.asarray(m.average_distance(points, T1, T2, symmetric=True))
+    _save("average_distance", **out)
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
+    gen_average_distance()
     gen_voxelization()
     gen_interpolate()
     gen_tdf()

@@ -373,12 +373,21 @@ def install():
     for name, sub in [
         ("morefusion", ""), ("morefusion.functions", "functions"),
         ("morefusion.functions.geometry", "functions/geometry"),
-        ("morefusion.contrib", "contrib"),
+        ("morefusion.contrib", "contrib"), ("morefusion.functions.loss", "functions/loss"),
     ]:
         pkg = types.ModuleType(name)
         pkg.__path__ = [os.path.join(base, sub)]
         pkg.__package__ = name
         sys.modules[name] = pkg
+    # morefusion.geometry: only `nn` is touched (functions/loss/average_distance.py:77); its
+    # __init__ imports open3d & co.  Stand-in = the body of the reference's CPU path
+    # (geometry/knn/nn.py:11-14: sklearn KD-tree, first neighbour).
+    import sklearn.neighbors
+    geo = types.ModuleType("morefusion.geometry")
+    geo.nn = lambda ref, query: sklearn.neighbors.KDTree(np.asarray(ref)).query(
+        np.asarray(query), return_distance=False)[:, 0]
+    sys.modules["morefusion.geometry"] = geo
+    sys.modules["morefusion"].geometry = geo
     _INSTALLED = True
 
 
@@ -399,4 +408,5 @@ def load_functions_namespace():
     tdf = ref_module(g + "truncated_distance_function")
     fm.pseudo_occupancy_voxelization = tdf.pseudo_occupancy_voxelization
     fm.truncated_distance_function = tdf.truncated_distance_function
+    sys.modules["morefusion.functions.geometry"].transform_points = fm.transform_points
     return fm

@@ -85,8 +85,6 @@ def test_fused_voxelize_equals_operator_composition(cuda_device):
     in place) produces bit-identical conv3 input to average_voxelization_3d + occ convs + pack,
     across consecutive calls with different inputs (exercises the sparse re-zeroing)."""
     from morefusion_b200.contrib.singleview_3d.models import Model
-    import morefusion_b200 as mf
-    mf.config.check_nan = False
     B = 3
     w = ocnn.init_weights(21, seed=2)
     m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)

@@ -277,3 +277,52 @@ def test_transform_points_backward(cuda_device):
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(pts.grad, p2.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(T.grad[:, :3], T2.grad[:, :3], rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------ a12
+def test_average_distance_golden_and_grad(cuda_device):
+    from oracle import loss as oloss
+    g = golden("average_distance")
+    f = F()
+    pts = cu(g["points"], cuda_device)
+    for sym, key in ((False, "ref_add"), (True, "ref_add_s")):
+        T1 = cu(g["T1"], cuda_device).requires_grad_(True)
+        T2 = cu(g["T2"], cuda_device).requires_grad_(True)
+        out = f.average_distance(pts, T1, T2, symmetric=sym)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), g[key], rtol=1e-6, atol=1e-7)
+        # rows 2.. have non-zero distances everywhere (row 0 is the identical pose: sqrt'(0) = inf)
+        go = np.zeros(5, F32)
+        go[2:] = np.array([0.5, -1.0, 2.0], F32)
+        want = oloss.average_distance(g["points"], g["T1"], g["T2"][2:], symmetric=sym,
+                                      return_grads=True, gout=go[2:])
+        out2 = f.average_distance(pts, T1, T2[2:], symmetric=sym)
+        out2.backward(cu(go[2:], cuda_device))
+        np.testing.assert_allclose(T2.grad[2:].cpu().numpy(), want[1], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(T1.grad.cpu().numpy(), want[2], rtol=1e-4, atol=1e-4)
+
+
+def test_average_distance_training_shape(cuda_device):
+    """Training-like shape (model.py:417,429: 500 CAD points per object, one pose per point),
+    symmetric: the matrix-free NN equals a brute-force argmin over exact fp32 squared distances
+    (torch.cdist's |a|^2+|b|^2-2ab expansion flips near-ties); gradients equal torch autograd."""
+    torch.manual_seed(0)
+    P, M = 500, 200
+    pts = torch.rand(P, 3, device=cuda_device) * 0.2 - 0.1
+    def rand_T(n):
+        q = torch.randn(n, 4, device=cuda_device)
+        T = F().transformation_matrix(q, torch.rand(n, 3, device=cuda_device) * 0.02)
+        return T
+    Tt = rand_T(1)[0].detach().requires_grad_(True)
+    Tp = (rand_T(M).detach() * 1.0).requires_grad_(True)
+    out = F().average_distance(pts, Tt, Tp, symmetric=True)
+    out.sum().backward()
+    Tt2, Tp2 = Tt.detach().clone().requires_grad_(True), Tp.detach().clone().requires_grad_(True)
+    a = pts @ Tt2[:3, :3].T + Tt2[:3, 3]
+    b = torch.einsum("mij,pj->mpi", Tp2[:, :3, :3], pts) + Tp2[:, None, :3, 3]
+    diff = b.detach()[:, :, None, :] - a.detach()[None, None, :, :]
+    idx = ((diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]).argmin(2)
+    ref = (a[idx] - b).norm(dim=2).mean(1)
+    ref.sum().backward()
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(Tp.grad[:, :3], Tp2.grad[:, :3], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(Tt.grad[:3], Tt2.grad[:3], rtol=1e-3, atol=1e-2)

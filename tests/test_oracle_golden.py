@@ -295,3 +295,18 @@ def test_chainer_adam_first_step():
     gvec = np.array([1.0, -2.0, 0.5], F32)
     opt.update(p, gvec)
     np.testing.assert_allclose(p, -0.01 * np.sign(gvec), rtol=1e-4)
+
+
+def test_average_distance_loss():
+    from oracle import loss as oloss
+    from oracle import metrics as om
+    g = golden("average_distance")
+    add = oloss.average_distance(g["points"], g["T1"], g["T2"], symmetric=False)
+    adds = oloss.average_distance(g["points"], g["T1"], g["T2"], symmetric=True)
+    assert np.array_equal(add, g["ref_add"])                              # reference code, exact
+    np.testing.assert_allclose(adds, g["ref_add_s"], rtol=1e-6, atol=1e-7)
+    # the reference's own KAT (tests/functions_tests/loss_tests/test_average_distance.py:23-31):
+    # loss == metrics.average_distance ADD
+    for i in range(g["T2"].shape[0]):
+        want = om.average_distance(g["points"].astype(np.float64), g["T1"], g["T2"][i])[0]
+        np.testing.assert_allclose(add[i], want, rtol=1e-5, atol=1e-6)
