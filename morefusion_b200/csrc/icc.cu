@@ -161,7 +161,7 @@ __device__ __forceinline__ void point_in_grid(const float* R, const float* tt, f
 }
 
 // ------------------------------------------------------------------ the persistent kernel
-__global__ void __launch_bounds__(kIccThreads, 2)
+__global__ void __launch_bounds__(kIccThreads, 4)
 k_icc_run(IccParams p, IccAlpha alpha) {
   __shared__ float sR[kIccMaxObj][9];
   __shared__ float sT[kIccMaxObj][3];

@@ -128,7 +128,7 @@ struct AvgParams {
   const int* tile_list_n;
   const unsigned int* occ_bits;   // one bit per (b, voxel): some point falls into it
   const int* mode;         // 1 = fast (leader scatter), 0 = general (tile kernel)
-  int n_fill_ctas, n_lead_ctas, zero_groups;
+  int n_fill_ctas, n_lead_ctas, zero_groups, lead_stride;
   int tiles_per_batch, n_chunks, n_items;
 };
 
@@ -142,10 +142,17 @@ __global__ void __launch_bounds__(256)
 k_avg_fill_scatter(AvgParams p) {
   const int fast = __ldg(p.mode);
   __shared__ int skeys[kLeaderSmemKeys];
-  if ((int)blockIdx.x >= p.n_lead_ctas) {
+  // roles are interleaved along the grid (one leader CTA every `lead_stride` blocks) so that the
+  // latency-bound leader warps and the bandwidth-bound zero stream share every SM from the
+  // first wave to the last instead of running one after the other
+  const int q = blockIdx.x / p.lead_stride, r = blockIdx.x - q * p.lead_stride;
+  const bool is_lead = (r == 0) && (q < p.n_lead_ctas);
+  const int lead_id = q;
+  if (!is_lead) {
     // fill role: the output is walked LINEARLY (plane by plane, 16 KiB per CTA) so that L2
     // write-back sees long contiguous runs, like a plain fill kernel
-    const int fid = blockIdx.x - p.n_lead_ctas;
+    const int leaders_before = min(q + 1, p.n_lead_ctas);       // leader blocks with index < mine
+    const int fid = blockIdx.x - leaders_before;
     const int plane = fid / p.zero_groups, seg = fid - plane * p.zero_groups;
     const int b = plane / (p.C + 1), c = plane - b * (p.C + 1);
     float* base = (c < p.C) ? p.matrix + ((long long)b * p.C + c) * p.V
@@ -180,7 +187,7 @@ k_avg_fill_scatter(AvgParams p) {
   // The CTA's 8 points lie in at most a few batch segments; their keys are staged in shared
   // memory once and every warp scans them from there.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long n_first = (long long)blockIdx.x * 8;
+  const long long n_first = (long long)lead_id * 8;
   const long long n_last = min(n_first + 7, p.N - 1);
   int k_first = -1, k_last = -1;                            // first / last valid key of the CTA
   for (long long j = n_first; j <= n_last; ++j) {
@@ -533,6 +540,8 @@ extern "C" int mf_average_voxelization_3d_fwd(
     if (n_fill + n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
     p.n_fill_ctas = (int)n_fill;
     p.n_lead_ctas = (int)n_lead;
+    p.lead_stride = (int)((n_fill + n_lead) / n_lead);
+    if (p.lead_stride < 1) p.lead_stride = 1;
     k_avg_fill_scatter<<<(unsigned)(n_fill + n_lead), 256, 0, stream>>>(p);
     MF_LAUNCH_CHECK();
     long long occ_max = n_tiles < N ? n_tiles : N;             // at most one new tile per point
