@@ -164,7 +164,9 @@ __global__ void k_occ_fwd(const float* __restrict__ points, long long P, GridGeo
   long long V = (long long)g.X * g.Y * g.Z;
   long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int iz = (int)(v % g.Z), iy = (int)((v / g.Z) % g.Y), ix = (int)(v / ((long long)g.Y * g.Z));
-  float dmin = __int_as_float(0x7f800000);
+  // min_p sqrt(s_p) == sqrt(min_p s_p) bit-for-bit (correctly rounded sqrt is monotone), so the
+  // IEEE square root is taken once per voxel instead of once per (voxel, point)
+  float smin = __int_as_float(0x7f800000);
   for (long long base = 0; base < P; base += kOccTile) {
     int n = (int)min((long long)kOccTile, P - base);
     for (int e = threadIdx.x; e < n * 3; e += blockDim.x) {
@@ -174,14 +176,16 @@ __global__ void k_occ_fwd(const float* __restrict__ points, long long P, GridGeo
     }
     __syncthreads();
     if (v < V)
+#pragma unroll 4
       for (int j = 0; j < n; ++j) {
         float d0 = __fsub_rn((float)ix, sq[3 * j]), d1 = __fsub_rn((float)iy, sq[3 * j + 1]),
               d2 = __fsub_rn((float)iz, sq[3 * j + 2]);
-        dmin = fminf(dmin, __fsqrt_rn(sq3(d0, d1, d2)));
+        smin = fminf(smin, sq3(d0, d1, d2));
       }
     __syncthreads();
   }
   if (v < V) {
+    const float dmin = __fsqrt_rn(smin);
     dmin_out[v] = dmin;
     float m = fmaxf(__fsub_rn(threshold, dmin), 0.f);
     grid[v] = fminf(m, 1.f);
@@ -197,10 +201,11 @@ __global__ void k_occ_bwd(const float* __restrict__ ggrid, const float* __restri
   long long V = (long long)g.X * g.Y * g.Z;
   long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int iz = (int)(v % g.Z), iy = (int)((v / g.Z) % g.Y), ix = (int)(v / ((long long)g.Y * g.Z));
-  float dmin = 0.f, gd = 0.f;
+  float dmin = 0.f, gd = 0.f, s_hi = 0.f;
   bool active = false;
   if (v < V) {
     dmin = dmin_in[v];
+    s_hi = dmin * dmin * 1.000001f + 1e-30f;
     float r = __fsub_rn(threshold, dmin);
     active = (r > 0.f) && (r <= 1.f);
     gd = -ggrid[v];
@@ -217,7 +222,9 @@ __global__ void k_occ_bwd(const float* __restrict__ ggrid, const float* __restri
       for (int j = 0; j < n; ++j) {
         float d0 = __fsub_rn((float)ix, sq[3 * j]), d1 = __fsub_rn((float)iy, sq[3 * j + 1]),
               d2 = __fsub_rn((float)iz, sq[3 * j + 2]);
-        float d = __fsqrt_rn(sq3(d0, d1, d2));
+        const float s2 = sq3(d0, d1, d2);
+        if (s2 > s_hi) continue;                   // cannot round to dmin: skip the IEEE sqrt
+        float d = __fsqrt_rn(s2);
         if (d == dmin) {
           float inv = __fdiv_rn(gd, d);
           float* gp = gpoints + (base + j) * 3;
