@@ -29,6 +29,7 @@ namespace mf {
 
 constexpr int kIccThreads = 256;
 constexpr int kIccMaxObj = 32;
+constexpr int kIccMaxChunks = 1024;      // chunk tables staged in shared memory up to this many chunks / scene
 constexpr unsigned long long kKeyEmpty = 0xFFFFFFFFFFFFFFFFull;
 
 struct IccParams {
@@ -167,7 +168,14 @@ k_icc_run(IccParams p, IccAlpha alpha) {
   __shared__ float sT[kIccMaxObj][3];
   __shared__ float sred[8 * 12];
   __shared__ float stot[4];
-  __shared__ int sflag;
+  // per-scene constants staged once (they are read by every work item of every iteration)
+  __shared__ float sPitch[kIccMaxObj];
+  __shared__ float sOrigin[kIccMaxObj][3];
+  __shared__ int sPtEnd[kIccMaxObj];
+  __shared__ int sChunkObj[kIccMaxChunks];
+  __shared__ int sChunkStart[kIccMaxChunks];
+  // per-warp running sums of (gR | gt) per source object: no block barrier per work item
+  __shared__ float sAcc[kIccThreads / 32][kIccMaxObj][12];
 
   const int tid = threadIdx.x;
   const int scene = blockIdx.x / p.G, cta = blockIdx.x % p.G;
@@ -181,6 +189,20 @@ k_icc_run(IccParams p, IccAlpha alpha) {
   unsigned int* bar = p.barrier + scene;
   unsigned int epoch = 0;
   const int n_items = sc.N * sc.C;
+  const bool chunks_in_smem = sc.C <= kIccMaxChunks;
+  if (tid < sc.N) {
+    int o = sc.o0 + tid;
+    sPitch[tid] = p.pitch[o];
+    sOrigin[tid][0] = p.origin[3 * o]; sOrigin[tid][1] = p.origin[3 * o + 1]; sOrigin[tid][2] = p.origin[3 * o + 2];
+    sPtEnd[tid] = p.obj_pt_off[o + 1];
+  }
+  if (chunks_in_smem)
+    for (int e = tid; e < sc.C; e += kIccThreads) {
+      sChunkObj[e] = p.chunk_obj[sc.c0 + e];
+      sChunkStart[e] = p.chunk_start[sc.c0 + e];
+    }
+  __syncthreads();
+  const int warp_id = tid >> 5, lane_id = tid & 31;
 
   for (int it = 0; it < p.n_iter; ++it) {
     // ---- P0: rotations of this scene's objects (q, t may have been updated by other CTAs)
@@ -199,18 +221,18 @@ k_icc_run(IccParams p, IccAlpha alpha) {
 
     // ---- P1: scatter
     for (int w = cta; w < n_items; w += p.G) {
-      int il = w / sc.C, cc = sc.c0 + (w - il * sc.C);
+      int il = w / sc.C, cl = w - il * sc.C;
       int gi = sc.o0 + il;
-      int gj = p.chunk_obj[cc];
+      int gj = chunks_in_smem ? sChunkObj[cl] : p.chunk_obj[sc.c0 + cl];
       int jl = gj - sc.o0;
-      int pt = p.chunk_start[cc] + tid;
-      if (pt >= p.obj_pt_off[gj + 1]) continue;
-      float pitch = p.pitch[gi];
+      int pt = (chunks_in_smem ? sChunkStart[cl] : p.chunk_start[sc.c0 + cl]) + tid;
+      if (pt >= sPtEnd[jl]) continue;
+      float pitch = sPitch[il];
       float trunc = p.threshold * pitch;
       int ks = ksize_of(pitch, trunc), half = ks / 2;
       float fx, fy, fz;
       point_in_grid(sR[jl], sT[jl], p.points[3 * pt], p.points[3 * pt + 1], p.points[3 * pt + 2],
-                    p.origin[3 * gi], p.origin[3 * gi + 1], p.origin[3 * gi + 2], pitch, fx, fy, fz);
+                    sOrigin[il][0], sOrigin[il][1], sOrigin[il][2], pitch, fx, fy, fz);
       float rx = roundf(fx), ry = roundf(fy), rz = roundf(fz);
       if (!(rx >= (float)(-half) && rx <= (float)(D - 1 + half) && ry >= (float)(-half) &&
             ry <= (float)(D - 1 + half) && rz >= (float)(-half) && rz <= (float)(D - 1 + half)))
@@ -335,24 +357,27 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     const float c_in0 = 1.f / stot[3];
     const float c_in1 = stot[2] / (stot[3] * stot[3]);
 
+    for (int e = tid; e < (kIccThreads / 32) * kIccMaxObj * 12; e += kIccThreads)
+      (&sAcc[0][0][0])[e] = 0.f;
+    __syncthreads();
     for (int w = cta; w < n_items; w += p.G) {
-      int il = w / sc.C, cl = w - il * sc.C, cc = sc.c0 + cl;
+      int il = w / sc.C, cl = w - il * sc.C;
       int gi = sc.o0 + il;
-      int gj = p.chunk_obj[cc];
+      int gj = chunks_in_smem ? sChunkObj[cl] : p.chunk_obj[sc.c0 + cl];
       int jl = gj - sc.o0;
-      int pt = p.chunk_start[cc] + tid;
+      int pt = (chunks_in_smem ? sChunkStart[cl] : p.chunk_start[sc.c0 + cl]) + tid;
       float g12[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) g12[k] = 0.f;
       bool any = false;
-      if (pt < p.obj_pt_off[gj + 1]) {
-        float pitch = p.pitch[gi];
+      if (pt < sPtEnd[jl]) {
+        float pitch = sPitch[il];
         float trunc = p.threshold * pitch;
         int ks = ksize_of(pitch, trunc), half = ks / 2;
         float px = p.points[3 * pt], py = p.points[3 * pt + 1], pz = p.points[3 * pt + 2];
         float fx, fy, fz;
-        point_in_grid(sR[jl], sT[jl], px, py, pz, p.origin[3 * gi], p.origin[3 * gi + 1],
-                      p.origin[3 * gi + 2], pitch, fx, fy, fz);
+        point_in_grid(sR[jl], sT[jl], px, py, pz, sOrigin[il][0], sOrigin[il][1], sOrigin[il][2],
+                      pitch, fx, fy, fz);
         float rx = roundf(fx), ry = roundf(fy), rz = roundf(fz);
         if (rx >= (float)(-half) && rx <= (float)(D - 1 + half) && ry >= (float)(-half) &&
             ry <= (float)(D - 1 + half) && rz >= (float)(-half) && rz <= (float)(D - 1 + half)) {
@@ -366,11 +391,20 @@ k_icc_run(IccParams p, IccAlpha alpha) {
             for (int dy = -half; dy <= half; ++dy) {
               int iy = (int)(ry + (float)dy);
               if (iy < 0 || iy >= D) continue;
+              // the (up to 2*half+1) keys of one z-run are loaded together, then examined
+              unsigned long long kz[3];
+              if (half == 1) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                  int iz = (int)(rz + (float)(q - 1));
+                  kz[q] = (iz >= 0 && iz < D) ? __ldcg(keys + (ix * D + iy) * D + iz) : kKeyEmpty;
+                }
+              }
               for (int dz = -half; dz <= half; ++dz) {
                 int iz = (int)(rz + (float)dz);
                 if (iz < 0 || iz >= D) continue;
                 int v = (ix * D + iy) * D + iz;
-                unsigned long long key = __ldcg(keys + v);
+                unsigned long long key = (half == 1) ? kz[dz + 1] : __ldcg(keys + v);
                 if ((unsigned int)(key & 0xffffffffu) != (unsigned int)pt || key == kKeyEmpty)
                   continue;
                 float4 cf = __ldcg(coefs + v);
@@ -393,20 +427,23 @@ k_icc_run(IccParams p, IccAlpha alpha) {
           g12[8] = az * px; g12[9] = az * py; g12[10] = az * pz; g12[11] = az;
         }
       }
-      if (tid == 0) sflag = 0;
-      __syncthreads();
-      if (any) sflag = 1;
-      __syncthreads();
-      float* slot = p.slots + ((size_t)sc.slot0 + (size_t)il * sc.C + cl) * 12;
-      if (sflag) {
-        block_sum<12>(g12, sred);
-        if (tid == 0)
+      // warp-level fixed-order tree, then lane 0 adds to this warp's running sum for object j
+      if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-          for (int k = 0; k < 12; ++k) slot[k] = g12[k];
-      } else if (tid < 12) {
-        slot[tid] = 0.f;
+        for (int k = 0; k < 12; ++k) g12[k] = warp_sum(g12[k]);
+        if (lane_id == 0)
+#pragma unroll
+          for (int k = 0; k < 12; ++k) sAcc[warp_id][jl][k] += g12[k];
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    // one slot per (CTA, object): warps summed in fixed order
+    for (int e = tid; e < sc.N * 12; e += kIccThreads) {
+      int jl = e / 12, k = e - jl * 12;
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kIccThreads / 32; ++wv) s += sAcc[wv][jl][k];
+      p.slots[(((size_t)scene * p.G + cta) * kIccMaxObj + jl) * 12 + k] = s;
     }
     group_barrier(bar, p.G, epoch);
 
@@ -414,19 +451,14 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     for (int jl = cta; jl < sc.N; jl += p.G) {
       if (tid < 32) {
         int gj = sc.o0 + jl;
-        // chunks of object j are contiguous in the chunk table
-        const int cj0 = p.obj_chunk_off[gj] - sc.c0, cj1 = p.obj_chunk_off[gj + 1] - sc.c0;
         float a[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = 0.f;
-        int nc = cj1 - cj0;
-        if (nc > 0)
-          for (int e = tid; e < sc.N * nc; e += 32) {
-            int il = e / nc, cl = cj0 + (e - il * nc);
-            const float* slot = p.slots + ((size_t)sc.slot0 + (size_t)il * sc.C + cl) * 12;
+        for (int c = tid; c < p.G; c += 32) {                 // fixed order: lane-strided, then tree
+          const float* slot = p.slots + (((size_t)scene * p.G + c) * kIccMaxObj + jl) * 12;
 #pragma unroll
-            for (int k = 0; k < 12; ++k) a[k] += __ldcg(slot + k);
-          }
+          for (int k = 0; k < 12; ++k) a[k] += __ldcg(slot + k);
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
         if (tid == 0) {
@@ -501,7 +533,8 @@ static IccLayout icc_layout(int Ntot, int D, int S, int G, int n_slots) {
   L.coefs = o; o += al((size_t)Ntot * V * 16);
   L.maxbits = o; o += al((size_t)Ntot * 2 * 4);
   L.partials = o; o += al((size_t)S * G * 16);
-  L.slots = o; o += al((size_t)n_slots * 48);
+  L.slots = o; o += al((size_t)S * G * kIccMaxObj * 48);   // one (gR|gt) slot per (CTA, object)
+  (void)n_slots;
   L.barrier = o; o += al((size_t)S * 4);
   L.total = o;
   return L;
