@@ -291,6 +291,19 @@ int mf_icc_run(int n_scenes, int n_objects_total, int voxel_dim, float voxel_thr
                const float* alpha_q_host, const float* alpha_t_host, float beta1, float beta2,
                float eps, float eta, float* loss_history, float* grads, int group_size,
                void* workspace, size_t workspace_bytes, void* stream);
+/* same, plus phase_ns: device uint64 [n_scenes][n_iter][8] receiving %globaltimer stamps at the
+ * phase boundaries of every iteration (profiling aid; NULL = off) */
+int mf_icc_run_profiled(int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold,
+               float sdf_offset, const int32_t* scene_obj_off, const int32_t* obj_pt_off,
+               const int32_t* scene_chunk_off, const int32_t* chunk_obj,
+               const int32_t* chunk_start, const int32_t* scene_slot_off,
+               const int32_t* obj_chunk_off, int n_slots,
+               const float* points, const float* sdf, const float* pitch, const float* origin,
+               const float* grid_target, const float* grid_nontarget_empty, float* quaternion,
+               float* translation, float* adam_state, int n_iter, int update,
+               const float* alpha_q_host, const float* alpha_t_host, float beta1, float beta2,
+               float eps, float eta, float* loss_history, float* grads, int group_size,
+               void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream);
 
 /* ------------------------------------------------------------------------
  * a12  average_distance (ADD / ADD-S training loss) + nearest neighbour

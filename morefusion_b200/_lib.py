@@ -62,6 +62,8 @@ SIGNATURES = {
                    + [c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_p, c_sz, c_p]),
     "mf_average_distance_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "mf_average_distance_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "mf_icc_run_profiled": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
+                            + [c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_p, c_sz, c_p, c_p]),
 }
 
 _lib = None

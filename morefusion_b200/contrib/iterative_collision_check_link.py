@@ -91,7 +91,8 @@ class _Problem:
 
 
 def _run(prob, quaternion, translation, adam_state, *, n_iter, update, alpha_q, alpha_t,
-         voxel_threshold, sdf_offset, group_size=0, beta1=0.9, beta2=0.999, eps=1e-8, eta=1.0):
+         voxel_threshold, sdf_offset, group_size=0, beta1=0.9, beta2=0.999, eps=1e-8, eta=1.0,
+         phase_ns=None):
     L = _lib.lib()
     dev = prob.device
     loss = torch.empty((prob.S, n_iter), dtype=torch.float32, device=dev)
@@ -106,7 +107,7 @@ def _run(prob, quaternion, translation, adam_state, *, n_iter, update, alpha_q, 
         ws = _util.workspace(nws, dev)
         aq = (ctypes.c_float * 128)(*([float(np.float32(a)) for a in alpha_q] + [0.0] * (128 - len(alpha_q))))
         at = (ctypes.c_float * 128)(*([float(np.float32(a)) for a in alpha_t] + [0.0] * (128 - len(alpha_t))))
-        rc = L.mf_icc_run(
+        rc = L.mf_icc_run_profiled(
             prob.S, prob.Ntot, prob.voxel_dim, float(voxel_threshold), float(sdf_offset),
             _lib.ptr(prob.scene_obj_off), _lib.ptr(prob.obj_pt_off), _lib.ptr(prob.scene_chunk_off),
             _lib.ptr(prob.chunk_obj), _lib.ptr(prob.chunk_start), _lib.ptr(prob.scene_slot_off),
@@ -115,7 +116,7 @@ def _run(prob, quaternion, translation, adam_state, *, n_iter, update, alpha_q, 
             _lib.ptr(quaternion), _lib.ptr(translation), _lib.ptr(adam_state), n_iter,
             int(update), ctypes.cast(aq, ctypes.c_void_p), ctypes.cast(at, ctypes.c_void_p),
             beta1, beta2, eps, eta, _lib.ptr(loss), _lib.ptr(grads), G, _lib.ptr(ws), ws.numel(),
-            _lib.stream())
+            _lib.ptr(phase_ns), _lib.stream())
     _lib.check(rc, "icc_run")
     return loss, grads
 

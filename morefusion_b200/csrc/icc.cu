@@ -29,7 +29,6 @@ namespace mf {
 
 constexpr int kIccThreads = 256;
 constexpr int kIccMaxObj = 32;
-constexpr int kIccMaxChunks = 1024;      // chunk tables staged in shared memory up to this many chunks / scene
 constexpr unsigned long long kKeyEmpty = 0xFFFFFFFFFFFFFFFFull;
 
 struct IccParams {
@@ -56,12 +55,13 @@ struct IccParams {
   unsigned int* maxbits;       // [Ntot][2]
   float* partials;             // [S][G][4]
   float* slots;                // [sum N_s*C_s][12]
-  unsigned int* barrier;       // [S]
+  unsigned int* barrier;       // [S][1 + kBarSub]
   float* loss;                 // [S][n_iter]
   float* grads;                // [Ntot,7] gradient of the last iteration (gq | gt)
   int Ntot;
   int G, n_iter, update;
   float one_minus_beta1, one_minus_beta2, eps, eta;
+  unsigned long long* phase_ns;  // optional [S][n_iter][8] globaltimer stamps at phase boundaries (profiling)
 };
 
 struct IccAlpha {
@@ -70,18 +70,27 @@ struct IccAlpha {
 };
 
 // ------------------------------------------------------------------ helpers
-__device__ __forceinline__ void group_barrier(unsigned int* counter, int G, unsigned int& epoch) {
+// Two-level barrier over the G CTAs of a scene.  Same-address atomics from different SMs
+// serialise in L2 (~15-30 cycles each), so 592 arrivals on one word cost ~10 us; here a CTA
+// arrives on one of kBarSub sub-counters and only the last arriver of a sub-group touches the
+// master word that everybody polls.  All counters are monotonic (never reset inside the kernel).
+constexpr int kBarSub = 24;
+__device__ __forceinline__ void group_barrier(unsigned int* bar /* [1 + kBarSub] */, int G, int cta,
+                                              unsigned int& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    const int nsub = G < kBarSub ? G : kBarSub;
+    const int sub = cta % nsub;
+    const unsigned int sub_size = (unsigned int)((G - sub + nsub - 1) / nsub);
     __threadfence();
-    atomicAdd(counter, 1u);
-    epoch += (unsigned)G;
+    unsigned int old = atomicAdd(bar + 1 + sub, 1u);
+    if ((old + 1u) % sub_size == 0u) atomicAdd(bar, 1u);
+    epoch += (unsigned)nsub;
     long long t0 = clock64();
     while (true) {
-      unsigned int v = *((volatile unsigned int*)counter);
+      unsigned int v = *((volatile unsigned int*)bar);
       if ((int)(v - epoch) >= 0) break;
       if (clock64() - t0 > 6000000000LL) __trap();   // never hang the GPU
-      __nanosleep(20);
     }
     __threadfence();
   }
@@ -161,6 +170,15 @@ __device__ __forceinline__ void point_in_grid(const float* R, const float* tt, f
   fz = (z - oz) / pitch;
 }
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ICC_STAMP(k)                                                                      \
+  if (p.phase_ns && cta == 0 && tid == 0)                                                 \
+    p.phase_ns[((size_t)scene * p.n_iter + it) * 8 + (k)] = gtime_ns();
+
 // ------------------------------------------------------------------ the persistent kernel
 __global__ void __launch_bounds__(kIccThreads, 4)
 k_icc_run(IccParams p, IccAlpha alpha) {
@@ -172,8 +190,6 @@ k_icc_run(IccParams p, IccAlpha alpha) {
   __shared__ float sPitch[kIccMaxObj];
   __shared__ float sOrigin[kIccMaxObj][3];
   __shared__ int sPtEnd[kIccMaxObj];
-  __shared__ int sChunkObj[kIccMaxChunks];
-  __shared__ int sChunkStart[kIccMaxChunks];
   // per-warp running sums of (gR | gt) per source object: no block barrier per work item
   __shared__ float sAcc[kIccThreads / 32][kIccMaxObj][12];
 
@@ -186,25 +202,23 @@ k_icc_run(IccParams p, IccAlpha alpha) {
   sc.C = p.scene_chunk_off[scene + 1] - sc.c0;
   sc.slot0 = p.scene_slot_off[scene];
   const int D = p.D, V = D * D * D;
-  unsigned int* bar = p.barrier + scene;
+  unsigned int* bar = p.barrier + (size_t)scene * (1 + kBarSub);
   unsigned int epoch = 0;
-  const int n_items = sc.N * sc.C;
-  const bool chunks_in_smem = sc.C <= kIccMaxChunks;
   if (tid < sc.N) {
     int o = sc.o0 + tid;
     sPitch[tid] = p.pitch[o];
     sOrigin[tid][0] = p.origin[3 * o]; sOrigin[tid][1] = p.origin[3 * o + 1]; sOrigin[tid][2] = p.origin[3 * o + 2];
     sPtEnd[tid] = p.obj_pt_off[o + 1];
   }
-  if (chunks_in_smem)
-    for (int e = tid; e < sc.C; e += kIccThreads) {
-      sChunkObj[e] = p.chunk_obj[sc.c0 + e];
-      sChunkStart[e] = p.chunk_start[sc.c0 + e];
-    }
   __syncthreads();
   const int warp_id = tid >> 5, lane_id = tid & 31;
+  const int pt0 = p.obj_pt_off[sc.o0];
+  const int pts_in_scene = p.obj_pt_off[sc.o0 + sc.N] - pt0;
+  const int n_tests = sc.N * pts_in_scene;                    // (target grid, point) pairs
+  const int n_units = (n_tests + 31) / 32;
 
   for (int it = 0; it < p.n_iter; ++it) {
+    ICC_STAMP(0)
     // ---- P0: rotations of this scene's objects (q, t may have been updated by other CTAs)
     if (tid < sc.N) {
       int o = sc.o0 + tid;
@@ -219,14 +233,17 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     }
     __syncthreads();
 
-    // ---- P1: scatter
-    for (int w = cta; w < n_items; w += p.G) {
-      int il = w / sc.C, cl = w - il * sc.C;
-      int gi = sc.o0 + il;
-      int gj = chunks_in_smem ? sChunkObj[cl] : p.chunk_obj[sc.c0 + cl];
-      int jl = gj - sc.o0;
-      int pt = (chunks_in_smem ? sChunkStart[cl] : p.chunk_start[sc.c0 + cl]) + tid;
-      if (pt >= sPtEnd[jl]) continue;
+    // ---- P1: scatter.  Work unit = 32 consecutive (target grid, point) tests handled by one
+    // warp; warps of all CTAs are interleaved over the units so that every CTA sees the same mix
+    // of in-range (27 atomics per point) and out-of-range (rejected at once) tests.
+    for (int u = cta * (kIccThreads / 32) + warp_id; u < n_units; u += p.G * (kIccThreads / 32)) {
+      const int tt = u * 32 + lane_id;
+      if (tt >= n_tests) continue;
+      const int il = tt / pts_in_scene, pp = tt - il * pts_in_scene;
+      const int pt = pt0 + pp;
+      int jl = 0;
+      while (jl + 1 < sc.N && pt >= sPtEnd[jl]) ++jl;
+      const int gi = sc.o0 + il, gj = sc.o0 + jl;
       float pitch = sPitch[il];
       float trunc = p.threshold * pitch;
       int ks = ksize_of(pitch, trunc), half = ks / 2;
@@ -260,8 +277,9 @@ k_icc_run(IccParams p, IccAlpha alpha) {
         }
       }
     }
-    group_barrier(bar, p.G, epoch);
+    group_barrier(bar, p.G, cta, epoch);
 
+    ICC_STAMP(1)
     // ---- P2: winners' weights -> per-(grid, kind) max
     {
       const int n_gk = sc.N * 2;
@@ -281,8 +299,9 @@ k_icc_run(IccParams p, IccAlpha alpha) {
         if ((tid & 31) == 0 && m > 0.f) atomicMax(p.maxbits + gi * 2 + kind, __float_as_uint(m));
       }
     }
-    group_barrier(bar, p.G, epoch);
+    group_barrier(bar, p.G, cta, epoch);
 
+    ICC_STAMP(2)
     // ---- P3: grids, loss partial sums, backward coefficients
     {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rew_num, rew_den, pen_num, pen_den
@@ -334,8 +353,9 @@ k_icc_run(IccParams p, IccAlpha alpha) {
         dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2]; dst[3] = acc[3];
       }
     }
-    group_barrier(bar, p.G, epoch);
+    group_barrier(bar, p.G, cta, epoch);
 
+    ICC_STAMP(3)
     // ---- P4: totals, then gather-backward
     if (tid < 32) {
       float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -360,80 +380,65 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     for (int e = tid; e < (kIccThreads / 32) * kIccMaxObj * 12; e += kIccThreads)
       (&sAcc[0][0][0])[e] = 0.f;
     __syncthreads();
-    for (int w = cta; w < n_items; w += p.G) {
-      int il = w / sc.C, cl = w - il * sc.C;
-      int gi = sc.o0 + il;
-      int gj = chunks_in_smem ? sChunkObj[cl] : p.chunk_obj[sc.c0 + cl];
-      int jl = gj - sc.o0;
-      int pt = (chunks_in_smem ? sChunkStart[cl] : p.chunk_start[sc.c0 + cl]) + tid;
-      float g12[12];
+    // Voxel-centric gather (the structure of the reference's backward kernel, tdf.py:119-145):
+    // every voxel that has a winner contributes  unit(f - v) * d loss/d tdf[v]  to its winning
+    // point; the dependent chain per voxel is only key -> (coefficients, point) -> arithmetic.
+    {
+      const int n_gk = sc.N * 2;
+      const int blocks_per = (V + kIccThreads - 1) / kIccThreads;
+      for (int w = cta; w < n_gk * blocks_per; w += p.G) {
+        const int gk = w / blocks_per, v = (w - gk * blocks_per) * kIccThreads + tid;
+        const int il = gk >> 1, kind = gk & 1, gi = sc.o0 + il;
+        float g12[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) g12[k] = 0.f;
-      bool any = false;
-      if (pt < sPtEnd[jl]) {
-        float pitch = sPitch[il];
-        float trunc = p.threshold * pitch;
-        int ks = ksize_of(pitch, trunc), half = ks / 2;
-        float px = p.points[3 * pt], py = p.points[3 * pt + 1], pz = p.points[3 * pt + 2];
-        float fx, fy, fz;
-        point_in_grid(sR[jl], sT[jl], px, py, pz, sOrigin[il][0], sOrigin[il][1], sOrigin[il][2],
-                      pitch, fx, fy, fz);
-        float rx = roundf(fx), ry = roundf(fy), rz = roundf(fz);
-        if (rx >= (float)(-half) && rx <= (float)(D - 1 + half) && ry >= (float)(-half) &&
-            ry <= (float)(D - 1 + half) && rz >= (float)(-half) && rz <= (float)(D - 1 + half)) {
-          const int kind = (gi == gj) ? 0 : 1;
-          const unsigned long long* keys = p.keys + ((size_t)gi * 2 + kind) * V;
-          const float4* coefs = p.coefs + (size_t)gi * V;
-          float ax = 0.f, ay = 0.f, az = 0.f;
-          for (int dx = -half; dx <= half; ++dx) {
-            int ix = (int)(rx + (float)dx);
-            if (ix < 0 || ix >= D) continue;
-            for (int dy = -half; dy <= half; ++dy) {
-              int iy = (int)(ry + (float)dy);
-              if (iy < 0 || iy >= D) continue;
-              // the (up to 2*half+1) keys of one z-run are loaded together, then examined
-              unsigned long long kz[3];
-              if (half == 1) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                  int iz = (int)(rz + (float)(q - 1));
-                  kz[q] = (iz >= 0 && iz < D) ? __ldcg(keys + (ix * D + iy) * D + iz) : kKeyEmpty;
-                }
-              }
-              for (int dz = -half; dz <= half; ++dz) {
-                int iz = (int)(rz + (float)dz);
-                if (iz < 0 || iz >= D) continue;
-                int v = (ix * D + iy) * D + iz;
-                unsigned long long key = (half == 1) ? kz[dz + 1] : __ldcg(keys + v);
-                if ((unsigned int)(key & 0xffffffffu) != (unsigned int)pt || key == kKeyEmpty)
-                  continue;
-                float4 cf = __ldcg(coefs + v);
-                float dg = kind == 0 ? (cf.y * c_in0 - cf.z * c_in1 - cf.x * c_rw) : cf.w * c_in0;
-                float gtdf = -dg / trunc;
-                float ddx = fx - (float)ix, ddy = fy - (float)iy, ddz = fz - (float)iz;
-                float n = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-                if (n > 0.f) {
-                  ax += ddx / n * gtdf;
-                  ay += ddy / n * gtdf;
-                  az += ddz / n * gtdf;
-                  any = true;
-                }
+        for (int k = 0; k < 12; ++k) g12[k] = 0.f;
+        bool any = false;
+        int jl = 1 << 30;
+        if (v < V && !(kind == 1 && sc.N == 1)) {
+          const unsigned long long key = __ldcg(p.keys + ((size_t)gi * 2 + kind) * V + v);
+          if (key != kKeyEmpty) {
+            const float4 cf = __ldcg(p.coefs + (size_t)gi * V + v);
+            const float dg = kind == 0 ? (cf.y * c_in0 - cf.z * c_in1 - cf.x * c_rw) : cf.w * c_in0;
+            if (dg != 0.f) {
+              const int pt = (int)(unsigned int)(key & 0xffffffffu);
+              jl = 0;
+              while (jl + 1 < sc.N && pt >= sPtEnd[jl]) ++jl;
+              const float pitch = sPitch[il];
+              const float trunc = p.threshold * pitch;
+              const float px = p.points[3 * pt], py = p.points[3 * pt + 1], pz = p.points[3 * pt + 2];
+              float fx, fy, fz;
+              point_in_grid(sR[jl], sT[jl], px, py, pz, sOrigin[il][0], sOrigin[il][1],
+                            sOrigin[il][2], pitch, fx, fy, fz);
+              const int iz = v % D, iy = (v / D) % D, ix = v / (D * D);
+              const float ddx = fx - (float)ix, ddy = fy - (float)iy, ddz = fz - (float)iz;
+              const float n = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+              if (n > 0.f) {
+                const float gtdf = -dg / trunc;
+                const float ax = ddx / n * gtdf, ay = ddy / n * gtdf, az = ddz / n * gtdf;
+                // x = R p + t :  gt += gx ; gR += gx (x) p
+                g12[0] = ax * px; g12[1] = ax * py; g12[2] = ax * pz; g12[3] = ax;
+                g12[4] = ay * px; g12[5] = ay * py; g12[6] = ay * pz; g12[7] = ay;
+                g12[8] = az * px; g12[9] = az * py; g12[10] = az * pz; g12[11] = az;
+                any = true;
               }
             }
           }
-          // x = R p + t :  gt += gx ; gR += gx (x) p
-          g12[0] = ax * px; g12[1] = ax * py; g12[2] = ax * pz; g12[3] = ax;
-          g12[4] = ay * px; g12[5] = ay * py; g12[6] = ay * pz; g12[7] = ay;
-          g12[8] = az * px; g12[9] = az * py; g12[10] = az * pz; g12[11] = az;
         }
-      }
-      // warp-level fixed-order tree, then lane 0 adds to this warp's running sum for object j
-      if (__any_sync(0xffffffffu, any)) {
+        // winners in one warp's 32 voxels may belong to different source objects: objects are
+        // taken in order of first occurrence, each with a fixed-order masked tree
+        unsigned todo = __ballot_sync(0xffffffffu, any);
+        while (todo) {
+          const int leader = __ffs(todo) - 1;
+          const int jcur = __shfl_sync(0xffffffffu, jl, leader);
+          const bool mine = any && (jl == jcur);
+          float sums[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) g12[k] = warp_sum(g12[k]);
-        if (lane_id == 0)
+          for (int k = 0; k < 12; ++k) sums[k] = warp_sum(mine ? g12[k] : 0.f);
+          if (lane_id == 0)
 #pragma unroll
-          for (int k = 0; k < 12; ++k) sAcc[warp_id][jl][k] += g12[k];
+            for (int k = 0; k < 12; ++k) sAcc[warp_id][jcur][k] += sums[k];
+          todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
       }
     }
     __syncthreads();
@@ -445,22 +450,23 @@ k_icc_run(IccParams p, IccAlpha alpha) {
       for (int wv = 0; wv < kIccThreads / 32; ++wv) s += sAcc[wv][jl][k];
       p.slots[(((size_t)scene * p.G + cta) * kIccMaxObj + jl) * 12 + k] = s;
     }
-    group_barrier(bar, p.G, epoch);
+    group_barrier(bar, p.G, cta, epoch);
 
+    ICC_STAMP(4)
     // ---- P5: per-object reduction + quaternion backward + Chainer Adam; reset keys
     for (int jl = cta; jl < sc.N; jl += p.G) {
-      if (tid < 32) {
+      {
         int gj = sc.o0 + jl;
+        // all threads: slots of the G CTAs (thread-strided), then a fixed-order block tree
         float a[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = 0.f;
-        for (int c = tid; c < p.G; c += 32) {                 // fixed order: lane-strided, then tree
+        for (int c = tid; c < p.G; c += kIccThreads) {
           const float* slot = p.slots + (((size_t)scene * p.G + c) * kIccMaxObj + jl) * 12;
 #pragma unroll
           for (int k = 0; k < 12; ++k) a[k] += __ldcg(slot + k);
         }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
+        block_sum<12>(a, sred);
         if (tid == 0) {
           float q[4] = {p.q[4 * gj], p.q[4 * gj + 1], p.q[4 * gj + 2], p.q[4 * gj + 3]};
           float gR[9] = {a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10]};
@@ -494,6 +500,7 @@ k_icc_run(IccParams p, IccAlpha alpha) {
         }
       }
     }
+    ICC_STAMP(5)
     if (it + 1 < p.n_iter) {
       // reset for the next iteration (dense: 16 B per voxel-kind, L2 resident)
       const size_t nk = (size_t)sc.N * 2 * V;
@@ -502,7 +509,7 @@ k_icc_run(IccParams p, IccAlpha alpha) {
         k0[e] = kKeyEmpty;
       for (int e = cta * kIccThreads + tid; e < sc.N * 2; e += p.G * kIccThreads)
         p.maxbits[sc.o0 * 2 + e] = 0u;
-      group_barrier(bar, p.G, epoch);
+      group_barrier(bar, p.G, cta, epoch);
     }
   }
 }
@@ -512,7 +519,7 @@ __global__ void k_icc_init(unsigned long long* keys, size_t n_keys, unsigned int
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_keys) keys[i] = kKeyEmpty;
   if (i < (size_t)n_max) maxbits[i] = 0u;
-  if (i < (size_t)S) barrier[i] = 0u;
+  if (i < (size_t)S * (1 + kBarSub)) barrier[i] = 0u;
 }
 
 static size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -535,7 +542,7 @@ static IccLayout icc_layout(int Ntot, int D, int S, int G, int n_slots) {
   L.partials = o; o += al((size_t)S * G * 16);
   L.slots = o; o += al((size_t)S * G * kIccMaxObj * 48);   // one (gR|gt) slot per (CTA, object)
   (void)n_slots;
-  L.barrier = o; o += al((size_t)S * 4);
+  L.barrier = o; o += al((size_t)S * (1 + kBarSub) * 4);
   L.total = o;
   return L;
 }
@@ -555,6 +562,13 @@ extern "C" size_t mf_icc_workspace_bytes(int n_objects_total, int voxel_dim, int
   return icc_layout(n_objects_total, voxel_dim, n_scenes, group_size, n_slots).total;
 }
 
+extern "C" int mf_icc_run_profiled(
+    int, int, int, float, float, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+    const int32_t*, const int32_t*, const int32_t*, int, const float*, const float*, const float*,
+    const float*, const float*, const float*, float*, float*, float*, int, int, const float*,
+    const float*, float, float, float, float, float*, float*, int, void*, size_t,
+    unsigned long long*, void*);
+
 extern "C" int mf_icc_run(
     int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold, float sdf_offset,
     const int32_t* scene_obj_off, const int32_t* obj_pt_off, const int32_t* scene_chunk_off,
@@ -567,6 +581,27 @@ extern "C" int mf_icc_run(
     float beta1, float beta2, float eps, float eta,
     float* loss_history, float* grads, int group_size,
     void* workspace, size_t workspace_bytes, void* stream_) {
+  return mf_icc_run_profiled(n_scenes, n_objects_total, voxel_dim, voxel_threshold, sdf_offset,
+                             scene_obj_off, obj_pt_off, scene_chunk_off, chunk_obj, chunk_start,
+                             scene_slot_off, obj_chunk_off, n_slots, points, sdf, pitch, origin,
+                             grid_target, grid_nontarget_empty, quaternion, translation, adam_state,
+                             n_iter, update, alpha_q_host, alpha_t_host, beta1, beta2, eps, eta,
+                             loss_history, grads, group_size, workspace, workspace_bytes, nullptr,
+                             stream_);
+}
+
+extern "C" int mf_icc_run_profiled(
+    int n_scenes, int n_objects_total, int voxel_dim, float voxel_threshold, float sdf_offset,
+    const int32_t* scene_obj_off, const int32_t* obj_pt_off, const int32_t* scene_chunk_off,
+    const int32_t* chunk_obj, const int32_t* chunk_start, const int32_t* scene_slot_off,
+    const int32_t* obj_chunk_off, int n_slots,
+    const float* points, const float* sdf, const float* pitch, const float* origin,
+    const float* grid_target, const float* grid_nontarget_empty,
+    float* quaternion, float* translation, float* adam_state,
+    int n_iter, int update, const float* alpha_q_host, const float* alpha_t_host,
+    float beta1, float beta2, float eps, float eta,
+    float* loss_history, float* grads, int group_size,
+    void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_scenes <= 0 || n_objects_total <= 0 || voxel_dim <= 0 || n_iter <= 0 || n_iter > 128)
     return MF_E_BADARG;
@@ -601,6 +636,7 @@ extern "C" int mf_icc_run(
   p.one_minus_beta1 = (float)(1.0 - (double)beta1);
   p.one_minus_beta2 = (float)(1.0 - (double)beta2);
   p.eps = eps; p.eta = eta;
+  p.phase_ns = phase_ns;
   IccAlpha alpha;
   for (int i = 0; i < 128; ++i) {
     alpha.aq[i] = (update && i < n_iter) ? alpha_q_host[i] : 0.f;
