@@ -19,6 +19,7 @@
 // (cnn.cu) the 128 output voxels x 64 channels of one K block are ONE 5-D TMA box.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cnn.cuh"
@@ -328,6 +329,220 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
   }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// One CTA per SM loops over work units (group, m-tile, n-tile, k-split).  The shared-memory
+// stage ring runs continuously across units and the accumulator is double-buffered in TMEM
+// (2 x BLOCK_N columns), so the epilogue of unit i (tcgen05.ld, bias/ReLU, stores) overlaps the
+// TMA + MMA main loop of unit i+1 and the per-CTA set-up (barrier init, TMEM allocation,
+// descriptor prefetch, pipeline fill) is paid once per SM instead of once per tile -- which is
+// what the short-K head GEMMs (2-16 K blocks per tile) are dominated by in the one-shot kernel.
+struct TcSched {
+  int m_tiles, n_tiles, groups, splitk, n_units;
+};
+
+__device__ __forceinline__ void unit_decode(const TcSched& sc, int u, int& g, int& mt, int& nt,
+                                            int& split) {
+  split = u % sc.splitk;
+  int r = u / sc.splitk;
+  nt = r % sc.n_tiles;
+  r /= sc.n_tiles;
+  mt = r % sc.m_tiles;
+  g = r / sc.m_tiles;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
+  constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcExtra& e = args.e;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < sc.groups; ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmA[g])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmW[g])) : "memory");
+    }
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);       // one arrival per epilogue warp
+    mbar_init(&tmem_empty_bar[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer
+    int kc = 0;                                        // K blocks issued so far (ring position)
+    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x) {
+      int g, mt, nt, split;
+      unit_decode(sc, u, g, mt, nt, split);
+      const GemmParams& p = args.p[g];
+      const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N;
+      const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
+      int cb = 0, cw = 0, ch = 0, cd = 0;
+      if (p.mode == GEMM_CONV_S2D) {
+        int Do = p.Do;
+        cw = m0 % Do;
+        ch = (m0 / Do) % Do;
+        cd = (m0 / (Do * Do)) % Do;
+        cb = m0 / (Do * Do * Do);
+      }
+      for (int kb = kb0; kb < kb1; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, e.err, 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        unsigned char* sb = sa + TC_A_BYTES;
+        if (p.mode == GEMM_CONV_S2D) {
+          int a = kb / e.kb_per_a, c = (kb - a * e.kb_per_a) * TC_BLOCK_K;
+          tma_load_5d(sa, &args.tmA[g], &full_bar[s], c, cw + (a & 1), ch + ((a >> 1) & 1),
+                      cd + ((a >> 2) & 1), cb);
+        } else {
+          tma_load_2d(sa, &args.tmA[g], &full_bar[s], kb * TC_BLOCK_K, m0);
+        }
+        tma_load_2d(sb, &args.tmW[g], &full_bar[s], kb * TC_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    int kc = 0, it = 0;
+    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
+      int g, mt, nt, split;
+      unit_decode(sc, u, g, mt, nt, split);
+      const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4);    // epilogue has drained this buffer
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = kb0; kb < kb1; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, e.err, 2);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = make_sw128_desc(sa);
+        const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+          umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
+      int g, mt, nt, split;
+      unit_decode(sc, u, g, mt, nt, split);
+      const GemmParams& p = args.p[g];
+      const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], aph, e.err, 3);
+      tcgen05_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const long long roff = row_ok ? out_row_offset(p, m) : 0;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tacc + (uint32_t)c0, r);
+        const int n = n0 + c0;
+        if (!row_ok || n >= p.N) continue;
+        if (p.N & 31) {
+          float* dst = reinterpret_cast<float*>(p.out) + roff + n;
+          const int nj = min(32, p.N - n);
+          for (int j = 0; j < nj; ++j) {
+            float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+            dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+          }
+          continue;
+        }
+        if (e.splitk > 1) {
+          float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+          v[j] = p.relu ? fmaxf(x, 0.f) : x;
+        }
+        if (p.out_mode == OUT_F32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + roff + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            uint4 uu;
+            uu.x = *reinterpret_cast<uint32_t*>(&h0);
+            uu.y = *reinterpret_cast<uint32_t*>(&h1);
+            uu.z = *reinterpret_cast<uint32_t*>(&h2);
+            uu.w = *reinterpret_cast<uint32_t*>(&h3);
+            dst[j] = uu;
+          }
+        }
+      }
+      // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc]))
+                     : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+  }
+}
+
 // split-K epilogue: sum the slices, bias + activation + layout; 4 columns per thread
 __global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p, int splitk) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,6 +595,34 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MF_OK : MF_E_BADARG;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t stream) {
+  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
+  static bool attr = false;
+  static int n_sm = 148;
+  if (!attr) {
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    MF_CUDA_TRY(cudaGetDevice(&dev));
+    MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    attr = true;
+  }
+  int grid = sc.n_units < n_sm ? sc.n_units : n_sm;
+  k_gemm_tc_persistent<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(args, sc);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+static bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MF_GEMM_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 template <int BLOCK_N, int STAGES>
@@ -492,7 +735,11 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   }
   dim3 grid(n_tiles, m_tiles, splitk * n_groups);
   int rc;
-  if (BN == 256) rc = launch<256, 4>(args, grid, stream);
+  if (persistent_enabled()) {
+    TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk};
+    if (BN == 256) rc = launch_persistent<256, 4>(args, sc, stream);
+    else rc = launch_persistent<128, 6>(args, sc, stream);
+  } else if (BN == 256) rc = launch<256, 4>(args, grid, stream);
   else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;
   if (splitk > 1) {
