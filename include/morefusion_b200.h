@@ -251,6 +251,10 @@ int mf_gemm_bf16_tc_grouped(const GemmParams* p, int n_groups, void* workspace,
  * [M][N] partial sums when the launch splits K (few output tiles, long K). */
 size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N);
 int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes, void* stream);
+/* profiling hook: device buffer of 16*8 int64 receiving clock64 stamps of CTA 0's roles per work
+ * unit (0/1 TMA producer begin/end, 2/3/4 MMA issuer buffer-free / first-operands / committed,
+ * 5/6/7 epilogue accumulator-ready / accumulator-drained / stores issued); NULL switches it off */
+int mf_gemm_tc_set_stamps(void* dev_buf);
 int mf_cnn_interp_cl(const void* grid_bf16, int s2d, const float* points /*[B,3,P]*/, int B,
                      int P, int C, int D, float divisor, void* feat_bf16, int ldf, int col_off,
                      void* stream);

@@ -44,6 +44,7 @@ class GemmParams(ctypes.Structure):
 
 
 GEMM_LINEAR, GEMM_CONV_S2D = 0, 1
+FEAT_LD = 1024          # row pitch (elements) of the [points, 984] concat feature and head-1 weights
 OUT_BF16, OUT_F32, OUT_S2D_BF16 = 0, 1, 2
 
 
@@ -132,9 +133,11 @@ class Model(torch.nn.Module):
             p[n + "/b"] = f32(m.bias)
         # heads: layer 1 of the three heads share their input -> one GEMM with N = 3*640
         heads = ("rot", "trans", "conf")
-        p["head1/W"] = torch.cat(
-            [getattr(self, f"conv1_{h}").weight.detach().reshape(640, 984) for h in heads], 0
-        ).to(torch.bfloat16).contiguous()
+        # row pitch padded 984 -> FEAT_LD so every 128-byte TMA row segment is line-aligned
+        # (K stays 984 in the tensor maps; the pad columns are never read)
+        W1 = torch.cat(
+            [getattr(self, f"conv1_{h}").weight.detach().reshape(640, 984) for h in heads], 0)
+        p["head1/W"] = torch.nn.functional.pad(W1, (0, FEAT_LD - 984)).to(torch.bfloat16).contiguous()
         p["head1/b"] = torch.cat([f32(getattr(self, f"conv1_{h}").bias) for h in heads])
         for h in heads:
             for layer in (2, 3, 4):
@@ -158,7 +161,7 @@ class Model(torch.nn.Module):
         z = lambda *s, dt=bf: torch.zeros(*s, dtype=dt, device=dev)     # noqa: E731
         NP = B * P
         b = dict(
-            feat=z(NP, 984), feat2=z(NP, 144, dt=f32),
+            feat=z(NP, FEAT_LD), feat2=z(NP, 144, dt=f32),
             x3=z(B, 17, 17, 17, 8 * Ct),          # s2d of the zero-padded 32^3 x Ct grid
             x4=z(B, 9, 9, 9, 8 * 256),            # s2d of the zero-padded 16^3 x 256 grid (= H3)
             h4=z(B, 8, 8, 8, 512),
@@ -265,7 +268,7 @@ class Model(torch.nn.Module):
                 _lib.ptr(w["conv1_pcd/W"]), _lib.ptr(w["conv1_pcd/b"]),
                 _lib.ptr(w["conv2_rgb/W"]), _lib.ptr(w["conv2_rgb/b"]),
                 _lib.ptr(w["conv2_pcd/W"]), _lib.ptr(w["conv2_pcd/b"]),
-                B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), 984, _lib.ptr(buf["feat2"]), s()),
+                B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), FEAT_LD, _lib.ptr(buf["feat2"]), s()),
                 "point_mlp")
             self.n_launches += 1
             Cocc = 16 if self._with_occupancy else 0
@@ -331,17 +334,17 @@ class Model(torch.nn.Module):
         s = _lib.stream
         with torch.cuda.device(dev):
             _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["x4"]), 1, _lib.ptr(points), B, P, 256, 16,
-                                          2.0, _lib.ptr(buf["feat"]), 984, 216, s()), "interp3")
+                                          2.0, _lib.ptr(buf["feat"]), FEAT_LD, 216, s()), "interp3")
             # conv4: 16^3 x 256 -> 8^3 x 512
             self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
                        64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
                        ldo=512)
             _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["h4"]), 0, _lib.ptr(points), B, P, 512, 8,
-                                          4.0, _lib.ptr(buf["feat"]), 984, 472, s()), "interp4")
+                                          4.0, _lib.ptr(buf["feat"]), FEAT_LD, 472, s()), "interp4")
             self.n_launches += 2
             # heads (model.py:239-254)
             self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
-                       lda=984, ldo=1920)
+                       lda=FEAT_LD, ldo=1920)
             heads = ("rot", "trans", "conf")
             # layers 2-4 of the three heads: one grouped launch per layer (grid.z = head)
             self._gemm_grouped(L, [dict(

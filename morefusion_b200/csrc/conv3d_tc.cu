@@ -278,9 +278,12 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
         // not 16-byte aligned, scalar stores
         float* dst = reinterpret_cast<float*>(p.out) + roff + n;
         const int nj = min(32, p.N - n);
-        for (int j = 0; j < nj; ++j) {
-          float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-          dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {      // static indices: keeps r[] in registers
+          if (j < nj) {
+            float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+            dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+          }
         }
         continue;
       }
@@ -338,7 +341,12 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
 // what the short-K head GEMMs (2-16 K blocks per tile) are dominated by in the one-shot kernel.
 struct TcSched {
   int m_tiles, n_tiles, groups, splitk, n_units;
+  long long* stamps;      // profiling hook (mf_gemm_tc_set_stamps): clock64 per role per unit, CTA 0
 };
+#define TC_STAMP(slot)                                                        \
+  do {                                                                        \
+    if (sc.stamps && blockIdx.x == 0 && it < 16) sc.stamps[it * 8 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void unit_decode(const TcSched& sc, int u, int& g, int& mt, int& nt,
                                             int& split) {
@@ -350,14 +358,19 @@ __device__ __forceinline__ void unit_decode(const TcSched& sc, int u, int& g, in
   g = r / sc.m_tiles;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool STAGED>
 __global__ void __launch_bounds__(256, 1)
 k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
   constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  constexpr int OUT_ROW_BYTES = BLOCK_N * 2 + 16;            // bf16 row + pad (bank spread)
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // bf16 output staging: one row per epilogue thread, drained to global memory with one
+  // cp.async.bulk per row (full-line writes issued by the copy engine instead of 32 scattered
+  // 16-byte stores per instruction through the LSU)
+  unsigned char* out_stage = smem + (size_t)STAGES * STAGE_BYTES;
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
@@ -398,10 +411,12 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
   if (warp == 0 && lane == 0) {
     // ===== TMA producer
     int kc = 0;                                        // K blocks issued so far (ring position)
-    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x) {
+    int it = 0;
+    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
       int g, mt, nt, split;
       unit_decode(sc, u, g, mt, nt, split);
       const GemmParams& p = args.p[g];
+      TC_STAMP(0);
       const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N;
       const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
       int cb = 0, cw = 0, ch = 0, cd = 0;
@@ -428,6 +443,7 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         }
         tma_load_2d(sb, &args.tmW[g], &full_bar[s], kb * TC_BLOCK_K, n0);
       }
+      TC_STAMP(1);
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer
@@ -442,12 +458,14 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4);    // epilogue has drained this buffer
       tcgen05_fence_after();
+      TC_STAMP(2);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = kb0; kb < kb1; ++kb, ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1;
         mbar_wait(&full_bar[s], ph, e.err, 2);
         tcgen05_fence_after();
+        if (kb == kb0) TC_STAMP(3);
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t adesc = make_sw128_desc(sa);
         const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
@@ -458,6 +476,7 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         umma_commit(&empty_bar[s]);
       }
       umma_commit(&tmem_full_bar[acc]);
+      TC_STAMP(4);
     }
   } else if (warp >= 4) {
     // ===== epilogue
@@ -472,10 +491,14 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], aph, e.err, 3);
       tcgen05_fence_after();
+      if (threadIdx.x == 128) TC_STAMP(5);
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const long long roff = row_ok ? out_row_offset(p, m) : 0;
       const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+      // the previous unit's bulk copy must have finished READING this thread's staging row
+      if (STAGED) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bool staged = false;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
@@ -485,9 +508,12 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         if (p.N & 31) {
           float* dst = reinterpret_cast<float*>(p.out) + roff + n;
           const int nj = min(32, p.N - n);
-          for (int j = 0; j < nj; ++j) {
-            float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-            dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {      // static indices: keeps r[] in registers
+            if (j < nj) {
+              float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+              dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+            }
           }
           continue;
         }
@@ -501,16 +527,27 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-          v[j] = p.relu ? fmaxf(x, 0.f) : x;
+        for (int j = 0; j < 8; ++j) {
+          float4 bq = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n) + j)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.out_mode == OUT_F32) {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + roff + n);
+          // STAGED: into this thread's shared-memory row, drained after the last chunk;
+          // otherwise straight to global memory (16-byte stores)
+          uint4* dst = STAGED ? reinterpret_cast<uint4*>(out_stage + (size_t)(q * 32 + lane) * OUT_ROW_BYTES + c0 * 2)
+                              : reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + roff + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
@@ -524,8 +561,24 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
             uu.w = *reinterpret_cast<uint32_t*>(&h3);
             dst[j] = uu;
           }
+          staged = STAGED;
         }
       }
+      if (threadIdx.x == 128) TC_STAMP(6);
+      if (staged) {
+        // generic-proxy writes -> async proxy, then one bulk copy of this thread's row
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (row_ok) {
+          const int ncols = min(BLOCK_N, p.N - n0);
+          const bf16* gdst = reinterpret_cast<const bf16*>(p.out) + roff + n0;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                       "r"(smem_u32(out_stage + (size_t)(q * 32 + lane) * OUT_ROW_BYTES)),
+                       "r"((uint32_t)(ncols * 2))
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (threadIdx.x == 128) TC_STAMP(7);
       // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
       tcgen05_fence_before();
       __syncwarp();
@@ -533,6 +586,7 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc]))
                      : "memory");
     }
+    if (STAGED) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // row copies landed
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -597,13 +651,20 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
   return r == CUDA_SUCCESS ? MF_OK : MF_E_BADARG;
 }
 
-template <int BLOCK_N, int STAGES>
+static long long* g_tc_stamps = nullptr;
+extern "C" int mf_gemm_tc_set_stamps(void* dev_buf) {
+  g_tc_stamps = reinterpret_cast<long long*>(dev_buf);
+  return MF_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool STAGED>
 static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t stream) {
-  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
+  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 +
+                       (STAGED ? TC_BLOCK_M * (BLOCK_N * 2 + 16) : 0);
   static bool attr = false;
   static int n_sm = 148;
   if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES>,
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES, STAGED>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     MF_CUDA_TRY(cudaGetDevice(&dev));
@@ -611,7 +672,7 @@ static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t
     attr = true;
   }
   int grid = sc.n_units < n_sm ? sc.n_units : n_sm;
-  k_gemm_tc_persistent<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(args, sc);
+  k_gemm_tc_persistent<BLOCK_N, STAGES, STAGED><<<grid, 256, smem, stream>>>(args, sc);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
@@ -736,9 +797,19 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   dim3 grid(n_tiles, m_tiles, splitk * n_groups);
   int rc;
   if (persistent_enabled()) {
-    TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk};
-    if (BN == 256) rc = launch_persistent<256, 4>(args, sc, stream);
-    else rc = launch_persistent<128, 6>(args, sc, stream);
+    TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk,
+               g_tc_stamps};
+    static const bool staged = [] {
+      const char* v = getenv("MF_GEMM_STAGED_EPILOGUE");
+      return v && v[0] == '1';
+    }();
+    if (staged) {
+      if (BN == 256) rc = launch_persistent<256, 3, true>(args, sc, stream);
+      else rc = launch_persistent<128, 5, true>(args, sc, stream);
+    } else {
+      if (BN == 256) rc = launch_persistent<256, 4, false>(args, sc, stream);
+      else rc = launch_persistent<128, 6, false>(args, sc, stream);
+    }
   } else if (BN == 256) rc = launch<256, 4>(args, grid, stream);
   else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;
