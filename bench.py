@@ -208,10 +208,12 @@ def run_ours(args, rank, world, local):
         runner.load_host(b)
         torch.cuda.synchronize()
         dev_sets.append({k: v.clone() for k, v in runner.st.items()})
-    pinned_sets = []
+    pinned_blobs = []                                 # one pinned host blob per rotating batch
     for b in batches:
         runner.load_host(b)
-        pinned_sets.append({k: v.clone().pin_memory() for k, v in runner.host_in.items()})
+        blob, _ = runner.new_host_blob()
+        blob.copy_(runner.host_in_blob)
+        pinned_blobs.append(blob)
     torch.cuda.synchronize()
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -252,21 +254,17 @@ def run_ours(args, rank, world, local):
 
     # ---- end to end: pinned host buffers in, pinned host poses out, copies inside the timing
     for i in range(3):
-        for k, v in pinned_sets[i % n_sets].items():
-            runner.host_in[k].copy_(v)
-        runner.upload(); runner.run(); runner.download()
+        runner.upload(pinned_blobs[i % n_sets]); runner.run(); runner.download()
     torch.cuda.synchronize()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier(world)
     torch.cuda.synchronize()
     for i in range(K):
-        src = pinned_sets[i % n_sets]
         flush.zero_()
         ev2[i][0].record()
-        for k in runner.st:
-            runner.st[k].copy_(src[k], non_blocking=True)     # H2D from pinned memory
+        runner.upload(pinned_blobs[i % n_sets])                # H2D from pinned memory (one copy)
         runner.run()
-        runner.download()                                      # D2H of rot/trans/conf
+        runner.download()                                      # D2H of rot/trans/conf (one copy)
         ev2[i][1].record()
     torch.cuda.synchronize()
     barrier(world)

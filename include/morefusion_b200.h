@@ -262,6 +262,15 @@ int mf_cnn_pose(const float* out_rot, const float* out_trans, const float* out_c
                 const float* points, const int32_t* class_id, const float* pitch,
                 const float* origin, int B, int P, int n_fg_class, float* rot /*[B,P,4]*/,
                 float* trans /*[B,P,3]*/, float* conf /*[B,P]*/, void* stream);
+/* last head layer (conv4_{rot,trans,conf}, model.py:249-254) fused with the pose epilogue: only
+ * the 4+3+1 output rows of each object's class are evaluated.  hd3 = bf16 [B*P, ld] holding the
+ * rot | trans | conf 128-channel blocks; weights bf16 [rows,128] row-major, biases fp32.  class_id
+ * is 1-based and must lie in [1, nfg] (as in the reference's indexing, model.py:256-262). */
+int mf_cnn_head4_pose(const void* hd3, int ld, const void* w_rot, const float* b_rot,
+                      const void* w_trans, const float* b_trans, const void* w_conf,
+                      const float* b_conf, const float* points, const int32_t* class_id,
+                      const float* pitch, const float* origin, int B, int P, int nfg, float* rot,
+                      float* trans, float* conf, void* stream);
 
 /* ------------------------------------------------------------------------
  * a8 / a9  IterativeCollisionCheckLink + its Adam loop, fused

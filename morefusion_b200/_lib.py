@@ -57,6 +57,7 @@ SIGNATURES = {
     "mf_gemm_bf16_tc_grouped": (c_i, [c_p, c_i, c_p, c_sz, c_p]),
     "mf_cnn_interp_cl": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_i, c_p]),
     "mf_cnn_pose": (c_i, [c_p] * 7 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "mf_cnn_head4_pose": (c_i, [c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "mf_icc_max_group_size": (c_i, [c_i]),
     "mf_icc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
     "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9

@@ -98,6 +98,11 @@ class Model(torch.nn.Module):
         self._wbufs = {}
         self.use_tensor_cores = True
         self.fused_voxelize = True
+        # independent branches (occupancy stencil || point MLP + voxelisation; conv3-level gather
+        # || conv4) run on a second stream; captured into the CUDA graphs as parallel branches
+        self.fused_head4 = True     # last head layer + class select + pose epilogue in one kernel
+        self.concurrent_branches = True
+        self._side_streams = {}
         self.launch_log = []
         self.n_launches = 0      # kernels of this library launched so far (bench's gpu_launches)
 
@@ -257,11 +262,46 @@ class Model(torch.nn.Module):
             self._pack()
         return L, dev, B, P, self._packed, self._work_buffers(B, P, dev)
 
+    def _side(self, dev):
+        key = (dev.type, dev.index)
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(dev)
+        return self._side_streams[key]
+
+    def _occ_branch(self, L, st, w, buf, B, D, Ct):
+        s = _lib.stream
+        g = st["gne"].to(torch.float32).contiguous()
+        if self.use_tensor_cores and D == 32:
+            _lib.check(L.mf_cnn_occ_convs_tc(
+                _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                _lib.ptr(buf["occ1_bf16"]), _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs_tc")
+        else:
+            _lib.check(L.mf_cnn_occ_convs(
+                _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                _lib.ptr(buf["occ1"]), None, _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs")
+        self.n_launches += 2
+        return g
+
     def _stage_pre(self, st):
         L, dev, B, P, w, buf = self._ctx(st)
         D = self._voxel_dim
         s = _lib.stream
         with torch.cuda.device(dev):
+            fused = self.fused_voxelize
+            if fused and buf.get("x3_dense_dirty", False):
+                buf["x3"].zero_()            # last call packed densely: sparse clear invalid
+                buf["x3_dense_dirty"] = False
+            forked = None
+            if fused and self._with_occupancy and self.concurrent_branches:
+                # the occupancy stencil writes channels [144,160) of x3, the point branch
+                # channels [0,144): disjoint bytes, no ordering needed between them
+                main, side = torch.cuda.current_stream(dev), self._side(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._occ_branch(L, st, w, buf, B, D, 144 + 16)
+                forked = (main, side)
             _lib.check(L.mf_cnn_point_mlp(
                 _lib.ptr(st["values"]), _lib.ptr(st["points"]),
                 _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
@@ -273,29 +313,19 @@ class Model(torch.nn.Module):
             self.n_launches += 1
             Cocc = 16 if self._with_occupancy else 0
             Ct = 144 + Cocc
-            g = st["gne"].to(torch.float32).contiguous() if self._with_occupancy else None
-            if self.fused_voxelize:
-                if buf.get("x3_dense_dirty", False):
-                    buf["x3"].zero_()            # last call packed densely: sparse clear invalid
-                    buf["x3_dense_dirty"] = False
+            g = (st["gne"].to(torch.float32).contiguous()
+                 if (self._with_occupancy and not fused) else None)
+            if fused:
                 # _voxelize (model.py:143-164) fused with the bf16 s2d packing; the occupancy
                 # stencil writes its 16 channels into the same buffer
                 _lib.check(L.mf_cnn_voxelize_s2d(
                     _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
                     _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "voxelize_s2d")
                 self.n_launches += 3
-                if self._with_occupancy and self.use_tensor_cores and D == 32:
-                    _lib.check(L.mf_cnn_occ_convs_tc(
-                        _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
-                        _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
-                        _lib.ptr(buf["occ1_bf16"]), _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs_tc")
-                    self.n_launches += 2
+                if forked:
+                    forked[0].wait_stream(forked[1])
                 elif self._with_occupancy:
-                    _lib.check(L.mf_cnn_occ_convs(
-                        _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
-                        _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
-                        _lib.ptr(buf["occ1"]), None, _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs")
-                    self.n_launches += 2
+                    self._occ_branch(L, st, w, buf, B, D, Ct)
             else:
                 # unfused reference composition: the public operator + an explicit pack
                 pts_np = st["points"].permute(0, 2, 1).reshape(B * P, 3).contiguous()
@@ -333,8 +363,21 @@ class Model(torch.nn.Module):
         points = st["points"]
         s = _lib.stream
         with torch.cuda.device(dev):
-            _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["x4"]), 1, _lib.ptr(points), B, P, 256, 16,
-                                          2.0, _lib.ptr(buf["feat"]), FEAT_LD, 216, s()), "interp3")
+            def interp3():
+                _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["x4"]), 1, _lib.ptr(points), B, P, 256,
+                                              16, 2.0, _lib.ptr(buf["feat"]), FEAT_LD, 216, s()),
+                           "interp3")
+            forked = None
+            if self.concurrent_branches:
+                # the conv3-level gather only reads x4: overlap it with conv4 (whose split-K
+                # launch leaves SMs idle)
+                main, side = torch.cuda.current_stream(dev), self._side(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    interp3()
+                forked = (main, side)
+            else:
+                interp3()
             # conv4: 16^3 x 256 -> 8^3 x 512
             self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
                        64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
@@ -342,6 +385,8 @@ class Model(torch.nn.Module):
             _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["h4"]), 0, _lib.ptr(points), B, P, 512, 8,
                                           4.0, _lib.ptr(buf["feat"]), FEAT_LD, 472, s()), "interp4")
             self.n_launches += 2
+            if forked:
+                forked[0].wait_stream(forked[1])
             # heads (model.py:239-254)
             self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
                        lda=FEAT_LD, ldo=1920)
@@ -355,6 +400,20 @@ class Model(torch.nn.Module):
                 A=buf["hd2"][:, i * 256:], W=w[f"conv3_{h}/W"], bias=w[f"conv3_{h}/b"],
                 out=buf["hd3"], M=NP, N=128, K=256, lda=768, ldo=384, col_off=i * 128)
                 for i, h in enumerate(heads)])
+            if self.fused_head4:
+                # layer 4 + class selection + pose epilogue in one kernel (only the object's
+                # class rows are evaluated)
+                _lib.check(L.mf_cnn_head4_pose(
+                    _lib.ptr(buf["hd3"]), 384,
+                    _lib.ptr(w["conv4_rot/W"]), _lib.ptr(w["conv4_rot/b"]),
+                    _lib.ptr(w["conv4_trans/W"]), _lib.ptr(w["conv4_trans/b"]),
+                    _lib.ptr(w["conv4_conf/W"]), _lib.ptr(w["conv4_conf/b"]),
+                    _lib.ptr(points), _lib.ptr(st["class_id"]), _lib.ptr(st["pitch"]),
+                    _lib.ptr(st["origin"]), B, P, nfg,
+                    _lib.ptr(out["rot"]), _lib.ptr(out["trans"]), _lib.ptr(out["conf"]), s()),
+                    "head4_pose")
+                self.n_launches += 1
+                return
             self._gemm_grouped(L, [dict(
                 A=buf["hd3"][:, i * 128:], W=w[f"conv4_{h}/W"], bias=w[f"conv4_{h}/b"],
                 out=buf["out_" + h], M=NP, N=buf["out_" + h].shape[1], K=128, lda=384, relu=0,
@@ -379,25 +438,47 @@ class Runner:
     def __init__(self, model, B, P, device, graph=True):
         self.model, self.B, self.P, self.device = model, B, P, device
         f32 = torch.float32
-        self.st = dict(
-            values=torch.zeros((B, 32, P), dtype=f32, device=device),
-            points=torch.zeros((B, 3, P), dtype=f32, device=device),
-            class_id=torch.ones((B,), dtype=torch.int32, device=device),
-            pitch=torch.ones((B,), dtype=f32, device=device),
-            origin=torch.zeros((B, 3), dtype=f32, device=device),
-            gne=torch.zeros((B, 32, 32, 32), dtype=torch.uint8, device=device))
-        self.out = dict(rot=torch.zeros((B, P, 4), dtype=f32, device=device),
-                        trans=torch.zeros((B, P, 3), dtype=f32, device=device),
-                        conf=torch.zeros((B, P), dtype=f32, device=device))
-        self.host_in = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in self.st.items()}
-        self.host_out = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in self.out.items()}
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.st.values())
-        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.out.values())
+        # inputs and outputs live in ONE device blob / ONE pinned host blob each, so a step's
+        # host->device and device->host traffic is a single copy either way
+        in_spec = [("values", (B, 32, P), f32), ("points", (B, 3, P), f32),
+                   ("class_id", (B,), torch.int32), ("pitch", (B,), f32),
+                   ("origin", (B, 3), f32), ("gne", (B, 32, 32, 32), torch.uint8)]
+        out_spec = [("rot", (B, P, 4), f32), ("trans", (B, P, 3), f32), ("conf", (B, P), f32)]
+        self._in_spec, self._out_spec = in_spec, out_spec
+        self.in_blob, self.st = self._blob(in_spec, device)
+        self.out_blob, self.out = self._blob(out_spec, device)
+        self.st["class_id"].fill_(1)
+        self.st["pitch"].fill_(1.0)
+        self.host_in_blob, self.host_in = self._blob(in_spec, "cpu")
+        self.host_out_blob, self.host_out = self._blob(out_spec, "cpu")
+        self.h2d_bytes = self.in_blob.numel()
+        self.d2h_bytes = self.out_blob.numel()
         self.graphs = None
         self.ev = None
         self.launches_per_step = None
         if graph:
             self._capture()
+
+    @staticmethod
+    def _blob(spec, device):
+        """One uint8 allocation with a 256-byte aligned typed view per entry."""
+        offs, total = [], 0
+        for _, shape, dt in spec:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            offs.append(total)
+            total += (n + 255) // 256 * 256
+        blob = torch.zeros(total, dtype=torch.uint8, device=device)
+        if str(device) == "cpu":
+            blob = blob.pin_memory()
+        views = {}
+        for (name, shape, dt), o in zip(spec, offs):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            views[name] = blob[o:o + n].view(dt).view(shape)
+        return blob, views
+
+    def new_host_blob(self):
+        """A further pinned input blob with the same layout (for rotating host batches)."""
+        return self._blob(self._in_spec, "cpu")
 
     def _eager(self):
         m = self.model
@@ -450,11 +531,12 @@ class Runner:
             v.copy_(torch.as_tensor(src).to(v.dtype))
         self.upload()
 
-    def upload(self):
-        for k, v in self.host_in.items():
-            self.st[k].copy_(v, non_blocking=True)
+    def upload(self, host_blob=None):
+        """One async H2D copy of a pinned input blob (default: this runner's own)."""
+        self.in_blob.copy_(self.host_in_blob if host_blob is None else host_blob,
+                           non_blocking=True)
 
     def download(self):
-        for k, v in self.out.items():
-            self.host_out[k].copy_(v, non_blocking=True)
+        """One async D2H copy of rot/trans/conf into the pinned output blob."""
+        self.host_out_blob.copy_(self.out_blob, non_blocking=True)
         return self.host_out

@@ -735,6 +735,8 @@ __global__ void k_pose(const float* __restrict__ out_rot,    // [B*P, nfg*4]
   if (n >= (long long)B * P) return;
   long long b = n / P, p = n % P;
   int fg = class_id[b] - 1;
+  if (fg < 0) fg += nfg;                  // python-style wrap of the reference's fancy index
+  fg = min(max(fg, 0), nfg - 1);
   const float* q = out_rot + n * (nfg * 4) + fg * 4;
   float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + 1e-5f;  // F.normalize
 #pragma unroll
@@ -747,6 +749,79 @@ __global__ void k_pose(const float* __restrict__ out_rot,    // [B*P, nfg*4]
   }
   float cf = out_conf[n * nfg + fg];
   conf[n] = 1.f / (1.f + expf(-cf));
+}
+
+
+// ---- last head layer fused with the pose epilogue ------------------------------------------
+// The reference evaluates conv4_{rot,trans,conf} for all n_fg classes and then keeps the rows of
+// the object's class (model.py:249-262).  Only those 4 + 3 + 1 rows are computed here: a CTA
+// handles 128 points of ONE object, stages the 8 weight rows of its class in shared memory as
+// fp32, and each thread does the 8 K=128 dot products of its point (bf16 operands, fp32
+// accumulate, k ascending) followed by the epilogue of k_pose.
+__global__ void __launch_bounds__(128)
+k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: rot|trans|conf x 128
+             const bf16* __restrict__ w_rot, const float* __restrict__ b_rot,      // [nfg*4,128]
+             const bf16* __restrict__ w_trans, const float* __restrict__ b_trans,  // [nfg*3,128]
+             const bf16* __restrict__ w_conf, const float* __restrict__ b_conf,    // [nfg,128]
+             const float* __restrict__ points, const int* __restrict__ class_id,
+             const float* __restrict__ pitch, const float* __restrict__ origin, int B, int P,
+             int nfg, float* __restrict__ rot, float* __restrict__ trans,
+             float* __restrict__ conf) {
+  __shared__ float w[8][128];
+  __shared__ float bias[8];
+  const int b = blockIdx.y;
+  int fg = class_id[b] - 1;
+  if (fg < 0) fg += nfg;                  // python-style wrap of the reference's fancy index
+  fg = min(max(fg, 0), nfg - 1);
+  for (int e = threadIdx.x; e < 8 * 128; e += 128) {
+    int r = e >> 7, k = e & 127;
+    const bf16* src = r < 4 ? w_rot + (size_t)(fg * 4 + r) * 128
+                    : r < 7 ? w_trans + (size_t)(fg * 3 + r - 4) * 128
+                            : w_conf + (size_t)fg * 128;
+    w[r][k] = __bfloat162float(src[k]);
+  }
+  if (threadIdx.x < 8) {
+    int r = threadIdx.x;
+    bias[r] = r < 4 ? b_rot[fg * 4 + r] : r < 7 ? b_trans[fg * 3 + r - 4] : b_conf[fg];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= P) return;
+  const long long n = (long long)b * P + p;
+  const bf16* h = hd3 + n * ld;
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll
+  for (int seg = 0; seg < 3; ++seg) {                 // rot / trans / conf feature blocks
+    const int r0 = seg == 0 ? 0 : seg == 1 ? 4 : 7, r1 = seg == 0 ? 4 : seg == 1 ? 7 : 8;
+    const uint4* hv = reinterpret_cast<const uint4*>(h + seg * 128);
+#pragma unroll 4
+    for (int v = 0; v < 16; ++v) {
+      uint4 u = __ldg(hv + v);
+      const bf16* hb = reinterpret_cast<const bf16*>(&u);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __bfloat162float(hb[j]);
+#pragma unroll
+      for (int r = r0; r < r1; ++r) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r] = fmaf(w[r][v * 8 + j], x[j], acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] += bias[r];
+  float nrm = sqrtf(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3]) + 1e-5f;
+  *reinterpret_cast<float4*>(rot + n * 4) =
+      make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
+  const float pt = pitch[b];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float cam = points[((long long)b * 3 + k) * P + p] * pt + origin[b * 3 + k];
+    trans[n * 3 + k] = cam + acc[4 + k] * pt;
+  }
+  conf[n] = 1.f / (1.f + expf(-acc[7]));
 }
 
 }  // namespace mf
@@ -900,6 +975,24 @@ extern "C" int mf_cnn_pose(const float* out_rot, const float* out_trans, const f
     return MF_E_BADARG;
   k_pose<<<div_up((long long)B * P, 128), 128, 0, (cudaStream_t)stream_>>>(
       out_rot, out_trans, out_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_head4_pose(const void* hd3, int ld, const void* w_rot, const float* b_rot,
+                                 const void* w_trans, const float* b_trans, const void* w_conf,
+                                 const float* b_conf, const float* points,
+                                 const int32_t* class_id, const float* pitch, const float* origin,
+                                 int B, int P, int nfg, float* rot, float* trans, float* conf,
+                                 void* stream_) {
+  if (B <= 0 || P <= 0 || nfg <= 0 || ld < 384 || (ld & 7) || B > 65535) return MF_E_BADARG;
+  if (!hd3 || !w_rot || !b_rot || !w_trans || !b_trans || !w_conf || !b_conf || !points ||
+      !class_id || !pitch || !origin || !rot || !trans || !conf)
+    return MF_E_BADARG;
+  dim3 grid((unsigned)div_up(P, 128), (unsigned)B);
+  k_head4_pose<<<grid, 128, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)hd3, ld, (const bf16*)w_rot, b_rot, (const bf16*)w_trans, b_trans,
+      (const bf16*)w_conf, b_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

@@ -75,10 +75,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a broken pipeline must not hang the GPU (traps after ~2 s)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+// Bounded wait.  `backoff_ns` > 0 parks the polling thread between polls (__nanosleep) so that
+// waiting roles do not take issue slots from the roles doing work on the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code,
+                                          unsigned backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (backoff_ns) __nanosleep(backoff_ns);
     if (clock64() - t0 > 4000000000LL) {
       if (err) atomicExch(err, code);
       __threadfence_system();
@@ -148,6 +152,57 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// explicit shared-space accesses (the staging pointer is derived from a generic pointer, which
+// would otherwise compile to generic LD/ST)
+__device__ __forceinline__ void sts_v4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+// issue only; pair with tmem_ld_wait(r) before reading r (the wait names r as in/out operands so
+// the compiler cannot move reads of r above it)
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                 "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                 "+r"(r[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ long long out_row_offset(const GemmParams& p, int m) {
@@ -358,19 +413,18 @@ __device__ __forceinline__ void unit_decode(const TcSched& sc, int u, int& g, in
   g = r / sc.m_tiles;
 }
 
-template <int BLOCK_N, int STAGES, bool STAGED>
-__global__ void __launch_bounds__(256, 1)
+constexpr int TC_P_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-11: epilogue
+constexpr int TC_STG_BYTES = 32 * 128;   // per-epilogue-warp staging tile
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_P_THREADS, 1)
 k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
   constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  constexpr int OUT_ROW_BYTES = BLOCK_N * 2 + 16;            // bf16 row + pad (bank spread)
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  // bf16 output staging: one row per epilogue thread, drained to global memory with one
-  // cp.async.bulk per row (full-line writes issued by the copy engine instead of 32 scattered
-  // 16-byte stores per instruction through the LSU)
-  unsigned char* out_stage = smem + (size_t)STAGES * STAGE_BYTES;
+  unsigned char* out_stage = smem + (size_t)STAGES * STAGE_BYTES;   // 8 x TC_STG_BYTES
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
@@ -392,8 +446,8 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4);       // one arrival per epilogue warp
-    mbar_init(&tmem_empty_bar[1], 4);
+    mbar_init(&tmem_empty_bar[0], 8);       // one arrival per epilogue warp
+    mbar_init(&tmem_empty_bar[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -430,7 +484,7 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       for (int kb = kb0; kb < kb1; ++kb, ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, e.err, 1);
+        mbar_wait(&empty_bar[s], ph ^ 1, e.err, 1, 64);
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
         unsigned char* sb = sa + TC_A_BYTES;
@@ -456,14 +510,14 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4);    // epilogue has drained this buffer
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4, 32);    // epilogue has drained this buffer
       tcgen05_fence_after();
       TC_STAMP(2);
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = kb0; kb < kb1; ++kb, ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (kc / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph, e.err, 2);
+        mbar_wait(&full_bar[s], ph, e.err, 2, 20);
         tcgen05_fence_after();
         if (kb == kb0) TC_STAMP(3);
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -479,114 +533,153 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       TC_STAMP(4);
     }
   } else if (warp >= 4) {
-    // ===== epilogue
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps.  Warp w reads TMEM lane quarter w%4 (hardware rule) and the
+    // column half (w-4)/4 of the tile, so a tile is drained by two warps per lane quarter.
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    constexpr int EPI_COLS = BLOCK_N / 2, NCH = EPI_COLS / 32;
+    const uint32_t stg_s = smem_u32(out_stage + (size_t)(warp - 4) * TC_STG_BYTES);  // 32 rows x 128 B
     int it = 0;
     for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
       int g, mt, nt, split;
       unit_decode(sc, u, g, mt, nt, split);
       const GemmParams& p = args.p[g];
-      const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N;
+      const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N + hsel * EPI_COLS;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], aph, e.err, 3);
+      mbar_wait(&tmem_full_bar[acc], aph, e.err, 3, 128);
       tcgen05_fence_after();
       if (threadIdx.x == 128) TC_STAMP(5);
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const long long roff = row_ok ? out_row_offset(p, m) : 0;
-      const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      // the previous unit's bulk copy must have finished READING this thread's staging row
-      if (STAGED) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      bool staged = false;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tacc + (uint32_t)c0, r);
-        const int n = n0 + c0;
-        if (!row_ok || n >= p.N) continue;
-        if (p.N & 31) {
-          float* dst = reinterpret_cast<float*>(p.out) + roff + n;
-          const int nj = min(32, p.N - n);
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N + hsel * EPI_COLS) +
+                            ((uint32_t)(q * 32) << 16);
+      const bool coalesced_bf16 = !(p.N & 31) && e.splitk == 1 && p.out_mode != OUT_F32;
+      if (coalesced_bf16) {
+        // bf16 outputs.  Chunks of 32 columns: the tcgen05.ld of chunk c+1 is in flight while
+        // chunk c gets bias/ReLU/convert.  Two chunks (64 columns = 128 B per row) are staged in
+        // this warp's XOR-swizzled shared-memory tile and written out with row-contiguous
+        // 16-byte stores: one instruction covers 4 rows x 128 B (whole lines) instead of 32
+        // rows x 16 B.
+        const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+        const bool relu = p.relu != 0;
+        const int Nn = p.N;
+        const float* __restrict__ bias = p.bias;
+        bf16* __restrict__ outp = reinterpret_cast<bf16*>(p.out);
+        long long rofs[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {      // static indices: keeps r[] in registers
-            if (j < nj) {
-              float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-              dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+        for (int i = 0; i < 8; ++i) rofs[i] = __shfl_sync(0xffffffffu, roff, i * 4 + (lane >> 3));
+        uint32_t ra[32], rb[32];
+        auto process = [&](uint32_t (&r)[32], int c) {
+          const int n = n0 + c * 32;
+          if (n < Nn) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bq = bias ? __ldg(reinterpret_cast<const float4*>(bias + n) + j)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 uu;
+              if (relu) {       // ReLU folded into the conversion (cvt.rn.relu)
+                uu.x = pack_bf16x2_relu(v[8 * j + 0], v[8 * j + 1]);
+                uu.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
+                uu.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]);
+                uu.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
+              } else {
+                uu.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                uu.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                uu.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                uu.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              }
+              const int piece = ((c & 1) * 4 + j) ^ (lane & 7);
+              sts_v4(stg_s + lane * 128 + piece * 16, uu);
             }
           }
-          continue;
-        }
-        if (e.splitk > 1) {
-          float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
+          if (c & 1) {
+            // flush the 64 staged columns [n0 + (c-1)*32, +64)
+            __syncwarp();
+            const int ncol = n0 + (c - 1) * 32 + (lane & 7) * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          continue;
-        }
-        float v[32];
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);
+              const uint4 uu = lds_v4(stg_s + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+              if (((okmask >> row) & 1u) && ncol < Nn)
+                *reinterpret_cast<uint4*>(outp + rofs[i] + ncol) = uu;
+            }
+            __syncwarp();
+          }
+        };
+        tmem_ld_32x32_issue(tacc, ra);
+        tmem_ld_wait(ra);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 bq = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n) + j)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+        for (int c = 0; c < NCH; c += 2) {
+          tmem_ld_32x32_issue(tacc + (uint32_t)((c + 1) * 32), rb);
+          process(ra, c);
+          tmem_ld_wait(rb);
+          if (c + 2 < NCH) tmem_ld_32x32_issue(tacc + (uint32_t)((c + 2) * 32), ra);
+          process(rb, c + 1);
+          if (c + 2 < NCH) tmem_ld_wait(ra);
         }
-        if (p.relu) {
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tacc + (uint32_t)c0, r);
+          const int n = n0 + c0;
+          if (!row_ok || n >= p.N) continue;
+          if (p.N & 31) {
+            // ragged N (small-N heads, fp32 row-major output only; enforced on the host)
+            float* dst = reinterpret_cast<float*>(p.out) + roff + n;
+            const int nj = min(32, p.N - n);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.out_mode == OUT_F32) {
+            for (int j = 0; j < 32; ++j) {      // static indices: keeps r[] in registers
+              if (j < nj) {
+                float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+              }
+            }
+            continue;
+          }
+          if (e.splitk > 1) {
+            float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            continue;
+          }
+          // fp32 row-major output with bias / ReLU
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff + n);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          // STAGED: into this thread's shared-memory row, drained after the last chunk;
-          // otherwise straight to global memory (16-byte stores)
-          uint4* dst = STAGED ? reinterpret_cast<uint4*>(out_stage + (size_t)(q * 32 + lane) * OUT_ROW_BYTES + c0 * 2)
-                              : reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + roff + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-            uint4 uu;
-            uu.x = *reinterpret_cast<uint32_t*>(&h0);
-            uu.y = *reinterpret_cast<uint32_t*>(&h1);
-            uu.z = *reinterpret_cast<uint32_t*>(&h2);
-            uu.w = *reinterpret_cast<uint32_t*>(&h3);
-            dst[j] = uu;
+          for (int j = 0; j < 8; ++j) {
+            float4 bq = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n) + j)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o = make_float4(__uint_as_float(r[4 * j + 0]) + bq.x,
+                                   __uint_as_float(r[4 * j + 1]) + bq.y,
+                                   __uint_as_float(r[4 * j + 2]) + bq.z,
+                                   __uint_as_float(r[4 * j + 3]) + bq.w);
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            dst[j] = o;
           }
-          staged = STAGED;
         }
       }
       if (threadIdx.x == 128) TC_STAMP(6);
-      if (staged) {
-        // generic-proxy writes -> async proxy, then one bulk copy of this thread's row
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (row_ok) {
-          const int ncols = min(BLOCK_N, p.N - n0);
-          const bf16* gdst = reinterpret_cast<const bf16*>(p.out) + roff + n0;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                       "r"(smem_u32(out_stage + (size_t)(q * 32 + lane) * OUT_ROW_BYTES)),
-                       "r"((uint32_t)(ncols * 2))
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (threadIdx.x == 128) TC_STAMP(7);
       // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc]))
                      : "memory");
+      if (threadIdx.x == 128) TC_STAMP(7);
     }
-    if (STAGED) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // row copies landed
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -657,14 +750,13 @@ extern "C" int mf_gemm_tc_set_stamps(void* dev_buf) {
   return MF_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool STAGED>
+template <int BLOCK_N, int STAGES>
 static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t stream) {
-  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 +
-                       (STAGED ? TC_BLOCK_M * (BLOCK_N * 2 + 16) : 0);
+  constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
   static bool attr = false;
   static int n_sm = 148;
   if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES, STAGED>,
+    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     MF_CUDA_TRY(cudaGetDevice(&dev));
@@ -672,7 +764,7 @@ static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t
     attr = true;
   }
   int grid = sc.n_units < n_sm ? sc.n_units : n_sm;
-  k_gemm_tc_persistent<BLOCK_N, STAGES, STAGED><<<grid, 256, smem, stream>>>(args, sc);
+  k_gemm_tc_persistent<BLOCK_N, STAGES><<<grid, TC_P_THREADS, smem, stream>>>(args, sc);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
@@ -799,17 +891,8 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   if (persistent_enabled()) {
     TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk,
                g_tc_stamps};
-    static const bool staged = [] {
-      const char* v = getenv("MF_GEMM_STAGED_EPILOGUE");
-      return v && v[0] == '1';
-    }();
-    if (staged) {
-      if (BN == 256) rc = launch_persistent<256, 3, true>(args, sc, stream);
-      else rc = launch_persistent<128, 5, true>(args, sc, stream);
-    } else {
-      if (BN == 256) rc = launch_persistent<256, 4, false>(args, sc, stream);
-      else rc = launch_persistent<128, 6, false>(args, sc, stream);
-    }
+    if (BN == 256) rc = launch_persistent<256, 4>(args, sc, stream);
+    else rc = launch_persistent<128, 6>(args, sc, stream);
   } else if (BN == 256) rc = launch<256, 4>(args, grid, stream);
   else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;

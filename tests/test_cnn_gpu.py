@@ -115,3 +115,62 @@ def test_fused_voxelize_equals_operator_composition(cuda_device):
     same(x3_of(b, True), ref_b)     # sparse clear of a's voxels
     same(x3_of(c, True), ref_c)
     assert torch.equal(x3_of(a, False), ref_a)    # and back
+
+
+def test_fused_head4_and_concurrent_branches_equal_sequential(cuda_device):
+    """Last head layer fused with class selection + pose epilogue, and the two-stream branch
+    overlap, give the same poses as the sequential grouped-GEMM + k_pose composition (fp32
+    accumulation order differs between the tensor-core GEMM and the fused dot products)."""
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    B = 3
+    w = ocnn.init_weights(21, seed=4)
+    inp = make_inputs(B, seed=11)
+    m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)
+
+    def run(fused, conc):
+        m.fused_head4, m.concurrent_branches = fused, conc
+        out = m.forward_features(
+            class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+            values=torch.as_tensor(inp["values"], device=cuda_device),
+            points=torch.as_tensor(inp["points"], device=cuda_device),
+            pitch=inp["pitch"], origin=inp["origin"],
+            grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device))
+        torch.cuda.synchronize()
+        return [o.clone() for o in out]
+
+    base = run(False, False)
+    conc = run(False, True)
+    for a, b in zip(base, conc):                      # same kernels, only the schedule differs
+        assert torch.equal(a, b)
+    fused = run(True, True)
+    # raw head outputs are O(1); fp32 summation-order differences only
+    torch.testing.assert_close(fused[1], base[1], rtol=0, atol=1e-5)     # trans
+    torch.testing.assert_close(fused[2], base[2], rtol=0, atol=1e-5)     # conf
+    drot = (fused[0] - base[0]).abs()
+    assert float(drot.max()) <= 1e-3 and float(drot.mean()) <= 1e-5, (drot.max(), drot.mean())
+
+
+def test_runner_graph_equals_forward_features(cuda_device):
+    """The serving entry (pinned host blob -> one H2D copy -> captured CUDA graphs -> one D2H
+    copy) returns exactly what forward_features computes for the same batch, across batches."""
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    B = 2
+    w = ocnn.init_weights(21, seed=6)
+    m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)
+    runner = m.make_runner(B, 1000, cuda_device, graph=True)
+    for seed in (21, 22, 23):
+        inp = make_inputs(B, seed=seed)
+        runner.load_host(inp)
+        runner.run()
+        host = runner.download()
+        torch.cuda.synchronize()
+        got = [host[k].clone() for k in ("rot", "trans", "conf")]
+        want = m.forward_features(
+            class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+            values=torch.as_tensor(inp["values"], device=cuda_device),
+            points=torch.as_tensor(inp["points"], device=cuda_device),
+            pitch=inp["pitch"], origin=inp["origin"],
+            grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device))
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b.cpu())
