@@ -562,10 +562,14 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         // 16-byte stores: one instruction covers 4 rows x 128 B (whole lines) instead of 32
         // rows x 16 B.
         const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
-        const bool relu = p.relu != 0;
-        const int Nn = p.N;
-        const float* __restrict__ bias = p.bias;
-        bf16* __restrict__ outp = reinterpret_cast<bf16*>(p.out);
+        // p = args.p[g] is an indexed constant-bank access (long latency).  Pin the fields the
+        // hot loop needs in registers; the empty asm makes them opaque so the compiler cannot
+        // rematerialise them with another indexed LDC in front of every store.
+        int relu_i = p.relu, Nn = p.N;
+        const float* bias = p.bias;
+        bf16* outp = reinterpret_cast<bf16*>(p.out);
+        asm volatile("" : "+r"(relu_i), "+r"(Nn), "+l"(bias), "+l"(outp));
+        const bool relu = relu_i != 0;
         long long rofs[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rofs[i] = __shfl_sync(0xffffffffu, roff, i * 4 + (lane >> 3));
@@ -627,27 +631,31 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
           if (c + 2 < NCH) tmem_ld_wait(ra);
         }
       } else {
+        int pN = p.N, pM = p.M, prelu = p.relu, pmode = p.out_mode;
+        const float* pbias = p.bias;
+        void* pout = p.out;
+        asm volatile("" : "+r"(pN), "+r"(pM), "+r"(prelu), "+r"(pmode), "+l"(pbias), "+l"(pout));
 #pragma unroll 1
         for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tacc + (uint32_t)c0, r);
           const int n = n0 + c0;
-          if (!row_ok || n >= p.N) continue;
-          if (p.N & 31) {
+          if (!row_ok || n >= pN) continue;
+          if (pN & 31) {
             // ragged N (small-N heads, fp32 row-major output only; enforced on the host)
-            float* dst = reinterpret_cast<float*>(p.out) + roff + n;
-            const int nj = min(32, p.N - n);
+            float* dst = reinterpret_cast<float*>(pout) + roff + n;
+            const int nj = min(32, pN - n);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {      // static indices: keeps r[] in registers
               if (j < nj) {
-                float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-                dst[j] = p.relu ? fmaxf(x, 0.f) : x;
+                float x = __uint_as_float(r[j]) + (pbias ? __ldg(pbias + n + j) : 0.f);
+                dst[j] = prelu ? fmaxf(x, 0.f) : x;
               }
             }
             continue;
           }
           if (e.splitk > 1) {
-            float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * p.M + m) * p.N + n);
+            float4* dst = reinterpret_cast<float4*>(e.ws + ((long long)split * pM + m) * pN + n);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -655,16 +663,16 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
             continue;
           }
           // fp32 row-major output with bias / ReLU
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff + n);
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(pout) + roff + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bq = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n) + j)
+            float4 bq = pbias ? __ldg(reinterpret_cast<const float4*>(pbias + n) + j)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 o = make_float4(__uint_as_float(r[4 * j + 0]) + bq.x,
                                    __uint_as_float(r[4 * j + 1]) + bq.y,
                                    __uint_as_float(r[4 * j + 2]) + bq.z,
                                    __uint_as_float(r[4 * j + 3]) + bq.w);
-            if (p.relu) {
+            if (prelu) {
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
             dst[j] = o;

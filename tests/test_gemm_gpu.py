@@ -29,7 +29,8 @@ def _call(kind, A, W, bias, out, M, N, K, **kw):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (8000, 1920, 984),
-                                   (8000, 256, 640), (1000, 128, 256), (4096, 512, 2048)])
+                                   (8000, 256, 640), (1000, 128, 256), (4096, 512, 2048),
+                                   (4096, 512, 8192), (2304, 256, 4096)])   # last two: split-K
 def test_tc_linear(cuda_device, M, N, K):
     torch.manual_seed(0)
     A = torch.randn(M, K, device=cuda_device).to(torch.bfloat16)
