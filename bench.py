@@ -238,16 +238,23 @@ def run_ours(args, rank, world, local):
     for i in range(K):
         set_inputs(i)
         flush.zero_()                     # L2 flush between timed iterations (untimed)
-        runner.set_events(*cev[i])
         ev[i][0].record()
-        runner.run()
+        runner.run()                      # whole step = one captured graph
         ev[i][1].record()
     torch.cuda.synchronize()
     barrier(world)
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    conv3_ms = [a.elapsed_time(b) for a, b in cev]
     total_ms = max_over_ranks(sum(step_ms), world, dev)
+    # second pass over the same K steps with the step split into three graphs so that the
+    # dominant kernel (conv3) is bracketed by events on the launching stream (roofline)
+    for i in range(K):
+        set_inputs(i)
+        flush.zero_()
+        runner.set_events(*cev[i])
+        runner.run()
+    torch.cuda.synchronize()
+    conv3_ms = [a.elapsed_time(b) for a, b in cev]
     launches = runner.launches_per_step * K if runner.graphs is not None else model.n_launches - n0
     runner.ev = None
     value = world * B_PER_RANK * K / (total_ms * 1e-3)
@@ -284,11 +291,13 @@ def run_ours(args, rank, world, local):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = dict(bound="tensor", kernel="k_gemm_tc<256,4> (conv3 160->256 k4 s2, implicit GEMM M=32768 N=256 K=10240)",
+    roof = dict(bound="tensor", kernel="k_gemm_tc_persistent<256,4> (conv3 160->256 k4 s2, implicit GEMM M=32768 N=256 K=10240)",
                 achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
                 frac=achieved / pk["bf16_sustained"], frac_of_burst_peak=achieved / pk["bf16"],
                 peak_source=pk["source"] + ", sustained figure (kernel timed inside the step)",
                 avg_launch_us=conv3_avg_ms * 1e3, share_of_step=conv3_avg_ms / float(np.mean(step_ms)),
+                timed="CUDA events around the conv3 launch in a second pass over the same K steps "
+                      "(step split into 3 graphs); `value` times the one-graph step",
                 traffic=traffic)
     # ---- CPU baseline: oracle port on the host cores, bounded sample
     threads = pick_threads(weights, batches[0])

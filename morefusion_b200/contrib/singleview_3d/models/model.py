@@ -509,6 +509,13 @@ class Runner:
                 fn()
             gs.append(g)
         self.graphs = gs
+        # the whole step as ONE graph (used whenever conv3 is not being timed on its own)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            m._stage_pre(self.st)
+            m._stage_conv3(self.st)
+            m._stage_post(self.st, self.out)
+        self.graph_step = g
 
     def set_events(self, e0, e1):
         self.ev = (e0, e1)
@@ -516,6 +523,8 @@ class Runner:
     def run(self):
         if self.graphs is None:
             return self._eager()
+        if not self.ev:
+            return self.graph_step.replay()
         self.graphs[0].replay()
         if self.ev:
             self.ev[0].record()

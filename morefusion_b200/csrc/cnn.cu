@@ -754,11 +754,13 @@ __global__ void k_pose(const float* __restrict__ out_rot,    // [B*P, nfg*4]
 
 // ---- last head layer fused with the pose epilogue ------------------------------------------
 // The reference evaluates conv4_{rot,trans,conf} for all n_fg classes and then keeps the rows of
-// the object's class (model.py:249-262).  Only those 4 + 3 + 1 rows are computed here: a CTA
-// handles 128 points of ONE object, stages the 8 weight rows of its class in shared memory as
-// fp32, and each thread does the 8 K=128 dot products of its point (bf16 operands, fp32
-// accumulate, k ascending) followed by the epilogue of k_pose.
-__global__ void __launch_bounds__(128)
+// the object's class (model.py:249-262).  Only those 4 + 3 + 1 rows are computed here.  A CTA
+// handles 32 points of ONE object and stages the 8 weight rows of its class in shared memory
+// (fp32, rows padded to 132 floats so the 8 rows fall into different banks); 8 consecutive lanes
+// own one point, lane r computing output row r as a K=128 dot product (bf16 operands, fp32
+// accumulate, k ascending).  The pose epilogue of k_pose follows after an 8-lane exchange.
+constexpr int kH4Pts = 32;
+__global__ void __launch_bounds__(256)
 k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: rot|trans|conf x 128
              const bf16* __restrict__ w_rot, const float* __restrict__ b_rot,      // [nfg*4,128]
              const bf16* __restrict__ w_trans, const float* __restrict__ b_trans,  // [nfg*3,128]
@@ -767,13 +769,13 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
              const float* __restrict__ pitch, const float* __restrict__ origin, int B, int P,
              int nfg, float* __restrict__ rot, float* __restrict__ trans,
              float* __restrict__ conf) {
-  __shared__ float w[8][128];
+  __shared__ __align__(16) float w[8][132];
   __shared__ float bias[8];
   const int b = blockIdx.y;
   int fg = class_id[b] - 1;
   if (fg < 0) fg += nfg;                  // python-style wrap of the reference's fancy index
   fg = min(max(fg, 0), nfg - 1);
-  for (int e = threadIdx.x; e < 8 * 128; e += 128) {
+  for (int e = threadIdx.x; e < 8 * 128; e += 256) {
     int r = e >> 7, k = e & 127;
     const bf16* src = r < 4 ? w_rot + (size_t)(fg * 4 + r) * 128
                     : r < 7 ? w_trans + (size_t)(fg * 3 + r - 4) * 128
@@ -785,43 +787,47 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
     bias[r] = r < 4 ? b_rot[fg * 4 + r] : r < 7 ? b_trans[fg * 3 + r - 4] : b_conf[fg];
   }
   __syncthreads();
-  const int p = blockIdx.x * 128 + threadIdx.x;
-  if (p >= P) return;
-  const long long n = (long long)b * P + p;
-  const bf16* h = hd3 + n * ld;
-  float acc[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-#pragma unroll
-  for (int seg = 0; seg < 3; ++seg) {                 // rot / trans / conf feature blocks
-    const int r0 = seg == 0 ? 0 : seg == 1 ? 4 : 7, r1 = seg == 0 ? 4 : seg == 1 ? 7 : 8;
-    const uint4* hv = reinterpret_cast<const uint4*>(h + seg * 128);
+  const int r = threadIdx.x & 7;
+  const int p = blockIdx.x * kH4Pts + (threadIdx.x >> 3);
+  const bool ok = p < P;
+  const long long n = (long long)b * P + (ok ? p : 0);
+  const int seg = r < 4 ? 0 : r < 7 ? 1 : 2;               // rot / trans / conf feature block
+  const uint4* hv = reinterpret_cast<const uint4*>(hd3 + n * ld + seg * 128);
+  float acc = 0.f;
 #pragma unroll 4
-    for (int v = 0; v < 16; ++v) {
-      uint4 u = __ldg(hv + v);
-      const bf16* hb = reinterpret_cast<const bf16*>(&u);
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = __bfloat162float(hb[j]);
-#pragma unroll
-      for (int r = r0; r < r1; ++r) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r] = fmaf(w[r][v * 8 + j], x[j], acc[r]);
-      }
-    }
+  for (int v = 0; v < 16; ++v) {
+    const uint4 u = __ldg(hv + v);
+    const bf16* hb = reinterpret_cast<const bf16*>(&u);
+    const float4 w0 = *reinterpret_cast<const float4*>(&w[r][v * 8]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&w[r][v * 8 + 4]);
+    acc = fmaf(w0.x, __bfloat162float(hb[0]), acc);
+    acc = fmaf(w0.y, __bfloat162float(hb[1]), acc);
+    acc = fmaf(w0.z, __bfloat162float(hb[2]), acc);
+    acc = fmaf(w0.w, __bfloat162float(hb[3]), acc);
+    acc = fmaf(w1.x, __bfloat162float(hb[4]), acc);
+    acc = fmaf(w1.y, __bfloat162float(hb[5]), acc);
+    acc = fmaf(w1.z, __bfloat162float(hb[6]), acc);
+    acc = fmaf(w1.w, __bfloat162float(hb[7]), acc);
   }
+  acc += bias[r];
+  // gather the point's 8 outputs to every lane of its 8-lane group
+  const int base = (threadIdx.x & 31) & ~7;
+  float o[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] += bias[r];
-  float nrm = sqrtf(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3]) + 1e-5f;
-  *reinterpret_cast<float4*>(rot + n * 4) =
-      make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
-  const float pt = pitch[b];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int j = 0; j < 8; ++j) o[j] = __shfl_sync(0xffffffffu, acc, base + j);
+  if (!ok) return;
+  if (r == 0) {
+    float nrm = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]) + 1e-5f;  // F.normalize
+    *reinterpret_cast<float4*>(rot + n * 4) =
+        make_float4(o[0] / nrm, o[1] / nrm, o[2] / nrm, o[3] / nrm);
+  } else if (r >= 4 && r < 7) {
+    const int k = r - 4;
+    const float pt = pitch[b];
     float cam = points[((long long)b * 3 + k) * P + p] * pt + origin[b * 3 + k];
-    trans[n * 3 + k] = cam + acc[4 + k] * pt;
+    trans[n * 3 + k] = cam + o[r] * pt;
+  } else if (r == 7) {
+    conf[n] = 1.f / (1.f + expf(-o[7]));
   }
-  conf[n] = 1.f / (1.f + expf(-acc[7]));
 }
 
 }  // namespace mf
@@ -989,8 +995,8 @@ extern "C" int mf_cnn_head4_pose(const void* hd3, int ld, const void* w_rot, con
   if (!hd3 || !w_rot || !b_rot || !w_trans || !b_trans || !w_conf || !b_conf || !points ||
       !class_id || !pitch || !origin || !rot || !trans || !conf)
     return MF_E_BADARG;
-  dim3 grid((unsigned)div_up(P, 128), (unsigned)B);
-  k_head4_pose<<<grid, 128, 0, (cudaStream_t)stream_>>>(
+  dim3 grid((unsigned)div_up(P, kH4Pts), (unsigned)B);
+  k_head4_pose<<<grid, 256, 0, (cudaStream_t)stream_>>>(
       (const bf16*)hd3, ld, (const bf16*)w_rot, b_rot, (const bf16*)w_trans, b_trans,
       (const bf16*)w_conf, b_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
   MF_LAUNCH_CHECK();

@@ -9,9 +9,9 @@ import torch
 def run(dev):
     from oracle import cnn as ocnn
     from oracle import icc as oicc
-    from . import synthetic
-    from .contrib import IterativeCollisionCheckLink
-    from .contrib.singleview_3d.models import Model
+    from morefusion_b200 import synthetic
+    from morefusion_b200.contrib import IterativeCollisionCheckLink
+    from morefusion_b200.contrib.singleview_3d.models import Model
 
     # ---- 3D-CNN section, 1 object
     w = ocnn.init_weights(21, seed=1)

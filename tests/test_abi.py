@@ -77,3 +77,20 @@ def test_argument_validation_matches_reference():
         f.transform_points(torch.zeros(4, 2), torch.eye(4))
     with pytest.raises(TypeError):                                         # keyword-only args
         f.average_voxelization_3d(v, p, b, 1, (0, 0, 0), 1.0, (2, 2, 2))
+
+
+def test_smoke_checker_imports_resolve():
+    """__graft_entry__.smoke() imports tests/smoke_extra.py by path; every import statement inside
+    its run() must resolve without a GPU (catches relative-import mistakes before the GPU box)."""
+    import importlib
+    import inspect
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    mod = importlib.import_module("smoke_extra")
+    for line in inspect.getsource(mod.run).splitlines():
+        stmt = line.strip()
+        if stmt.startswith(("from ", "import ")):
+            exec(stmt, {})
