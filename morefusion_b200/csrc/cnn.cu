@@ -722,6 +722,63 @@ __global__ void k_interp_cl(const bf16* __restrict__ grid, const float* __restri
   *reinterpret_cast<uint4*>(feat + n * ldf + col_off + c) = o;
 }
 
+
+// ---- small row-major grids (conv4 level, 8^3 x 512): shared-memory staged gather -------------
+// k_interp_cl re-reads every corner row from L2 (8 corners x P points x C channels: 65 MB for a
+// 4 MB grid).  Here a CTA owns (object b, 16 consecutive channels): it stages that 16-channel
+// slab of the object's grid (D^3 x 32 B) in shared memory once, then 2 threads per point gather
+// the 8 corners x 8 channels each from shared memory (256 points per pass, so the dependent
+// point-load -> gather chain is walked only P/256 times).  Same arithmetic, same corner order.
+constexpr int kInterpCH = 16;
+constexpr int kInterpThreads = 512;
+constexpr int kInterpTPP = kInterpCH / 8;            // threads per point
+__global__ void __launch_bounds__(kInterpThreads)
+k_interp_cl_staged(const bf16* __restrict__ grid, const float* __restrict__ points,  // [B,3,P]
+                   int B, int P, int C, int D, float divisor, bf16* __restrict__ feat, int ldf,
+                   int col_off) {
+  extern __shared__ __align__(16) unsigned char slab_raw[];
+  uint4* slab = reinterpret_cast<uint4*>(slab_raw);          // [D^3][kInterpTPP] x 16 B
+  const int b = blockIdx.y, c0 = blockIdx.x * kInterpCH;
+  const int V = D * D * D;
+  const bf16* src = grid + (long long)b * V * C + c0;
+  for (int e = threadIdx.x; e < V * kInterpTPP; e += kInterpThreads)
+    slab[e] = __ldg(reinterpret_cast<const uint4*>(src + (long long)(e / kInterpTPP) * C) +
+                    (e % kInterpTPP));
+  __syncthreads();
+  const int t = threadIdx.x % kInterpTPP;
+  for (int pp = threadIdx.x / kInterpTPP; pp < P; pp += kInterpThreads / kInterpTPP) {
+    float x = __fdiv_rn(points[((long long)b * 3 + 0) * P + pp], divisor);
+    float y = __fdiv_rn(points[((long long)b * 3 + 1) * P + pp], divisor);
+    float z = __fdiv_rn(points[((long long)b * 3 + 2) * P + pp], divisor);
+    int x0 = static_cast<int>(x), y0 = static_cast<int>(y), z0 = static_cast<int>(z);
+    float lx = x - (float)x0, ly = y - (float)y0, lz = z - (float)z0;
+    float hx = 1.f - lx, hy = 1.f - ly, hz = 1.f - lz;
+    const float w[8] = {hx * hy * hz, lx * hy * hz, hx * ly * hz, hx * hy * lz,
+                        lx * ly * hz, hx * ly * lz, lx * hy * lz, lx * ly * lz};
+    const int dx[8] = {0, 1, 0, 0, 1, 0, 1, 1};
+    const int dy[8] = {0, 0, 1, 0, 1, 1, 0, 1};
+    const int dz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ix = x0 + dx[j], iy = y0 + dy[j], iz = z0 + dz[j];
+      if (ix < 0 || ix >= D || iy < 0 || iy >= D || iz < 0 || iz >= D) continue;
+      const uint4 v = slab[((ix * D + iy) * D + iz) * kInterpTPP + t];
+      const bf16* h = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[j], __bfloat162float(h[k]), acc[k]);
+    }
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(feat + ((long long)b * P + pp) * ldf + col_off + c0 + t * 8) = o;
+  }
+}
+
 // ------------------------------------------------------------------ pose epilogue (model.py:256-273)
 __global__ void k_pose(const float* __restrict__ out_rot,    // [B*P, nfg*4]
                        const float* __restrict__ out_trans,  // [B*P, nfg*3]
@@ -961,6 +1018,15 @@ extern "C" int mf_cnn_interp_cl(const void* grid, int s2d, const float* points, 
   if (B <= 0 || P <= 0 || C <= 0 || D <= 0 || !grid || !points || !feat) return MF_E_BADARG;
   if ((C & 7) || (ldf & 7) || (col_off & 7)) return MF_E_UNSUPPORTED;
   long long tot = (long long)B * P * (C / 8);
+  const size_t slab_bytes = (size_t)D * D * D * kInterpCH * 2;
+  if (!s2d && C % kInterpCH == 0 && slab_bytes <= 48 * 1024 && B <= 65535) {
+    // small grid: stage a 16-channel slab per CTA, read the grid from L2 once
+    dim3 g((unsigned)(C / kInterpCH), (unsigned)B);
+    k_interp_cl_staged<<<g, kInterpThreads, slab_bytes, (cudaStream_t)stream_>>>(
+        (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+  }
   if (s2d)
     k_interp_cl<true><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
         (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);

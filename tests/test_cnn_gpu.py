@@ -174,3 +174,35 @@ def test_runner_graph_equals_forward_features(cuda_device):
         torch.cuda.synchronize()
         for a, b in zip(got, want):
             assert torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize("D,C,s2d", [(8, 512, 0), (8, 64, 0), (8, 48, 0), (16, 256, 0), (16, 256, 1)])
+def test_interp_cl_equals_public_operator(cuda_device, D, C, s2d):
+    """Internal channels-last bf16 gather (slab-staged for small grids, direct otherwise, s2d or
+    row-major) == the public interpolate_voxel_grid on the same bf16-rounded grid, up to the
+    final bf16 rounding of the output."""
+    import morefusion_b200 as mf
+    from morefusion_b200 import _lib
+    B, P = 3, 1000
+    torch.manual_seed(D + C + s2d)
+    grid = torch.randn(B, C, D, D, D, device=cuda_device).to(torch.bfloat16)
+    div = 32.0 / D
+    pts = torch.rand(B, 3, P, device=cuda_device) * 36.0 - 2.0          # some outside the grid
+    if s2d:
+        J = D // 2 + 1
+        xp = torch.nn.functional.pad(grid, (1, 1, 1, 1, 1, 1))
+        G = xp.reshape(B, C, J, 2, J, 2, J, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(
+            B, J, J, J, 8 * C).contiguous()
+    else:
+        G = grid.permute(0, 2, 3, 4, 1).contiguous()
+    feat = torch.zeros(B * P, C + 16, device=cuda_device, dtype=torch.bfloat16)
+    L = _lib.lib()
+    _lib.check(L.mf_cnn_interp_cl(_lib.ptr(G), s2d, _lib.ptr(pts), B, P, C, D, div, _lib.ptr(feat),
+                                  C + 16, 8, _lib.stream()), "interp_cl")
+    torch.cuda.synchronize()
+    p_flat = (pts / div).permute(0, 2, 1).reshape(B * P, 3).contiguous()
+    bi = torch.arange(B, device=cuda_device, dtype=torch.int32).repeat_interleave(P)
+    want = mf.functions.interpolate_voxel_grid(grid.float(), p_flat, bi)
+    got = feat[:, 8:8 + C].float()
+    assert torch.all(feat[:, :8] == 0) and torch.all(feat[:, 8 + C:] == 0)
+    torch.testing.assert_close(got, want, rtol=2 ** -7, atol=1e-6)
