@@ -126,64 +126,83 @@ struct AvgParams {
   const int* tile_count;   // [B][tiles_per_batch] points per voxel tile (from the prepass)
   const int* tile_list;    // occupied tiles (unordered) and their number
   const int* tile_list_n;
-  const unsigned int* occ_bits;   // one bit per (b, voxel): some point falls into it
   const int* mode;         // 1 = fast (leader scatter), 0 = general (tile kernel)
-  int n_fill_ctas, n_lead_ctas, zero_groups, lead_stride;
+  int n_lead_ctas, zero_groups;
   int tiles_per_batch, n_chunks, n_items;
 };
 
-// Kernel A (fused): CTAs [0, n_fill_ctas) stream zeros, the rest run the per-point leader
-// scatter.  The two roles never touch the same output element: in fast mode the fill skips
-// exactly the voxels whose occupancy bit is set and the leaders write exactly those.
-//   fill role   : no shared memory, no integer division in the loop, 16-byte streaming stores
-//   leader role : one warp per point; the lowest-index point of a voxel sums the voxel's
-//                 points in ascending order (lanes over channels), divides, writes C values+count
+// Prepass + dense zero fill in ONE launch.  CTAs [0, n_key_ctas) run the key / segment /
+// tile-count prepass (k_vox_keys' body; the last of them picks the forward mode), every other CTA
+// streams 16 KiB of zeros into matrix / counts with no look-ups at all, so the bulk of the
+// operator -- writing the dense, mostly-zero output -- runs at plain-fill speed while the
+// latency-bound prepass hides inside the first wave.  The occupied voxels are overwritten
+// afterwards by the leader scatter (fast mode) or the tile kernel (general mode); that is
+// N*(C+1) extra element writes (3 % of the output at the model shape).
+struct KeysArgs {
+  const float* points;
+  const int* bi;
+  VoxGeom g;
+  int* keys;
+  int* hdr;
+  int* seg_start;
+  int* seg_end;
+  int* flags;
+  int* tile_count;
+  int* flags2;
+  int* tile_list;
+  int* tile_list_n;
+  int* done;
+  int* mode;
+  int n_key_ctas;
+};
+
 __global__ void __launch_bounds__(256)
-k_avg_fill_scatter(AvgParams p) {
-  const int fast = __ldg(p.mode);
-  __shared__ int skeys[kLeaderSmemKeys];
-  // roles are interleaved along the grid (one leader CTA every `lead_stride` blocks) so that the
-  // latency-bound leader warps and the bandwidth-bound zero stream share every SM from the
-  // first wave to the last instead of running one after the other
-  const int q = blockIdx.x / p.lead_stride, r = blockIdx.x - q * p.lead_stride;
-  const bool is_lead = (r == 0) && (q < p.n_lead_ctas);
-  const int lead_id = q;
-  if (!is_lead) {
-    // fill role: the output is walked LINEARLY (plane by plane, 16 KiB per CTA) so that L2
-    // write-back sees long contiguous runs, like a plain fill kernel
-    const int leaders_before = min(q + 1, p.n_lead_ctas);       // leader blocks with index < mine
-    const int fid = blockIdx.x - leaders_before;
-    const int plane = fid / p.zero_groups, seg = fid - plane * p.zero_groups;
-    const int b = plane / (p.C + 1), c = plane - b * (p.C + 1);
-    float* base = (c < p.C) ? p.matrix + ((long long)b * p.C + c) * p.V
-                            : reinterpret_cast<float*>(p.counts) + (long long)b * p.V;
-    const unsigned int* bits = p.occ_bits + (((long long)b * p.V) >> 5);
-    const int* tcount = p.tile_count + b * p.tiles_per_batch;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    // all lookups first (independent loads in flight together), then the stores
-    int npts[4];
-    unsigned int mm[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int idx4 = seg * 1024 + k * 256 + threadIdx.x;          // float4 index in the plane
-      npts[k] = __ldg(tcount + (idx4 >> 6));                        // VT == 256: 64 float4 / tile
-      mm[k] = (__ldg(bits + (idx4 >> 3)) >> ((idx4 & 7) * 4)) & 0xFu;
+k_avg_keys_fill(AvgParams p, KeysArgs ka) {
+  if ((int)blockIdx.x < ka.n_key_ctas) {
+    long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < p.N)
+      vox_keys_point(ka.points, ka.bi, p.N, ka.g, ka.keys, ka.hdr, ka.seg_start, ka.seg_end,
+                     ka.flags, ka.tile_count, p.VT, ka.flags2, ka.tile_list, ka.tile_list_n,
+                     nullptr, n);
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ka.done, 1) == ka.n_key_ctas - 1);
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    int maxlen = 0;
+    for (int b = threadIdx.x; b < ka.g.B; b += 32) {
+      int s0 = __ldcg(ka.seg_start + b), s1 = __ldcg(ka.seg_end + b);
+      if (s0 >= 0) maxlen = max(maxlen, s1 - s0);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int idx4 = seg * 1024 + k * 256 + threadIdx.x;
-      if (npts[k] == 0 || (fast && mm[k] == 0)) {
-        __stcs(reinterpret_cast<float4*>(base) + idx4, z4);
-      } else if (fast) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (!((mm[k] >> j) & 1)) base[4 * idx4 + j] = 0.f;
-      }                                                             // general mode: tile kernel owns it
-    }
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    if (threadIdx.x == 0)
+      *ka.mode = ((__ldcg(ka.hdr) & kHdrSortedBit) && maxlen <= kLeaderMaxSeg) ? 1 : 0;
     return;
   }
+  // fill role: the output is walked linearly, plane by plane, 16 KiB per CTA
+  const int fid = blockIdx.x - ka.n_key_ctas;
+  const int plane = fid / p.zero_groups, seg = fid - plane * p.zero_groups;
+  const int b = plane / (p.C + 1), c = plane - b * (p.C + 1);
+  float* base = (c < p.C) ? p.matrix + ((long long)b * p.C + c) * p.V
+                          : reinterpret_cast<float*>(p.counts) + (long long)b * p.V;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* dst = reinterpret_cast<float4*>(base) + seg * 1024 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) __stcs(dst + k * 256, z4);
+}
+
+// Kernel A: per-point leader scatter (fast mode; exits otherwise).  One warp per point; the
+// lowest-index point of a voxel sums the voxel's points in ascending order (lanes over
+// channels), divides and writes C values + the count over the zeros of k_avg_keys_fill.
+__global__ void __launch_bounds__(256)
+k_avg_leaders(AvgParams p) {
+  const int fast = __ldg(p.mode);
+  __shared__ int skeys[kLeaderSmemKeys];
+  const int lead_id = blockIdx.x;
   if (!fast) return;
-  // ---- leader role (these CTAs come FIRST in the grid so that they overlap the zero stream).
   // The CTA's 8 points lie in at most a few batch segments; their keys are staged in shared
   // memory once and every warp scans them from there.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,14 +277,12 @@ k_avg_tiles(AvgParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = blockIdx.y;
-  int tb;
   if (p.mode && __ldg(p.mode)) return;                       // fast mode already wrote everything
-  if (p.tile_list) {
-    if ((int)blockIdx.x >= __ldg(p.tile_list_n)) return;     // fewer occupied tiles than CTAs
-    tb = __ldg(p.tile_list + blockIdx.x);
-  } else {
-    tb = blockIdx.x;                                          // dense mode (ragged shapes)
-  }
+  // grid-stride over the occupied tiles (sparse mode: the count is only known on the device,
+  // so the grid is a fixed few CTAs per SM) or over all tiles (ragged shapes)
+  const int n_work = p.tile_list ? __ldg(p.tile_list_n) : p.n_items;
+  for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+  const int tb = p.tile_list ? __ldg(p.tile_list + item) : item;
   const int ti = tb % p.tiles_per_batch, b = tb / p.tiles_per_batch;
   const int vbase = ti * p.VT;
   const int vt = min(p.VT, p.V - vbase);
@@ -355,6 +372,8 @@ k_avg_tiles(AvgParams p) {
   if (chunk == 0) {
     int* oc = p.counts + (long long)b * p.V + vbase;
     for (int v = tid; v < vt; v += kThreads) oc[v] = cnt[v];
+  }
+  __syncthreads();                                           // shared tile is reused by the next item
   }
 }
 
@@ -492,22 +511,12 @@ extern "C" int mf_average_voxelization_3d_fwd(
   int* mode = regB + 3;
   int* tile_count = regB + 4;
   const long long n_tiles_ws = (long long)p.tiles_per_batch * B;
-  const bool bitmap_ok = (V * B <= (1LL << 26)) && (V % 256 == 0);
-  unsigned int* occ_bits = bitmap_ok ? (unsigned int*)(tile_count + n_tiles_ws) : nullptr;
-  const size_t bits_words = bitmap_ok ? (size_t)(V * B / 32) : 0;
   int* tile_list = (int*)((char*)workspace + kWsListOff);
   int* keys = (int*)((char*)workspace + kWsKeysOff);
   // hdr = all ones (sorted bit set), seg_* = -1 (empty); flags/counter/tile counts = 0
   MF_CUDA_TRY(cudaMemsetAsync(hdr, 0xFF, (4 + 2 * (size_t)B) * sizeof(int), stream));
-  MF_CUDA_TRY(cudaMemsetAsync(regB, 0, (4 + (size_t)n_tiles_ws + bits_words) * sizeof(int), stream));
+  MF_CUDA_TRY(cudaMemsetAsync(regB, 0, (4 + (size_t)n_tiles_ws) * sizeof(int), stream));
   VoxGeom g{ox, oy, oz, pitch, X, Y, Z, B};
-  if (N > 0) {
-    k_vox_keys<<<div_up(N, 256), 256, 0, stream>>>(points, batch_indices, N, g, keys, hdr,
-                                                   seg_start, seg_end, flags, tile_count, p.VT,
-                                                   flags2, tile_list, tile_list_n, occ_bits, done,
-                                                   mode);
-    MF_LAUNCH_CHECK();
-  }
   p.values = values; p.keys = keys; p.hdr = hdr; p.seg_start = seg_start; p.seg_end = seg_end;
   p.N = N; p.C = C; p.B = B; p.V = (int)V;
   int nChunks = (C + 63) / 64;
@@ -530,27 +539,42 @@ extern "C" int mf_average_voxelization_3d_fwd(
                                      100 * 1024));
     attr_set = true;
   }
-  p.occ_bits = occ_bits; p.mode = mode;
-  const bool sparse_ok = bitmap_ok && (p.VT == 256) && (V % 4096 == 0) && C <= 256 && N > 0;
+  p.mode = mode;
+  p.zero_groups = 0;
+  p.n_lead_ctas = 0;
+  const bool sparse_ok = (V * B <= (1LL << 26)) && (p.VT == 256) && (V % 4096 == 0) && C <= 256 &&
+                         N > 0;
   if (sparse_ok) {
-    // A: fused zero stream + (fast mode) per-point leader scatter; B: occupied tiles (general mode)
-    p.zero_groups = (int)((V / 4 + 1023) / 1024);            // 16 KiB segments per plane
+    // 1. prepass + dense zero fill in one launch; 2. per-point leader scatter (fast mode);
+    // 3. occupied tiles through shared memory (general mode).  2 and 3 are mutually exclusive
+    // (device-side mode word) and overwrite only occupied voxels / tiles.
+    p.zero_groups = (int)(V / 4096);                           // 16 KiB segments per plane
     const long long n_fill = (long long)B * (C + 1) * p.zero_groups;
+    const long long n_key = div_up(N, 256);
     const long long n_lead = (N * 32 + 255) / 256;
-    if (n_fill + n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
-    p.n_fill_ctas = (int)n_fill;
+    if (n_fill + n_key >= (1LL << 31) || n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
     p.n_lead_ctas = (int)n_lead;
-    p.lead_stride = (int)((n_fill + n_lead) / n_lead);
-    if (p.lead_stride < 1) p.lead_stride = 1;
-    k_avg_fill_scatter<<<(unsigned)(n_fill + n_lead), 256, 0, stream>>>(p);
+    KeysArgs ka{points, batch_indices, g, keys, hdr, seg_start, seg_end, flags, tile_count,
+                flags2, tile_list, tile_list_n, done, mode, (int)n_key};
+    k_avg_keys_fill<<<(unsigned)(n_key + n_fill), 256, 0, stream>>>(p, ka);
+    MF_LAUNCH_CHECK();
+    k_avg_leaders<<<(unsigned)n_lead, 256, 0, stream>>>(p);
     MF_LAUNCH_CHECK();
     long long occ_max = n_tiles < N ? n_tiles : N;             // at most one new tile per point
+    if (occ_max > 592) occ_max = 592;                          // 4 x 148: grid-stride inside
     if (occ_max > 0) {
       dim3 grid((unsigned)occ_max, nChunks, 1);
       k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
       MF_LAUNCH_CHECK();
     }
   } else {
+    if (N > 0) {
+      k_vox_keys<<<div_up(N, 256), 256, 0, stream>>>(points, batch_indices, N, g, keys, hdr,
+                                                     seg_start, seg_end, flags, tile_count, p.VT,
+                                                     flags2, tile_list, tile_list_n, nullptr, done,
+                                                     mode);
+      MF_LAUNCH_CHECK();
+    }
     // ragged shapes: every tile through the shared-memory path
     p.tile_list = nullptr;
     p.mode = nullptr;
