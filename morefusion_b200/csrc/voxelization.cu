@@ -4,13 +4,14 @@
 //   morefusion/functions/geometry/average_voxelization_3d.py:57-115, :163-218
 //   morefusion/functions/geometry/max_voxelization_3d.py:75-138, :153-183
 //
-// average_voxelization_3d forward is a single-pass *output-tile* design:
-// a CTA owns (batch b, channel chunk, VT consecutive voxels), gathers the points
-// that fall into its voxel range into a shared-memory tile (ordered stream
-// compaction -> per-voxel sums in ascending point order, no atomics, bit-exact
-// against the oracle), divides by the counts and writes every output element
-// exactly once with coalesced stores.  HBM traffic = output bytes + a 4-byte key
-// per point per tile scan; no memset pass, no read-modify-write on HBM.
+// average_voxelization_3d forward:
+//   k_avg_keys_fill  prepass (keys, tile counts, batch segments, mode) fused into a dense,
+//                    look-up-free zero fill of matrix/counts (runs at the HBM write roofline)
+//   k_avg_leaders    fast mode (sorted batch indices): one warp per point; the lowest-index point
+//                    of a voxel sums the voxel's points in ascending order and overwrites it
+//   k_avg_tiles      general mode / ragged shapes: a CTA owns (batch, channel chunk, 256 voxels),
+//                    ordered stream compaction into a shared-memory tile, coalesced tile write
+// No atomics on the output, per-voxel sums in ascending point order -> bit-exact vs the oracle.
 #include "common.cuh"
 
 namespace mf {
