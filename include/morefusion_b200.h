@@ -233,11 +233,20 @@ int mf_cnn_occ_convs(const float* grid_nontarget_empty /*[B,D,D,D]*/, const floa
 int mf_cnn_occ_convs_tc(const float* grid_nontarget_empty, const float* w1, const float* b1,
                         const float* w2, const float* b2, int B, int D, void* h1_bf16 /*[B,V,8]*/,
                         void* X, int Ct, int c_off, void* stream);
+/* same, reading the occupancy grid as bytes (0/1; uint8 or bool storage): saves the cast the
+ * reference does inside the model (model.py:115-116) */
+int mf_cnn_occ_convs_tc_u8(const uint8_t* grid_nontarget_empty, const float* w1, const float* b1,
+                           const float* w2, const float* b2, int B, int D,
+                           void* h1_bf16 /*[B,V,8]*/, void* X, int Ct, int c_off, void* stream);
 /* average_voxelization_3d of model.py:143-164 (origin 0, pitch 1, D^3) fused with the s2d/bf16
  * packing: writes channels [0,C) of X.  prev_keys [B*P] int32 (in/out, initialise to -1) holds
  * the voxel keys of the previous call so that only those voxels are re-zeroed. */
 int mf_cnn_voxelize_s2d(const float* feat2 /*[B*P,C]*/, const float* points /*[B,3,P]*/, int B,
                         int P, int C, int D, int Ct, int32_t* prev_keys, void* X, void* stream);
+/* the same in two halves so that a caller can overlap the first with the point MLP that produces
+ * feat2: phases bit 0 = sparse clear + new keys (feat2 may be NULL), bit 1 = ordered scatter */
+int mf_cnn_voxelize_s2d_phase(const float* feat2, const float* points, int B, int P, int C, int D,
+                              int Ct, int32_t* prev_keys, void* X, int phases, void* stream);
 int mf_cnn_pack_s2d(const float* vox /*[B,C,D,D,D]*/, const float* hocc /*[B,V,Cocc] or NULL*/,
                     int B, int C, int Cocc, int D, void* X /*bf16 s2d, borders pre-zeroed*/,
                     void* stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mf_cnn_occ_convs": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
     "mf_cnn_occ_convs_tc": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mf_cnn_voxelize_s2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "mf_cnn_voxelize_s2d_phase": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p]),
+    "mf_cnn_occ_convs_tc_u8": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mf_cnn_pack_s2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "mf_gemm_bf16_simt": (c_i, [c_p, c_p]),
     "mf_gemm_bf16_tc_workspace_bytes": (c_sz, [c_i, c_i]),

@@ -262,15 +262,26 @@ class Model(torch.nn.Module):
             self._pack()
         return L, dev, B, P, self._packed, self._work_buffers(B, P, dev)
 
-    def _side(self, dev):
-        key = (dev.type, dev.index)
+    def _side(self, dev, which=0):
+        key = (dev.type, dev.index, which)
         if key not in self._side_streams:
             self._side_streams[key] = torch.cuda.Stream(dev)
         return self._side_streams[key]
 
     def _occ_branch(self, L, st, w, buf, B, D, Ct):
         s = _lib.stream
-        g = st["gne"].to(torch.float32).contiguous()
+        gne = st["gne"]
+        if self.use_tensor_cores and D == 32 and gne.dtype in (torch.uint8, torch.bool):
+            # byte grids go straight into the stencil (no cast pass)
+            g = gne.contiguous()
+            g = g.view(torch.uint8) if g.dtype == torch.bool else g
+            _lib.check(L.mf_cnn_occ_convs_tc_u8(
+                _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                _lib.ptr(buf["occ1_bf16"]), _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_convs_tc_u8")
+            self.n_launches += 2
+            return g
+        g = gne.to(torch.float32).contiguous()
         if self.use_tensor_cores and D == 32:
             _lib.check(L.mf_cnn_occ_convs_tc(
                 _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
@@ -302,6 +313,18 @@ class Model(torch.nn.Module):
                 with torch.cuda.stream(side):
                     self._occ_branch(L, st, w, buf, B, D, 144 + 16)
                 forked = (main, side)
+            forked2 = None
+            if fused and self.concurrent_branches:
+                # sparse clear of the previous call's voxels + this call's keys do not need the
+                # point MLP's output: third branch
+                side2 = self._side(dev, 1)
+                side2.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side2):
+                    _lib.check(L.mf_cnn_voxelize_s2d_phase(
+                        None, _lib.ptr(st["points"]), B, P, 144, D,
+                        144 + (16 if self._with_occupancy else 0), _lib.ptr(buf["prev_keys"]),
+                        _lib.ptr(buf["x3"]), 1, s()), "voxelize_s2d(clear+keys)")
+                forked2 = side2
             _lib.check(L.mf_cnn_point_mlp(
                 _lib.ptr(st["values"]), _lib.ptr(st["points"]),
                 _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
@@ -318,9 +341,16 @@ class Model(torch.nn.Module):
             if fused:
                 # _voxelize (model.py:143-164) fused with the bf16 s2d packing; the occupancy
                 # stencil writes its 16 channels into the same buffer
-                _lib.check(L.mf_cnn_voxelize_s2d(
-                    _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
-                    _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "voxelize_s2d")
+                if forked2 is not None:
+                    torch.cuda.current_stream(dev).wait_stream(forked2)
+                    _lib.check(L.mf_cnn_voxelize_s2d_phase(
+                        _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
+                        _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), 2, s()),
+                        "voxelize_s2d(scatter)")
+                else:
+                    _lib.check(L.mf_cnn_voxelize_s2d(
+                        _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
+                        _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "voxelize_s2d")
                 self.n_launches += 3
                 if forked:
                     forked[0].wait_stream(forked[1])

@@ -406,7 +406,8 @@ k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __res
 }
 
 // conv1_occ variant writing bf16 channels-last (input of k_occ_conv2_mma)
-__global__ void k_occ_conv1_bf16(const float* __restrict__ gne, const float* __restrict__ w,
+template <typename TIn>
+__global__ void k_occ_conv1_bf16(const TIn* __restrict__ gne, const float* __restrict__ w,
                                  const float* __restrict__ bias, int B, int D,
                                  bf16* __restrict__ h1) {
   __shared__ float sw[8 * 27 + 8];
@@ -431,7 +432,7 @@ __global__ void k_occ_conv1_bf16(const float* __restrict__ gne, const float* __r
       for (int kw = 0; kw < 3; ++kw) {
         int zz = z + kw - 1;
         if (zz < 0 || zz >= D) continue;
-        float in = gne[b * V + ((long long)xx * D + yy) * D + zz];
+        float in = (float)gne[b * V + ((long long)xx * D + yy) * D + zz];
         int tap = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = fmaf(sw[c * 27 + tap], in, acc[c]);
@@ -929,15 +930,15 @@ extern "C" int mf_cnn_occ_convs(const float* gne, const float* w1, const float* 
   return MF_OK;
 }
 
-extern "C" int mf_cnn_occ_convs_tc(const float* gne, const float* w1, const float* b1,
-                                   const float* w2, const float* b2, int B, int D,
-                                   void* h1_bf16, void* X, int Ct, int c_off, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+template <typename TIn>
+static int occ_convs_tc(const TIn* gne, const float* w1, const float* b1, const float* w2,
+                        const float* b2, int B, int D, void* h1_bf16, void* X, int Ct, int c_off,
+                        cudaStream_t stream) {
   if (B <= 0 || !gne || !w1 || !b1 || !w2 || !b2 || !h1_bf16 || !X) return MF_E_BADARG;
   if (D != 32) return MF_E_UNSUPPORTED;
   if ((Ct & 7) || (c_off & 7) || c_off + 16 > Ct) return MF_E_BADARG;
   long long BV = (long long)B * D * D * D;
-  k_occ_conv1_bf16<<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, (bf16*)h1_bf16);
+  k_occ_conv1_bf16<TIn><<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, (bf16*)h1_bf16);
   MF_LAUNCH_CHECK();
   static bool attr = false;
   if (!attr) {
@@ -951,22 +952,51 @@ extern "C" int mf_cnn_occ_convs_tc(const float* gne, const float* w1, const floa
   return MF_OK;
 }
 
-extern "C" int mf_cnn_voxelize_s2d(const float* feat2, const float* points, int B, int P, int C,
-                                   int D, int Ct, int32_t* prev_keys, void* X, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+extern "C" int mf_cnn_occ_convs_tc(const float* gne, const float* w1, const float* b1,
+                                   const float* w2, const float* b2, int B, int D,
+                                   void* h1_bf16, void* X, int Ct, int c_off, void* stream_) {
+  return occ_convs_tc<float>(gne, w1, b1, w2, b2, B, D, h1_bf16, X, Ct, c_off,
+                             (cudaStream_t)stream_);
+}
+
+extern "C" int mf_cnn_occ_convs_tc_u8(const uint8_t* gne, const float* w1, const float* b1,
+                                      const float* w2, const float* b2, int B, int D,
+                                      void* h1_bf16, void* X, int Ct, int c_off, void* stream_) {
+  return occ_convs_tc<uint8_t>(gne, w1, b1, w2, b2, B, D, h1_bf16, X, Ct, c_off,
+                               (cudaStream_t)stream_);
+}
+
+static int voxelize_s2d(const float* feat2, const float* points, int B, int P, int C, int D,
+                        int Ct, int32_t* prev_keys, void* X, int phases, cudaStream_t stream) {
   if (B <= 0 || P <= 0 || C <= 0 || C > 256 || (C & 1) || D <= 0 || (D & 1) || Ct < C)
     return MF_E_BADARG;
-  if (!feat2 || !points || !prev_keys || !X) return MF_E_BADARG;
+  if (!points || !prev_keys || !X || ((phases & 2) && !feat2)) return MF_E_BADARG;
   if ((long long)B * D * D * D >= (1LL << 31)) return MF_E_TOOLARGE;
   const int N = B * P;
-  k_s2d_clear<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(prev_keys, N, C, D, Ct, (bf16*)X);
-  MF_LAUNCH_CHECK();
-  k_s2d_keys<<<div_up(N, 256), 256, 0, stream>>>(points, B, P, D, prev_keys);
-  MF_LAUNCH_CHECK();
-  k_s2d_scatter<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(feat2, prev_keys, B, P, C, D, Ct,
-                                                                   (bf16*)X);
-  MF_LAUNCH_CHECK();
+  if (phases & 1) {
+    k_s2d_clear<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(prev_keys, N, C, D, Ct, (bf16*)X);
+    MF_LAUNCH_CHECK();
+    k_s2d_keys<<<div_up(N, 256), 256, 0, stream>>>(points, B, P, D, prev_keys);
+    MF_LAUNCH_CHECK();
+  }
+  if (phases & 2) {
+    k_s2d_scatter<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(feat2, prev_keys, B, P, C, D, Ct,
+                                                                     (bf16*)X);
+    MF_LAUNCH_CHECK();
+  }
   return MF_OK;
+}
+
+extern "C" int mf_cnn_voxelize_s2d(const float* feat2, const float* points, int B, int P, int C,
+                                   int D, int Ct, int32_t* prev_keys, void* X, void* stream_) {
+  return voxelize_s2d(feat2, points, B, P, C, D, Ct, prev_keys, X, 3, (cudaStream_t)stream_);
+}
+
+extern "C" int mf_cnn_voxelize_s2d_phase(const float* feat2, const float* points, int B, int P,
+                                         int C, int D, int Ct, int32_t* prev_keys, void* X,
+                                         int phases, void* stream_) {
+  if (phases < 1 || phases > 3) return MF_E_BADARG;
+  return voxelize_s2d(feat2, points, B, P, C, D, Ct, prev_keys, X, phases, (cudaStream_t)stream_);
 }
 
 extern "C" int mf_cnn_pack_s2d(const float* vox, const float* hocc, int B, int C, int Cocc, int D,
