@@ -24,4 +24,7 @@ Pinning status (see DESIGN.md "Oracle"):
     chainer.optimizers.Adam update rule, cuDNN ConvolutionND numerics,
     trimesh quaternion_from_matrix.  Restated from their published
     definitions; see ``oracle/icc.py`` and ``oracle/cnn.py`` headers.
+    ``oracle/cnn_train.py`` (differentiable restatement of the same forward + the training
+    loss, model.py:377-441) is pinned to ``oracle/cnn.py`` bit for bit on the forward pass and
+    to finite differences on its gradients; the reference pins neither.
 """

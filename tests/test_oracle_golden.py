@@ -310,3 +310,94 @@ def test_average_distance_loss():
     for i in range(g["T2"].shape[0]):
         want = om.average_distance(g["points"].astype(np.float64), g["T1"], g["T2"][i])[0]
         np.testing.assert_allclose(add[i], want, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- training-step oracle
+def _train_case(B=2, P=300, seed=0):
+    from oracle import cnn as ocnn
+    rs = np.random.RandomState(seed)
+    w = ocnn.init_weights(21, seed=3)
+    values = rs.normal(0, 1, (B, 32, P)).astype(np.float32)
+    c = rs.uniform(12, 20, (B, 3, 1))
+    d = rs.normal(size=(B, 3, P))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    points = (c + d * rs.uniform(6, 11, (B, 1, P))).astype(np.float32)
+    points[:, :, :4] = rs.uniform(-3, 35, (B, 3, 4))              # a few outside the grid
+    batch = dict(class_id=(np.arange(B) % 21 + 3).astype(np.int32), values=values, points=points,
+                 pitch=np.array([0.0065 + 0.0005 * i for i in range(B)], np.float32),
+                 origin=rs.uniform(-0.2, 0.6, (B, 3)).astype(np.float32),
+                 grid_nontarget_empty=(rs.uniform(size=(B, 32, 32, 32)) < 0.4))
+    qt = rs.normal(size=(B, 4)).astype(np.float32)
+    qt /= np.linalg.norm(qt, axis=1, keepdims=True)
+    kw = dict(quaternion_true=qt, translation_true=rs.uniform(-0.1, 0.7, (B, 3)).astype(np.float32),
+              cad_points=[rs.uniform(-0.05, 0.05, (60, 3)).astype(np.float32) for _ in range(B)],
+              symmetric=[bool(i % 2) for i in range(B)])
+    return w, batch, kw
+
+
+def test_training_oracle_forward_is_the_inference_oracle():
+    """oracle/cnn_train.py (differentiable torch restatement) == oracle/cnn.py bit for bit on the
+    forward pass, so gradients taken through it are gradients of the pinned forward arithmetic."""
+    import torch
+    from oracle import cnn as ocnn, cnn_train as ct
+    w, batch, _ = _train_case(B=2, P=1000, seed=1)
+    ref = ocnn.forward(w, n_fg_class=21, bf16=False, **batch)
+    with torch.no_grad():
+        out = ct.forward(ct.params_from_weights(w, requires_grad=False), n_fg_class=21, **batch)
+    for k in ("voxelized", "feat", "rot", "trans", "conf"):
+        assert np.array_equal(out[k].numpy(), ref[k]), k
+
+
+def test_training_oracle_loss_matches_operator_oracles():
+    """pose_loss == the reference formula evaluated with the already-pinned NumPy oracles
+    (transforms.transformation_matrix, loss.average_distance: model.py:405-441)."""
+    import torch
+    from oracle import cnn_train as ct, loss as oloss, transforms as otf
+    w, batch, kw = _train_case()
+    with torch.no_grad():
+        out = ct.forward(ct.params_from_weights(w, requires_grad=False), n_fg_class=21, **batch)
+        got = float(ct.pose_loss(out, **kw))
+    want = 0.0
+    B = out["rot"].shape[0]
+    for i in range(B):
+        q, t, conf = out["rot"][i].numpy(), out["trans"][i].numpy(), out["conf"][i].numpy()
+        Tp = otf.transformation_matrix(q, t)
+        Tt = otf.transformation_matrix(kw["quaternion_true"][i], kw["translation_true"][i])
+        add = oloss.average_distance(kw["cad_points"][i], Tt, Tp, symmetric=kw["symmetric"][i])
+        keep = conf > 0
+        want += np.mean(add[keep].astype(np.float64) * conf[keep]
+                        - ct.LAMBDA_CONFIDENCE * np.log(conf[keep].astype(np.float64)))
+    want /= B
+    assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (got, want)
+
+
+def test_training_oracle_gradients_match_finite_differences():
+    """float32 autograd gradients == float64 autograd gradients (<=1e-3 of the largest entry) and
+    float64 directional derivatives == central finite differences (<=2e-3 relative + 2e-7)."""
+    import torch
+    from oracle import cnn_train as ct
+    w, batch, kw = _train_case()
+    l32, g32, _ = ct.loss_and_grads(w, batch, **kw)
+    l64, g64, _ = ct.loss_and_grads(w, batch, dtype=torch.float64, **kw)
+    assert abs(l32 - l64) <= 1e-5 * max(1.0, abs(l64))
+    for k in w:
+        scale = np.abs(g64[k]).max()
+        assert scale > 0, k                                     # every parameter gets a gradient
+        assert np.abs(g32[k] - g64[k]).max() <= 1e-3 * scale, k
+
+    def loss64(wd):
+        p = {k: torch.tensor(np.asarray(v, dtype=np.float64)) for k, v in wd.items()}
+        with torch.no_grad():
+            return float(ct.pose_loss(ct.forward(p, n_fg_class=21, **batch), **kw))
+
+    rs = np.random.RandomState(5)
+    for k in ("conv3/W", "conv2_pcd/W", "conv1_occ/W", "conv3_trans/W", "conv4_conf/b"):
+        d = rs.normal(size=w[k].shape)
+        d /= np.linalg.norm(d)
+        eps = 1e-4
+        wp, wm = dict(w), dict(w)
+        wp[k] = w[k].astype(np.float64) + eps * d
+        wm[k] = w[k].astype(np.float64) - eps * d
+        fd = (loss64(wp) - loss64(wm)) / (2 * eps)
+        an = float((g64[k].astype(np.float64) * d).sum())
+        assert abs(fd - an) <= 2e-3 * abs(an) + 2e-7, (k, fd, an)     # 2e-7: fp64 FD noise floor
