@@ -94,3 +94,28 @@ def test_smoke_checker_imports_resolve():
         stmt = line.strip()
         if stmt.startswith(("from ", "import ")):
             exec(stmt, {})
+
+
+def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
+    """include/morefusion_b200.h compiles as C (no C++/torch types in the boundary) and the
+    GemmParams layout the Python side builds with ctypes is the one a C caller sees."""
+    import ctypes
+    import os
+    import subprocess
+    from morefusion_b200.contrib.singleview_3d.models.model import GemmParams
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [f[0] for f in GemmParams._fields_]
+    src = tmp_path / "layout.c"
+    prints = "\n".join(f'  printf("{f} %zu\\n", offsetof(GemmParams, {f}));' for f in fields)
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "morefusion_b200.h"\n'
+        "int main(void) {\n" + prints + '\n  printf("sizeof %zu\\n", sizeof(GemmParams));\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = dict(zip(out[0::2], map(int, out[1::2])))
+    for f in fields:
+        assert got[f] == getattr(GemmParams, f).offset, f
+    assert got["sizeof"] == ctypes.sizeof(GemmParams)
