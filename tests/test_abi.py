@@ -77,6 +77,12 @@ def test_argument_validation_matches_reference():
         f.transform_points(torch.zeros(4, 2), torch.eye(4))
     with pytest.raises(TypeError):                                         # keyword-only args
         f.average_voxelization_3d(v, p, b, 1, (0, 0, 0), 1.0, (2, 2, 2))
+    # transformation_matrix.py:6-17: shape contracts are asserts, for both call forms
+    for q, t in ((torch.zeros(3, 4), torch.zeros(2, 3)), (torch.zeros(3, 5), torch.zeros(3, 3)),
+                 (torch.zeros(4), torch.zeros(1, 3)), (torch.zeros(4), torch.zeros(4)),
+                 (torch.zeros(2, 3, 4), torch.zeros(2, 3))):
+        with pytest.raises(AssertionError):
+            f.transformation_matrix(q, t)
 
 
 def test_smoke_checker_imports_resolve():
