@@ -310,8 +310,8 @@ int mf_icc_run(int n_scenes, int n_objects_total, int voxel_dim, float voxel_thr
                const float* points, const float* sdf, const float* pitch, const float* origin,
                const float* grid_target, const float* grid_nontarget_empty, float* quaternion,
                float* translation, float* adam_state, int n_iter, int update,
-               const float* alpha_q_host, const float* alpha_t_host, float beta1, float beta2,
-               float eps, float eta, float* loss_history, float* grads, int group_size,
+               const float* alpha_q_host, const float* alpha_t_host, double beta1, double beta2,
+               double eps, double eta, float* loss_history, float* grads, int group_size,
                void* workspace, size_t workspace_bytes, void* stream);
 /* same, plus phase_ns: device uint64 [n_scenes][n_iter][8] receiving %globaltimer stamps at the
  * phase boundaries of every iteration (profiling aid; NULL = off) */
@@ -323,8 +323,8 @@ int mf_icc_run_profiled(int n_scenes, int n_objects_total, int voxel_dim, float 
                const float* points, const float* sdf, const float* pitch, const float* origin,
                const float* grid_target, const float* grid_nontarget_empty, float* quaternion,
                float* translation, float* adam_state, int n_iter, int update,
-               const float* alpha_q_host, const float* alpha_t_host, float beta1, float beta2,
-               float eps, float eta, float* loss_history, float* grads, int group_size,
+               const float* alpha_q_host, const float* alpha_t_host, double beta1, double beta2,
+               double eps, double eta, float* loss_history, float* grads, int group_size,
                void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream);
 
 /* ------------------------------------------------------------------------

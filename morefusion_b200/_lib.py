@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmorefusion_sm100a.so")
 
 c_f, c_i, c_i64, c_p, c_sz = (ctypes.c_float, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                               ctypes.c_size_t)
+c_d = ctypes.c_double
 
 # name -> (restype, argtypes); must list every symbol the header declares
 # (tests/test_abi.py cross-checks this table against include/morefusion_b200.h)
@@ -63,11 +64,11 @@ SIGNATURES = {
     "mf_icc_max_group_size": (c_i, [c_i]),
     "mf_icc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
     "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
-                   + [c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_p, c_sz, c_p]),
+                   + [c_i, c_i, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_i, c_p, c_sz, c_p]),
     "mf_average_distance_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "mf_average_distance_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     "mf_icc_run_profiled": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
-                            + [c_i, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p, c_p, c_i, c_p, c_sz, c_p, c_p]),
+                            + [c_i, c_i, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_i, c_p, c_sz, c_p, c_p]),
 }
 
 _lib = None

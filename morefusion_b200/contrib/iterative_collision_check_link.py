@@ -164,16 +164,23 @@ class IterativeCollisionCheckLink(torch.nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("IterativeCollisionCheckLink runs on CUDA only (no CPU fallback); "
                                "call .cuda() first")
-        key = tuple(id(x) for x in list(points) + list(sdf)) + (
-            id(pitch), id(origin), id(grid_target), id(grid_nontarget_empty))
-        if self._prob_cache[0] != key:
+        # The concatenated device copy of the inputs is reused only while every input is the same
+        # tensor at the same version: refilling a tensor in place (the ROS node pattern) bumps
+        # its version and rebuilds the copy.  numpy / python inputs cannot be versioned and are
+        # rebuilt on every call.
+        def ident(x):
+            if isinstance(x, torch.Tensor):
+                return (x.data_ptr(), x._version, tuple(x.shape), x.dtype, x.device)
+            return None
+        parts = list(points) + list(sdf) + [pitch, origin, grid_target, grid_nontarget_empty]
+        key = tuple(ident(x) for x in parts) + (len(points),)
+        if None in key or self._prob_cache[0] != key:
             prob = _Problem([dict(points=list(points), sdf=list(sdf), pitch=pitch, origin=origin,
                                   grid_target=grid_target,
                                   grid_nontarget_empty=grid_nontarget_empty)],
                             self._voxel_dim, dev)
-            # keep the inputs alive so that the id()-based key stays valid
-            self._prob_cache = (key, prob, (points, sdf, pitch, origin, grid_target,
-                                            grid_nontarget_empty))
+            # keep the inputs alive so that a recycled address cannot alias a stale key
+            self._prob_cache = (key, prob, parts)
         return self._prob_cache[1]
 
     def forward(self, points, sdf, pitch, origin, grid_target, grid_nontarget_empty):

@@ -95,6 +95,7 @@ class Model(torch.nn.Module):
             setattr(self, f"conv3_{head}", nn.Conv1d(256, 128, 1))
             setattr(self, f"conv4_{head}", nn.Conv1d(128, cout, 1))
         self._packed = None
+        self._packed_ver = None
         self._wbufs = {}
         self.use_tensor_cores = True
         self.fused_voxelize = True
@@ -115,7 +116,7 @@ class Model(torch.nn.Module):
                 if name + "/W" in weights:
                     mod.weight.copy_(torch.as_tensor(weights[name + "/W"]).reshape(mod.weight.shape))
                     mod.bias.copy_(torch.as_tensor(weights[name + "/b"]))
-        self._packed = None
+        self._packed_ver = None
         return self
 
     def _pack(self):
@@ -152,6 +153,13 @@ class Model(torch.nn.Module):
                     pass
                 p[f"conv{layer}_{h}/W"] = W.contiguous()
                 p[f"conv{layer}_{h}/b"] = f32(m.bias)
+        old = self._packed
+        if (old is not None and self._packed_dev == dev and old.keys() == p.keys()
+                and all(old[k].shape == p[k].shape and old[k].dtype == p[k].dtype for k in p)):
+            # refresh in place: captured CUDA graphs keep reading the same addresses
+            for k in p:
+                old[k].copy_(p[k])
+            return old
         self._packed = p
         self._packed_dev = dev
         return p
@@ -258,8 +266,14 @@ class Model(torch.nn.Module):
         L = _lib.lib()
         dev = st["values"].device
         B, _, P = st["values"].shape
-        if self._packed is None or self._packed_dev != self.conv3.weight.device:
+        # kernels read packed (bf16 / transposed) copies of the parameters: rebuild them whenever
+        # any parameter changed (load_state_dict, optimizer step, in-place edit all bump the
+        # tensor version) or moved
+        ver = tuple(p._version for p in self.parameters())
+        if (self._packed is None or self._packed_dev != self.conv3.weight.device
+                or self._packed_ver != ver):
             self._pack()
+            self._packed_ver = ver
         return L, dev, B, P, self._packed, self._work_buffers(B, P, dev)
 
     def _side(self, dev, which=0):

@@ -482,10 +482,15 @@ __global__ void k_s2d_keys(const float* __restrict__ points /*[B,3,P]*/, int B, 
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B * P) return;
   int b = n / P, p = n % P;
-  int ix = static_cast<int>(roundf(points[(b * 3 + 0) * P + p]));   // (p - 0) / 1.0
-  int iy = static_cast<int>(roundf(points[(b * 3 + 1) * P + p]));
-  int iz = static_cast<int>(roundf(points[(b * 3 + 2) * P + p]));
-  bool ok = ix >= 0 && ix < D && iy >= 0 && iy < D && iz >= 0 && iz < D;
+  const float fx = points[(b * 3 + 0) * P + p], fy = points[(b * 3 + 1) * P + p],
+              fz = points[(b * 3 + 2) * P + p];
+  int ix = static_cast<int>(roundf(fx));   // (p - 0) / 1.0
+  int iy = static_cast<int>(roundf(fy));
+  int iz = static_cast<int>(roundf(fz));
+  // NaN points are dropped (the public operator raises "points include nan";
+  // Model.predict masks them out before this point, model.py:178)
+  bool ok = !(isnan(fx) || isnan(fy) || isnan(fz)) && ix >= 0 && ix < D && iy >= 0 && iy < D &&
+            iz >= 0 && iz < D;
   keys[n] = ok ? b * D * D * D + (ix * D + iy) * D + iz : -1;
 }
 
@@ -902,12 +907,7 @@ extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const 
       !feat || !feat2)
     return MF_E_BADARG;
   long long NP = (long long)B * P;
-  static bool attr = false;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_point_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kMlpSmemFloats * 4));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM(k_point_mlp, kMlpSmemFloats * 4);
   k_point_mlp<<<div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(
       values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat, ldf,
       feat2);
@@ -940,12 +940,7 @@ static int occ_convs_tc(const TIn* gne, const float* w1, const float* b1, const 
   long long BV = (long long)B * D * D * D;
   k_occ_conv1_bf16<TIn><<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, (bf16*)h1_bf16);
   MF_LAUNCH_CHECK();
-  static bool attr = false;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_occ_conv2_mma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kOccTileBytes));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM(k_occ_conv2_mma, kOccTileBytes);
   k_occ_conv2_mma<<<(unsigned)(B * D), 256, kOccTileBytes, stream>>>(
       (const bf16*)h1_bf16, w2, b2, B, (bf16*)X, Ct, c_off);
   MF_LAUNCH_CHECK();
@@ -1004,12 +999,7 @@ extern "C" int mf_cnn_pack_s2d(const float* vox, const float* hocc, int B, int C
   if (B <= 0 || C <= 0 || Cocc < 0 || D <= 0 || (D & 1) || !vox || !X) return MF_E_BADARG;
   if (Cocc > 0 && !hocc) return MF_E_BADARG;
   size_t smem = (size_t)(C + Cocc) * (D + 1) * 4;
-  static bool attr = false;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_pack_s2d, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     96 * 1024));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM(k_pack_s2d, 96 * 1024);
   if (smem > 96 * 1024) return MF_E_UNSUPPORTED;
   k_pack_s2d<<<(unsigned)(B * D * D), 256, smem, (cudaStream_t)stream_>>>(vox, hocc, B, C, Cocc,
                                                                         D, (bf16*)X);

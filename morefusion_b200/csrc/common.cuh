@@ -17,6 +17,21 @@
     if (_e != cudaSuccess) return (int)_e;     \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember
+// what has been set per device, not per process, so a process that drives several GPUs works.
+// Races between host threads are benign (the attribute call is idempotent).
+#define MF_ENSURE_DYN_SMEM(func, bytes)                                                        \
+  do {                                                                                         \
+    static int _mf_smem_set[64];                                                               \
+    int _mf_dev = 0;                                                                           \
+    MF_CUDA_TRY(cudaGetDevice(&_mf_dev));                                                      \
+    if (_mf_dev < 0 || _mf_dev >= 64 || _mf_smem_set[_mf_dev] < (int)(bytes)) {                \
+      MF_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                       (int)(bytes)));                                         \
+      if (_mf_dev >= 0 && _mf_dev < 64) _mf_smem_set[_mf_dev] = (int)(bytes);                  \
+    }                                                                                          \
+  } while (0)
+
 namespace mf {
 
 static inline unsigned div_up(long long a, long long b) { return (unsigned)((a + b - 1) / b); }

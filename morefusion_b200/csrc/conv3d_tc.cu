@@ -761,16 +761,10 @@ extern "C" int mf_gemm_tc_set_stamps(void* dev_buf) {
 template <int BLOCK_N, int STAGES>
 static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t stream) {
   constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
-  static bool attr = false;
-  static int n_sm = 148;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc_persistent<BLOCK_N, STAGES>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int dev = 0;
-    MF_CUDA_TRY(cudaGetDevice(&dev));
-    MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM((k_gemm_tc_persistent<BLOCK_N, STAGES>), smem);
+  int n_sm = 148, dev = 0;
+  MF_CUDA_TRY(cudaGetDevice(&dev));
+  MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   int grid = sc.n_units < n_sm ? sc.n_units : n_sm;
   k_gemm_tc_persistent<BLOCK_N, STAGES><<<grid, TC_P_THREADS, smem, stream>>>(args, sc);
   MF_LAUNCH_CHECK();
@@ -789,12 +783,7 @@ static bool persistent_enabled() {
 template <int BLOCK_N, int STAGES>
 static int launch(const TcArgs& args, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, STAGES>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM((k_gemm_tc<BLOCK_N, STAGES>), smem);
   k_gemm_tc<BLOCK_N, STAGES><<<grid, 256, smem, stream>>>(args);
   MF_LAUNCH_CHECK();
   return MF_OK;

@@ -20,7 +20,12 @@
 //                chain through x = R p + t into per-item (gt, gR) partials (fixed-order trees)
 //   P5 update    per object: reduce partials, quaternion_matrix backward
 //                (quaternion_matrix.py:41-49), Chainer-form Adam; reset keys for the next iteration
-// Every reduction is a fixed-order tree: results are bit-reproducible for a given G.
+// Reductions: the four loss sums and the 12 per-object (gR | gt) sums are accumulated in FP64 from
+// exactly-representable terms (fp32 values / products of two fp32 values), then rounded to fp32
+// once.  The result is therefore independent of the summation order (up to 1e-16 relative), which
+// is what closed-loop parity needs: Adam divides every gradient component by its own sqrt(v), so
+// fp32 summation noise on a nearly-cancelling component turns into O(alpha) differences in the
+// pose after a few dozen iterations.  The oracle (oracle/icc.py) sums the same terms in fp64.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -53,8 +58,8 @@ struct IccParams {
   unsigned long long* keys;    // [Ntot][2][V]
   float4* coefs;               // [Ntot][V]
   unsigned int* maxbits;       // [Ntot][2]
-  float* partials;             // [S][G][4]
-  float* slots;                // [sum N_s*C_s][12]
+  double* partials;            // [S][G][4]
+  double* slots;               // [S][G][kIccMaxObj][12]
   unsigned int* barrier;       // [S][1 + kBarSub]
   float* loss;                 // [S][n_iter]
   float* grads;                // [Ntot,7] gradient of the last iteration (gq | gt)
@@ -97,11 +102,17 @@ __device__ __forceinline__ void group_barrier(unsigned int* bar /* [1 + kBarSub]
   __syncthreads();
 }
 
-// deterministic block-wide sum of NV values per thread; result valid in thread 0
-template <int NV>
-__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* [8*NV] */) {
+__device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of NV values per thread; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* [8*NV] */) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum_d(v[k]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   if (lane == 0)
@@ -111,7 +122,7 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* [8*NV] 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      float s = 0.f;
+      double s = 0.0;
       for (int w = 0; w < kIccThreads / 32; ++w) s += smem[w * NV + k];
       v[k] = s;
     }
@@ -184,14 +195,14 @@ __global__ void __launch_bounds__(kIccThreads, 4)
 k_icc_run(IccParams p, IccAlpha alpha) {
   __shared__ float sR[kIccMaxObj][9];
   __shared__ float sT[kIccMaxObj][3];
-  __shared__ float sred[8 * 12];
+  __shared__ double sred[8 * 12];
   __shared__ float stot[4];
   // per-scene constants staged once (they are read by every work item of every iteration)
   __shared__ float sPitch[kIccMaxObj];
   __shared__ float sOrigin[kIccMaxObj][3];
   __shared__ int sPtEnd[kIccMaxObj];
   // per-warp running sums of (gR | gt) per source object: no block barrier per work item
-  __shared__ float sAcc[kIccThreads / 32][kIccMaxObj][12];
+  __shared__ double sAcc[kIccThreads / 32][kIccMaxObj][12];
 
   const int tid = threadIdx.x;
   const int scene = blockIdx.x / p.G, cta = blockIdx.x % p.G;
@@ -304,7 +315,7 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     ICC_STAMP(2)
     // ---- P3: grids, loss partial sums, backward coefficients
     {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rew_num, rew_den, pen_num, pen_den
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};   // rew_num, rew_den, pen_num, pen_den (fp64 sums of fp32 terms)
       const int blocks_per = (V + kIccThreads - 1) / kIccThreads;
       for (int w = cta; w < sc.N * blocks_per; w += p.G) {
         int il = w / blocks_per, v = (w - il * blocks_per) * kIccThreads + tid;
@@ -342,14 +353,14 @@ k_icc_run(IccParams p, IccAlpha alpha) {
           }
         }
         p.coefs[(size_t)gi * V + v] = make_float4(ws * gt, wi * gne, wi, b1);
-        acc[0] += surface * gt;
-        acc[1] += gt;
-        acc[2] += inside * gne;
-        acc[3] += inside;
+        acc[0] += (double)(surface * gt);
+        acc[1] += (double)gt;
+        acc[2] += (double)(inside * gne);
+        acc[3] += (double)inside;
       }
       block_sum<4>(acc, sred);
       if (tid == 0) {
-        float* dst = p.partials + ((size_t)scene * p.G + cta) * 4;
+        double* dst = p.partials + ((size_t)scene * p.G + cta) * 4;
         dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2]; dst[3] = acc[3];
       }
     }
@@ -358,18 +369,20 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     ICC_STAMP(3)
     // ---- P4: totals, then gather-backward
     if (tid < 32) {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
       for (int c = tid; c < p.G; c += 32) {
-        const float* src = p.partials + ((size_t)scene * p.G + c) * 4;
+        const double* src = p.partials + ((size_t)scene * p.G + c) * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] += __ldcg(src + k);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a[k] = warp_sum(a[k]);
+      for (int k = 0; k < 4; ++k) a[k] = warp_sum_d(a[k]);
       if (tid == 0) {
+        // the four sums are rounded to fp32 once; everything after is fp32 like the reference
 #pragma unroll
-        for (int k = 0; k < 4; ++k) stot[k] = a[k];
-        if (cta == 0) p.loss[(size_t)scene * p.n_iter + it] = a[2] / a[3] - a[0] / a[1];
+        for (int k = 0; k < 4; ++k) stot[k] = (float)a[k];
+        if (cta == 0)
+          p.loss[(size_t)scene * p.n_iter + it] = stot[2] / stot[3] - stot[0] / stot[1];
       }
     }
     __syncthreads();
@@ -378,7 +391,7 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     const float c_in1 = stot[2] / (stot[3] * stot[3]);
 
     for (int e = tid; e < (kIccThreads / 32) * kIccMaxObj * 12; e += kIccThreads)
-      (&sAcc[0][0][0])[e] = 0.f;
+      (&sAcc[0][0][0])[e] = 0.0;
     __syncthreads();
     // Voxel-centric gather (the structure of the reference's backward kernel, tdf.py:119-145):
     // every voxel that has a winner contributes  unit(f - v) * d loss/d tdf[v]  to its winning
@@ -389,9 +402,9 @@ k_icc_run(IccParams p, IccAlpha alpha) {
       for (int w = cta; w < n_gk * blocks_per; w += p.G) {
         const int gk = w / blocks_per, v = (w - gk * blocks_per) * kIccThreads + tid;
         const int il = gk >> 1, kind = gk & 1, gi = sc.o0 + il;
-        float g12[12];
+        double g12[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) g12[k] = 0.f;
+        for (int k = 0; k < 12; ++k) g12[k] = 0.0;
         bool any = false;
         int jl = 1 << 30;
         if (v < V && !(kind == 1 && sc.N == 1)) {
@@ -416,9 +429,11 @@ k_icc_run(IccParams p, IccAlpha alpha) {
                 const float gtdf = -dg / trunc;
                 const float ax = ddx / n * gtdf, ay = ddy / n * gtdf, az = ddz / n * gtdf;
                 // x = R p + t :  gt += gx ; gR += gx (x) p
-                g12[0] = ax * px; g12[1] = ax * py; g12[2] = ax * pz; g12[3] = ax;
-                g12[4] = ay * px; g12[5] = ay * py; g12[6] = ay * pz; g12[7] = ay;
-                g12[8] = az * px; g12[9] = az * py; g12[10] = az * pz; g12[11] = az;
+                // exact fp64 products of fp32 factors
+                const double dax = ax, day = ay, daz = az, dpx = px, dpy = py, dpz = pz;
+                g12[0] = dax * dpx; g12[1] = dax * dpy; g12[2] = dax * dpz; g12[3] = dax;
+                g12[4] = day * dpx; g12[5] = day * dpy; g12[6] = day * dpz; g12[7] = day;
+                g12[8] = daz * dpx; g12[9] = daz * dpy; g12[10] = daz * dpz; g12[11] = daz;
                 any = true;
               }
             }
@@ -431,9 +446,9 @@ k_icc_run(IccParams p, IccAlpha alpha) {
           const int leader = __ffs(todo) - 1;
           const int jcur = __shfl_sync(0xffffffffu, jl, leader);
           const bool mine = any && (jl == jcur);
-          float sums[12];
+          double sums[12];
 #pragma unroll
-          for (int k = 0; k < 12; ++k) sums[k] = warp_sum(mine ? g12[k] : 0.f);
+          for (int k = 0; k < 12; ++k) sums[k] = warp_sum_d(mine ? g12[k] : 0.0);
           if (lane_id == 0)
 #pragma unroll
             for (int k = 0; k < 12; ++k) sAcc[warp_id][jcur][k] += sums[k];
@@ -445,7 +460,7 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     // one slot per (CTA, object): warps summed in fixed order
     for (int e = tid; e < sc.N * 12; e += kIccThreads) {
       int jl = e / 12, k = e - jl * 12;
-      float s = 0.f;
+      double s = 0.0;
 #pragma unroll
       for (int wv = 0; wv < kIccThreads / 32; ++wv) s += sAcc[wv][jl][k];
       p.slots[(((size_t)scene * p.G + cta) * kIccMaxObj + jl) * 12 + k] = s;
@@ -458,21 +473,22 @@ k_icc_run(IccParams p, IccAlpha alpha) {
       {
         int gj = sc.o0 + jl;
         // all threads: slots of the G CTAs (thread-strided), then a fixed-order block tree
-        float a[12];
+        double a[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) a[k] = 0.f;
+        for (int k = 0; k < 12; ++k) a[k] = 0.0;
         for (int c = tid; c < p.G; c += kIccThreads) {
-          const float* slot = p.slots + (((size_t)scene * p.G + c) * kIccMaxObj + jl) * 12;
+          const double* slot = p.slots + (((size_t)scene * p.G + c) * kIccMaxObj + jl) * 12;
 #pragma unroll
           for (int k = 0; k < 12; ++k) a[k] += __ldcg(slot + k);
         }
         block_sum<12>(a, sred);
         if (tid == 0) {
           float q[4] = {p.q[4 * gj], p.q[4 * gj + 1], p.q[4 * gj + 2], p.q[4 * gj + 3]};
-          float gR[9] = {a[0], a[1], a[2], a[4], a[5], a[6], a[8], a[9], a[10]};
+          float gR[9] = {(float)a[0], (float)a[1], (float)a[2], (float)a[4], (float)a[5],
+                         (float)a[6], (float)a[8], (float)a[9], (float)a[10]};
           float g7[7];
           quat_grad(q, gR, g7);
-          g7[4] = a[3]; g7[5] = a[7]; g7[6] = a[11];
+          g7[4] = (float)a[3]; g7[5] = (float)a[7]; g7[6] = (float)a[11];
 #pragma unroll
           for (int k = 0; k < 7; ++k) p.grads[(size_t)gj * 7 + k] = g7[k];
           if (p.update) {
@@ -539,8 +555,8 @@ static IccLayout icc_layout(int Ntot, int D, int S, int G, int n_slots) {
   L.keys = o; o += al((size_t)Ntot * 2 * V * 8);
   L.coefs = o; o += al((size_t)Ntot * V * 16);
   L.maxbits = o; o += al((size_t)Ntot * 2 * 4);
-  L.partials = o; o += al((size_t)S * G * 16);
-  L.slots = o; o += al((size_t)S * G * kIccMaxObj * 48);   // one (gR|gt) slot per (CTA, object)
+  L.partials = o; o += al((size_t)S * G * 32);
+  L.slots = o; o += al((size_t)S * G * kIccMaxObj * 96);   // one fp64 (gR|gt) slot per (CTA, object)
   (void)n_slots;
   L.barrier = o; o += al((size_t)S * (1 + kBarSub) * 4);
   L.total = o;
@@ -566,7 +582,7 @@ extern "C" int mf_icc_run_profiled(
     int, int, int, float, float, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
     const int32_t*, const int32_t*, const int32_t*, int, const float*, const float*, const float*,
     const float*, const float*, const float*, float*, float*, float*, int, int, const float*,
-    const float*, float, float, float, float, float*, float*, int, void*, size_t,
+    const float*, double, double, double, double, float*, float*, int, void*, size_t,
     unsigned long long*, void*);
 
 extern "C" int mf_icc_run(
@@ -578,7 +594,7 @@ extern "C" int mf_icc_run(
     const float* grid_target, const float* grid_nontarget_empty,
     float* quaternion, float* translation, float* adam_state,
     int n_iter, int update, const float* alpha_q_host, const float* alpha_t_host,
-    float beta1, float beta2, float eps, float eta,
+    double beta1, double beta2, double eps, double eta,
     float* loss_history, float* grads, int group_size,
     void* workspace, size_t workspace_bytes, void* stream_) {
   return mf_icc_run_profiled(n_scenes, n_objects_total, voxel_dim, voxel_threshold, sdf_offset,
@@ -599,7 +615,7 @@ extern "C" int mf_icc_run_profiled(
     const float* grid_target, const float* grid_nontarget_empty,
     float* quaternion, float* translation, float* adam_state,
     int n_iter, int update, const float* alpha_q_host, const float* alpha_t_host,
-    float beta1, float beta2, float eps, float eta,
+    double beta1, double beta2, double eps, double eta,
     float* loss_history, float* grads, int group_size,
     void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -628,14 +644,16 @@ extern "C" int mf_icc_run_profiled(
   p.keys = (unsigned long long*)(ws + L.keys);
   p.coefs = (float4*)(ws + L.coefs);
   p.maxbits = (unsigned int*)(ws + L.maxbits);
-  p.partials = (float*)(ws + L.partials);
-  p.slots = (float*)(ws + L.slots);
+  p.partials = (double*)(ws + L.partials);
+  p.slots = (double*)(ws + L.slots);
   p.barrier = (unsigned int*)(ws + L.barrier);
   p.loss = loss_history; p.grads = grads;
   p.Ntot = n_objects_total; p.G = G; p.n_iter = n_iter; p.update = update;
-  p.one_minus_beta1 = (float)(1.0 - (double)beta1);
-  p.one_minus_beta2 = (float)(1.0 - (double)beta2);
-  p.eps = eps; p.eta = eta;
+  // chainer: `m += (1 - hp.beta1) * (grad - m)` with python-float hyperparameters -> the
+  // difference is taken in double and only then rounded to the array dtype
+  p.one_minus_beta1 = (float)(1.0 - beta1);
+  p.one_minus_beta2 = (float)(1.0 - beta2);
+  p.eps = (float)eps; p.eta = (float)eta;
   p.phase_ns = phase_ns;
   IccAlpha alpha;
   for (int i = 0; i < 128; ++i) {

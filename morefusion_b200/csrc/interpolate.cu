@@ -183,12 +183,7 @@ extern "C" int mf_interpolate_voxel_grid_fwd(const float* voxelized, const float
   } else if (V * 4 * 8 <= 160 * 1024 && C >= 8 && P <= (1LL << 22) && B <= 65535) {
     // plane-staged path: 8 channel planes per CTA in shared memory
     constexpr int CG = 8;
-    static bool attr = false;
-    if (!attr) {
-      MF_CUDA_TRY(cudaFuncSetAttribute(k_interp_fwd_planes<CG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr = true;
-    }
+    MF_ENSURE_DYN_SMEM(k_interp_fwd_planes<CG>, 160 * 1024);
     dim3 grid((C + CG - 1) / CG, B);
     k_interp_fwd_planes<CG><<<grid, 256, (size_t)V * 4 * CG, stream>>>(
         voxelized, points, batch_indices, P, B, C, X, Y, Z, values);

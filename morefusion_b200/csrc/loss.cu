@@ -154,12 +154,7 @@ extern "C" int mf_average_distance_fwd(const float* points, int n_points, const 
   if (!points || !transform_true || !transforms_pred || !out) return MF_E_BADARG;
   size_t smem = (size_t)n_points * 12;
   if (smem > 200 * 1024) return MF_E_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_avg_dist_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024));
-    attr = true;
-  }
+  MF_ENSURE_DYN_SMEM(k_avg_dist_fwd, 200 * 1024);
   k_avg_dist_fwd<<<n_pred, kAdThreads, smem, (cudaStream_t)stream_>>>(
       points, n_points, transform_true, transforms_pred, symmetric, out, nn_indices);
   MF_LAUNCH_CHECK();

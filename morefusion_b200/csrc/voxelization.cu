@@ -4,14 +4,16 @@
 //   morefusion/functions/geometry/average_voxelization_3d.py:57-115, :163-218
 //   morefusion/functions/geometry/max_voxelization_3d.py:75-138, :153-183
 //
-// average_voxelization_3d forward:
-//   k_avg_keys_fill  prepass (keys, tile counts, batch segments, mode) fused into a dense,
-//                    look-up-free zero fill of matrix/counts (runs at the HBM write roofline)
-//   k_avg_leaders    fast mode (sorted batch indices): one warp per point; the lowest-index point
-//                    of a voxel sums the voxel's points in ascending order and overwrites it
-//   k_avg_tiles      general mode / ragged shapes: a CTA owns (batch, channel chunk, 256 voxels),
-//                    ordered stream compaction into a shared-memory tile, coalesced tile write
-// No atomics on the output, per-voxel sums in ascending point order -> bit-exact vs the oracle.
+// average_voxelization_3d forward = two launches, no memsets, no atomics on HBM:
+//   k_avg_prepass  one thread per point: voxel key, batch-segment boundaries, per-CTA flag word
+//   k_avg_fused    a CTA owns (batch b, 1024 consecutive voxels, <= 64 channels).  It finds the
+//                  points of b that fall into its voxels (ordered compaction of the keys), sums
+//                  them per occupied voxel in ascending point order in shared memory, divides,
+//                  and then streams its 4 KiB piece of every channel plane: one 16-byte store per
+//                  thread and plane, zeros straight from registers, occupied voxels patched in
+//                  from shared memory.  Every output element is written exactly once, so the
+//                  operator costs one pass over the (mostly zero) dense output.
+// Per-voxel sums are taken in ascending point order -> bit-exact vs the oracle.
 #include "common.cuh"
 
 namespace mf {
@@ -19,362 +21,329 @@ namespace mf {
 constexpr int kThreads = 256;
 constexpr int kListCap = 1024;           // keys scanned per round = 4 per thread
 constexpr int kStage = 64;               // list entries whose values are staged in smem at once
-constexpr int kHdrSortedBit = 2;         // hdr[0] bit: set = batch_indices non-decreasing
+constexpr int kGPT = 4;                  // 4-voxel groups per thread
+constexpr int kVS = kThreads * kGPT * 4; // voxels per CTA segment: 16 KiB of every plane
+constexpr int kSlots = 256;              // occupied voxels whose sums are resident per round
+constexpr int kSlotsRound = kSlots - 3;  // a 4-voxel group never straddles two rounds
 
 struct VoxGeom {
   float ox, oy, oz, pitch;
   int X, Y, Z, B;
 };
 
-constexpr int kLeaderMaxSeg = 4096;      // longest batch segment the per-point leader path scans
-constexpr int kLeaderSmemKeys = 8192;    // keys a leader CTA can stage in shared memory
-
-__device__ __forceinline__ void vox_keys_point(
-    const float* __restrict__ points, const int* __restrict__ bi, long long N, VoxGeom g,
-    int* __restrict__ keys, int* __restrict__ hdr, int* __restrict__ seg_start,
-    int* __restrict__ seg_end, int* __restrict__ flags, int* __restrict__ tile_count, int VT,
-    int* __restrict__ flags2, int* __restrict__ tile_list, int* __restrict__ tile_list_n,
-    unsigned int* __restrict__ occ_bits, long long n);
-
 // ---------------------------------------------------------------- prepass
-// key[n] = b*V + flat voxel index, or -1 if out of bounds.  Also: NaN flag,
-// sortedness, per-batch [seg_start, seg_end) when sorted.
-__global__ void k_vox_keys(const float* __restrict__ points, const int* __restrict__ bi,
-                           long long N, VoxGeom g, int* __restrict__ keys,
-                           int* __restrict__ hdr, int* __restrict__ seg_start,
-                           int* __restrict__ seg_end, int* __restrict__ flags,
-                           int* __restrict__ tile_count, int VT, int* __restrict__ flags2,
-                           int* __restrict__ tile_list, int* __restrict__ tile_list_n,
-                           unsigned int* __restrict__ occ_bits, int* __restrict__ done,
-                           int* __restrict__ mode) {
-  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) vox_keys_point(points, bi, N, g, keys, hdr, seg_start, seg_end, flags, tile_count, VT,
-                            flags2, tile_list, tile_list_n, occ_bits, n);
-  // ---- the last block to finish decides the forward mode: "fast" (per-point leader scatter)
-  // needs sorted batch indices and short segments; anything else takes the general tile kernel
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!s_last || threadIdx.x >= 32) return;
-  __threadfence();
-  int maxlen = 0;
-  for (int b = threadIdx.x; b < g.B; b += 32) {
-    int s0 = __ldcg(seg_start + b), s1 = __ldcg(seg_end + b);
-    if (s0 >= 0) maxlen = max(maxlen, s1 - s0);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  if (threadIdx.x == 0)
-    *mode = ((__ldcg(hdr) & kHdrSortedBit) && maxlen <= kLeaderMaxSeg) ? 1 : 0;
-}
-
-__device__ __forceinline__ void vox_keys_point(
-    const float* __restrict__ points, const int* __restrict__ bi, long long N, VoxGeom g,
-    int* __restrict__ keys, int* __restrict__ hdr, int* __restrict__ seg_start,
-    int* __restrict__ seg_end, int* __restrict__ flags, int* __restrict__ tile_count, int VT,
-    int* __restrict__ flags2, int* __restrict__ tile_list, int* __restrict__ tile_list_n,
-    unsigned int* __restrict__ occ_bits, long long n) {
-  float x = points[3 * n], y = points[3 * n + 1], z = points[3 * n + 2];
-  int b = bi[n];
+// key[n] = b*V + flat voxel index, or -1 if out of bounds.  seg_start[b] / seg_end[b] are
+// written by the points at the boundaries of b's run; entries of absent batches are never
+// written, so the consumer validates what it reads against batch_indices instead of relying on
+// an initialised workspace.  cta_flags[blockIdx.x] = OR of the MF_FLAG_* bits of this CTA's
+// points (every slot is written: no memset).
+__global__ void __launch_bounds__(kThreads)
+k_avg_prepass(const float* __restrict__ points, const int* __restrict__ bi, long long N,
+              VoxGeom g, int* __restrict__ keys, int* __restrict__ seg_start,
+              int* __restrict__ seg_end, int* __restrict__ cta_flags) {
+  const long long n = (long long)blockIdx.x * kThreads + threadIdx.x;
   int f = 0;
-  if (isnan(x) || isnan(y) || isnan(z)) f |= MF_FLAG_NAN_POINTS;
-  int ix = voxel_coord(x, g.ox, g.pitch);
-  int iy = voxel_coord(y, g.oy, g.pitch);
-  int iz = voxel_coord(z, g.oz, g.pitch);
-  bool okb = (b >= 0) && (b < g.B);
-  if (!okb) f |= MF_FLAG_BAD_BATCH_INDEX;
-  bool ok = okb && ix >= 0 && ix < g.X && iy >= 0 && iy < g.Y && iz >= 0 && iz < g.Z;
-  const int V = g.X * g.Y * g.Z;
-  const int flat = (ix * g.Y + iy) * g.Z + iz;
-  keys[n] = ok ? (b * V + flat) : -1;
-  if (ok) {
-    const int tile = b * ((V + VT - 1) / VT) + flat / VT;
-    // the first point to hit a tile appends it to the list of occupied tiles
-    if (atomicAdd(&tile_count[tile], 1) == 0) tile_list[atomicAdd(tile_list_n, 1)] = tile;
-    const int key = b * V + flat;
-    if (occ_bits) atomicOr(&occ_bits[key >> 5], 1u << (key & 31));
+  if (n < N) {
+    const float x = points[3 * n], y = points[3 * n + 1], z = points[3 * n + 2];
+    const int b = bi[n];
+    if (isnan(x) || isnan(y) || isnan(z)) f |= MF_FLAG_NAN_POINTS;
+    const int ix = voxel_coord(x, g.ox, g.pitch);
+    const int iy = voxel_coord(y, g.oy, g.pitch);
+    const int iz = voxel_coord(z, g.oz, g.pitch);
+    const bool okb = (b >= 0) && (b < g.B);
+    if (!okb) f |= MF_FLAG_BAD_BATCH_INDEX;
+    const bool ok = okb && ix >= 0 && ix < g.X && iy >= 0 && iy < g.Y && iz >= 0 && iz < g.Z;
+    const int V = g.X * g.Y * g.Z;
+    keys[n] = ok ? (b * V + (ix * g.Y + iy) * g.Z + iz) : -1;
+    const int prev = (n > 0) ? bi[n - 1] : b;
+    if (prev > b) f |= MF_FLAG_UNSORTED_BATCH;
+    if (okb) {
+      if (n == 0 || prev != b) seg_start[b] = (int)n;
+      if (n == N - 1 || bi[n + 1] != b) seg_end[b] = (int)(n + 1);
+    }
   }
-  int prev = (n > 0) ? bi[n - 1] : b;
-  if (prev > b) {
-    atomicAnd(&hdr[0], ~kHdrSortedBit);
-    f |= MF_FLAG_UNSORTED_BATCH;
+  f = __reduce_or_sync(0xffffffffu, (unsigned)f);
+  __shared__ int sf[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sf[threadIdx.x >> 5] = f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) a |= sf[w];
+    cta_flags[blockIdx.x] = a;
   }
-  if (okb) {
-    if (n == 0 || prev != b) seg_start[b] = (int)n;
-    if (n == N - 1 || bi[n + 1] != b) seg_end[b] = (int)(n + 1);
-  }
-  if (f && flags) atomicOr(flags, f);
-  if (f && flags2) atomicOr(flags2, f);
 }
 
-// ---------------------------------------------------------------- forward tiles
+// ---------------------------------------------------------------- forward
 struct AvgParams {
   const float* values;
   const int* keys;
-  const int* hdr;
+  const int* bi;
   const int* seg_start;
   const int* seg_end;
+  const int* cta_flags;
+  int n_key_ctas;
   long long N;
   int C, B, V;
-  int VT;       // voxels per tile
-  int CC;       // channels per chunk
-  int CCp;      // padded (odd) row length of the smem tile
-  int G;        // thread groups per CTA (each owns voxels v % G == g)
+  int CC;       // channels per chunk (grid.y chunks)
+  int CCp;      // padded (odd) row length of the smem rows
+  int LWs;      // log2 of the lane width LW >= CC of the staging / accumulate roles
+  int segs_per_batch;
+  int vec4;     // planes are 16-byte aligned and V % 4 == 0: float4 stores
   float* matrix;
   int* counts;
-  const int* tile_count;   // [B][tiles_per_batch] points per voxel tile (from the prepass)
-  const int* tile_list;    // occupied tiles (unordered) and their number
-  const int* tile_list_n;
-  const int* mode;         // 1 = fast (leader scatter), 0 = general (tile kernel)
-  int n_lead_ctas, zero_groups;
-  int tiles_per_batch, n_chunks, n_items;
+  int* flags_ws;     // workspace copy of the flag word (always written)
+  int* flags_user;   // caller's flag word (OR-ed into), may be null
 };
 
-// Prepass + dense zero fill in ONE launch.  CTAs [0, n_key_ctas) run the key / segment /
-// tile-count prepass (k_vox_keys' body; the last of them picks the forward mode), every other CTA
-// streams 16 KiB of zeros into matrix / counts with no look-ups at all, so the bulk of the
-// operator -- writing the dense, mostly-zero output -- runs at plain-fill speed while the
-// latency-bound prepass hides inside the first wave.  The occupied voxels are overwritten
-// afterwards by the leader scatter (fast mode) or the tile kernel (general mode); that is
-// N*(C+1) extra element writes (3 % of the output at the model shape).
-struct KeysArgs {
-  const float* points;
-  const int* bi;
-  VoxGeom g;
-  int* keys;
-  int* hdr;
-  int* seg_start;
-  int* seg_end;
-  int* flags;
-  int* tile_count;
-  int* flags2;
-  int* tile_list;
-  int* tile_list_n;
-  int* done;
-  int* mode;
-  int n_key_ctas;
-};
-
-__global__ void __launch_bounds__(256)
-k_avg_keys_fill(AvgParams p, KeysArgs ka) {
-  if ((int)blockIdx.x < ka.n_key_ctas) {
-    long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < p.N)
-      vox_keys_point(ka.points, ka.bi, p.N, ka.g, ka.keys, ka.hdr, ka.seg_start, ka.seg_end,
-                     ka.flags, ka.tile_count, p.VT, ka.flags2, ka.tile_list, ka.tile_list_n,
-                     nullptr, n);
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ka.done, 1) == ka.n_key_ctas - 1);
-    __syncthreads();
-    if (!s_last || threadIdx.x >= 32) return;
-    __threadfence();
-    int maxlen = 0;
-    for (int b = threadIdx.x; b < ka.g.B; b += 32) {
-      int s0 = __ldcg(ka.seg_start + b), s1 = __ldcg(ka.seg_end + b);
-      if (s0 >= 0) maxlen = max(maxlen, s1 - s0);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    if (threadIdx.x == 0)
-      *ka.mode = ((__ldcg(ka.hdr) & kHdrSortedBit) && maxlen <= kLeaderMaxSeg) ? 1 : 0;
-    return;
-  }
-  // fill role: the output is walked linearly, plane by plane, 16 KiB per CTA
-  const int fid = blockIdx.x - ka.n_key_ctas;
-  const int plane = fid / p.zero_groups, seg = fid - plane * p.zero_groups;
-  const int b = plane / (p.C + 1), c = plane - b * (p.C + 1);
-  float* base = (c < p.C) ? p.matrix + ((long long)b * p.C + c) * p.V
-                          : reinterpret_cast<float*>(p.counts) + (long long)b * p.V;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4* dst = reinterpret_cast<float4*>(base) + seg * 1024 + threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) __stcs(dst + k * 256, z4);
-}
-
-// Kernel A: per-point leader scatter (fast mode; exits otherwise).  One warp per point; the
-// lowest-index point of a voxel sums the voxel's points in ascending order (lanes over
-// channels), divides and writes C values + the count over the zeros of k_avg_keys_fill.
-__global__ void __launch_bounds__(256)
-k_avg_leaders(AvgParams p) {
-  const int fast = __ldg(p.mode);
-  __shared__ int skeys[kLeaderSmemKeys];
-  const int lead_id = blockIdx.x;
-  if (!fast) return;
-  // The CTA's 8 points lie in at most a few batch segments; their keys are staged in shared
-  // memory once and every warp scans them from there.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long n_first = (long long)lead_id * 8;
-  const long long n_last = min(n_first + 7, p.N - 1);
-  int k_first = -1, k_last = -1;                            // first / last valid key of the CTA
-  for (long long j = n_first; j <= n_last; ++j) {
-    int kk = __ldg(p.keys + j);
-    if (kk >= 0) { if (k_first < 0) k_first = kk; k_last = kk; }
-  }
-  if (k_first < 0) return;                                  // uniform: all 8 points out of bounds
-  const int s_lo = __ldg(p.seg_start + k_first / p.V), s_hi = __ldg(p.seg_end + k_last / p.V);
-  const bool staged = (s_hi - s_lo) <= kLeaderSmemKeys;
-  if (staged)
-    for (int e = threadIdx.x; e < s_hi - s_lo; e += 256) skeys[e] = __ldg(p.keys + s_lo + e);
-  __syncthreads();
-  const long long n = n_first + warp;
-  if (n >= p.N) return;
-  const int key = staged ? skeys[n - s_lo] : __ldg(p.keys + n);
-  if (key < 0) return;
-  const int b = key / p.V;
-  const int lo = __ldg(p.seg_start + b), hi = __ldg(p.seg_end + b);
-  const int nn = (int)n;
-  bool earlier = false;
-  for (int j0 = lo; j0 < nn && !earlier; j0 += 32) {
-    int j = j0 + lane;
-    bool m = (j < nn) && ((staged ? skeys[j - s_lo] : __ldg(p.keys + j)) == key);
-    earlier = __any_sync(0xffffffffu, m);
-  }
-  if (earlier) return;
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  int count = 0;
-  for (int j0 = nn - (nn - lo) % 32; j0 < hi; j0 += 32) {   // aligned chunks: j ascends
-    int j = j0 + lane;
-    bool m = (j >= nn) && (j < hi) && ((staged ? skeys[j - s_lo] : __ldg(p.keys + j)) == key);
-    unsigned mask = __ballot_sync(0xffffffffu, m);
-    while (mask) {
-      int l = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float* src = p.values + (long long)(j0 + l) * p.C;
-      for (int k = 0; k * 32 < p.C && k < 8; ++k) {
-        int c = lane + 32 * k;
-        if (c < p.C) acc[k] = __fadd_rn(acc[k], __ldg(src + c));
-      }
-      ++count;
-    }
-  }
-  const int flat = key - b * p.V;
-  const float cf = (float)count;
-  float* dst = p.matrix + (long long)b * p.C * p.V + flat;
-  for (int k = 0; k * 32 < p.C && k < 8; ++k) {
-    int c = lane + 32 * k;
-    if (c < p.C) dst[(long long)c * p.V] = __fdiv_rn(acc[k], cf);
-  }
-  if (lane == 0) p.counts[(long long)b * p.V + flat] = count;
-}
-
-// Kernel B: one CTA per (occupied tile, channel chunk): ordered compaction of the point keys in
-// its voxel range, per-voxel sums in ascending point order in shared memory, divide, write.
+// A CTA owns (batch b, kVS = 4096 consecutive voxels, CC channels): 16 KiB of each of its planes.
+// Thread t owns the 4-voxel groups t, t+256, t+512, t+768 of the segment, i.e. per plane four
+// float4 stores that, over the CTA, cover four consecutive 4 KiB blocks.
 __global__ void __launch_bounds__(kThreads)
-k_avg_tiles(AvgParams p) {
+k_avg_fused(AvgParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);          // [VT][CCp]
-  int* cnt = reinterpret_cast<int*>(tile + (size_t)p.VT * p.CCp);  // [VT]
-  int* list_n = cnt + p.VT;                                   // [kListCap]
-  int* list_v = list_n + kListCap;                            // [kListCap]
-  float* stage = reinterpret_cast<float*>(list_v + kListCap); // [kStage][CCp]
+  float* sums = reinterpret_cast<float*>(smem_raw);                 // [kSlots][CCp]
+  float* stage = sums + (size_t)kSlots * p.CCp;                     // [kStage][CCp]
+  int* list_n = reinterpret_cast<int*>(stage + (size_t)kStage * p.CCp);  // [kListCap] point id
+  int* list_s = list_n + kListCap;                                  // [kListCap] slot
+  int* cnt = list_s + kListCap;                                     // [kSlots]
+  int* base_s = cnt + kSlots;                                       // [kVS/4] first slot of a group
+  unsigned* occ = reinterpret_cast<unsigned*>(base_s + kVS / 4);    // [kVS/32] occupancy bits
   __shared__ int s_warp[kThreads / 32];
-  __shared__ int s_total;
+  __shared__ int s_total, s_lo, s_hi;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / p.segs_per_batch, seg = blockIdx.x - b * p.segs_per_batch;
   const int chunk = blockIdx.y;
-  if (p.mode && __ldg(p.mode)) return;                       // fast mode already wrote everything
-  // grid-stride over the occupied tiles (sparse mode: the count is only known on the device,
-  // so the grid is a fixed few CTAs per SM) or over all tiles (ragged shapes)
-  const int n_work = p.tile_list ? __ldg(p.tile_list_n) : p.n_items;
-  for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
-  const int tb = p.tile_list ? __ldg(p.tile_list + item) : item;
-  const int ti = tb % p.tiles_per_batch, b = tb / p.tiles_per_batch;
-  const int vbase = ti * p.VT;
-  const int vt = min(p.VT, p.V - vbase);
+  const int vbase = seg * kVS;
+  const int vt = min(kVS, p.V - vbase);
   const int c0 = chunk * p.CC;
   const int cc = min(p.CC, p.C - c0);
-  float* out = p.matrix + ((long long)b * p.C + c0) * p.V + vbase;
 
-  for (int e = tid; e < p.VT * p.CCp; e += kThreads) tile[e] = 0.f;
-  for (int e = tid; e < p.VT; e += kThreads) cnt[e] = 0;
-  long long lo = 0, hi = p.N;
-  if (p.hdr[0] & kHdrSortedBit) {
-    int s = p.seg_start[b];
-    if (s < 0) { lo = hi = 0; } else { lo = s; hi = p.seg_end[b]; }
-  }
-  const int klo = b * p.V + vbase, khi = klo + vt;
-  const int g = tid / p.CC, c = tid - g * p.CC;   // accumulate role
-  const bool acc_thread = (g < p.G) && (c < cc);
-  __syncthreads();
-
-  for (long long base = lo; base < hi; base += kListCap) {
-    // ---- ordered compaction of the keys in [base, base+kListCap)
-    long long i0 = base + 4LL * tid;
-    int k[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) k[j] = (i0 + j < hi) ? __ldg(p.keys + i0 + j) : -1;
-    int m = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) m += (k[j] >= klo && k[j] < khi) ? 1 : 0;
-    int incl = m;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+  // ---- flag word of the call (per-CTA words of the prepass, OR-ed)
+  int f = 0;
+  for (int i = tid; i < p.n_key_ctas; i += kThreads) f |= __ldg(p.cta_flags + i);
+  const int unsorted = __syncthreads_or(f & MF_FLAG_UNSORTED_BATCH);
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    const int fn = __syncthreads_or(f & MF_FLAG_NAN_POINTS) ? MF_FLAG_NAN_POINTS : 0;
+    const int fb = __syncthreads_or(f & MF_FLAG_BAD_BATCH_INDEX) ? MF_FLAG_BAD_BATCH_INDEX : 0;
+    if (tid == 0) {
+      const int all = fn | fb | (unsorted ? MF_FLAG_UNSORTED_BATCH : 0);
+      *p.flags_ws = all;
+      if (p.flags_user && all) atomicOr(p.flags_user, all);
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int woff = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) woff += (w < warp) ? s_warp[w] : 0;
-    if (tid == kThreads - 1) s_total = woff + incl;
-    int pos = woff + incl - m;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (k[j] >= klo && k[j] < khi) {
-        list_n[pos] = (int)(i0 + j);  // point id (N < 2^31 checked on host)
-        list_v[pos] = k[j] - klo;
-        ++pos;
+  }
+  // ---- the points of batch b: its run [lo, hi) when batch_indices are sorted, else all points
+  if (tid == 0) {
+    long long lo = 0, hi = p.N;
+    if (!unsorted) {
+      lo = hi = 0;
+      if (p.N > 0) {
+        const int s = p.seg_start[b], e = p.seg_end[b];
+        const bool oks = s >= 0 && s < p.N && __ldg(p.bi + s) == b && (s == 0 || __ldg(p.bi + s - 1) != b);
+        const bool oke = e > 0 && e <= p.N && __ldg(p.bi + e - 1) == b && (e == p.N || __ldg(p.bi + e) != b);
+        if (oks && oke && s < e) { lo = s; hi = e; }
       }
-    __syncthreads();
-    const int L = s_total;
-    // values of the listed points are staged through shared memory in batches of kStage rows
-    // (independent, coalesced loads), then added per voxel in ascending point order
-    for (int l0 = 0; l0 < L; l0 += kStage) {
-      const int nl = min(kStage, L - l0);
-      for (int e = tid; e < nl * cc; e += kThreads) {
-        int l = e / cc, ch = e - l * cc;
-        stage[l * p.CCp + ch] = __ldg(p.values + (long long)list_n[l0 + l] * p.C + c0 + ch);
+    }
+    s_lo = (int)lo;
+    s_hi = (int)hi;
+  }
+  for (int i = tid; i < kVS / 32; i += kThreads) occ[i] = 0u;
+  __syncthreads();
+  const int lo = s_lo, hi = s_hi;
+  const int klo = b * p.V + vbase, khi = klo + vt;
+
+  // ---- pass 1: occupancy bits of this segment
+  for (int j = lo + tid; j < hi; j += kThreads) {
+    const int k = __ldg(p.keys + j);
+    if (k >= klo && k < khi) atomicOr(&occ[(k - klo) >> 5], 1u << ((k - klo) & 31));
+  }
+  __syncthreads();
+  // slots are numbered in voxel order: exclusive scan of the per-group popcounts, group
+  // G = t + 256*k scanned k-major so that the numbering follows the voxel index
+  unsigned nib[kGPT];
+  int gbase[kGPT];
+  int n_occ = 0;                                              // occupied voxels of the segment
+  {
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < kGPT; ++k) {
+      const int G = tid + kThreads * k;
+      nib[k] = (occ[G >> 3] >> ((G & 7) * 4)) & 0xFu;
+      const int m = __popc(nib[k]);
+      int incl = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
+      __syncthreads();                                        // s_warp reuse
+      if (lane == 31) s_warp[warp] = incl;
       __syncthreads();
-      if (acc_thread) {
-        for (int l = 0; l < nl; ++l) {
-          int v = list_v[l0 + l];
-          if ((v % p.G) == g) {
-            tile[v * p.CCp + c] = __fadd_rn(tile[v * p.CCp + c], stage[l * p.CCp + c]);
-            if (c == 0) cnt[v] += 1;
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) {
+        woff += (w < warp) ? s_warp[w] : 0;
+        tot += s_warp[w];
+      }
+      gbase[k] = carry + woff + incl - m;
+      base_s[G] = gbase[k];
+      carry += tot;
+    }
+    n_occ = carry;
+  }
+  __syncthreads();
+  // trailing empty groups carry base == n_occ: they need a round of their own when n_occ is a
+  // multiple of kSlotsRound
+  const int n_rounds = n_occ / kSlotsRound + 1;
+  // thread roles of the staging / accumulate / divide loops: NR rows x LW channel lanes
+  const int LW = 1 << p.LWs, NR = kThreads >> p.LWs;
+  const int g = tid >> p.LWs, c = tid & (LW - 1);
+  const bool c_ok = c < cc;
+
+  for (int r = 0; r < n_rounds; ++r) {
+    const int n_used = min(kSlots, n_occ - r * kSlotsRound + 3);   // slots this round can touch
+    if (c_ok)
+      for (int sl = g; sl < n_used; sl += NR) sums[sl * p.CCp + c] = 0.f;
+    for (int e = tid; e < n_used; e += kThreads) cnt[e] = 0;
+    __syncthreads();
+    if (n_occ > 0)
+    for (int base = lo; base < hi; base += kListCap) {
+      // ---- ordered compaction of the keys in [base, base+kListCap) that belong to round r
+      const int i0 = base + 4 * tid;
+      int sl[4];
+      int m = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sl[j] = -1;
+        if (i0 + j < hi) {
+          const int k = __ldg(p.keys + i0 + j);
+          if (k >= klo && k < khi) {
+            const int v = k - klo, grp = v >> 2, bs = base_s[grp];
+            if (bs / kSlotsRound == r) {
+              const unsigned nb = (occ[grp >> 3] >> ((grp & 7) * 4)) & 0xFu;
+              sl[j] = bs - r * kSlotsRound + __popc(nb & ((1u << (v & 3)) - 1u));
+              ++m;
+            }
           }
         }
       }
+      int incl = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_warp[warp] = incl;
       __syncthreads();
+      int woff = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) woff += (w < warp) ? s_warp[w] : 0;
+      if (tid == kThreads - 1) s_total = woff + incl;
+      int pos = woff + incl - m;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (sl[j] >= 0) {
+          list_n[pos] = i0 + j;          // point id (N < 2^31 checked on host)
+          list_s[pos] = sl[j];
+          ++pos;
+        }
+      __syncthreads();
+      const int L = s_total;
+      // values of the listed points are staged through shared memory in batches of kStage rows
+      // (independent, coalesced loads), then added per slot in ascending point order
+      for (int l0 = 0; l0 < L; l0 += kStage) {
+        const int nl = min(kStage, L - l0);
+        if (c_ok)
+          for (int l = g; l < nl; l += NR)
+            stage[l * p.CCp + c] = __ldg(p.values + (long long)list_n[l0 + l] * p.C + c0 + c);
+        __syncthreads();
+        if (c_ok) {
+          // row group g owns the slots s % NR == g: a slot's points are added in list order
+          for (int l = 0; l < nl; ++l) {
+            const int s = list_s[l0 + l];
+            if ((s & (NR - 1)) == g) {
+              sums[s * p.CCp + c] = __fadd_rn(sums[s * p.CCp + c], stage[l * p.CCp + c]);
+              if (c == 0) cnt[s] += 1;
+            }
+          }
+        }
+        __syncthreads();
+      }
     }
-  }
-
-  // ---- write the tile: every output element exactly once, coalesced along v.
-  // thread <-> voxel (no integer division in the loop; the count is read once)
-  for (int v = tid; v < vt; v += kThreads) {
-    const int n = cnt[v];
-    const float fn = (float)n;
-    const float* row = tile + v * p.CCp;
-    float* o = out + v;
-    if (n > 0) {
-      for (int ch = 0; ch < cc; ++ch) __stcs(o + (long long)ch * p.V, __fdiv_rn(row[ch], fn));
+    // ---- averages in place
+    if (c_ok)
+      for (int sl = g; sl < n_used; sl += NR) {
+        const int n = cnt[sl];
+        if (n > 0) sums[sl * p.CCp + c] = __fdiv_rn(sums[sl * p.CCp + c], (float)n);
+      }
+    __syncthreads();
+    // ---- stream this segment's piece of every plane of the chunk: groups of round r only
+    bool mine[kGPT];
+    bool any_occ = false;
+#pragma unroll
+    for (int k = 0; k < kGPT; ++k) {
+      mine[k] = (gbase[k] / kSlotsRound == r) && (4 * (tid + kThreads * k) < vt);
+      any_occ |= mine[k] && nib[k] != 0u;
+    }
+    const long long plane0 = ((long long)b * p.C + c0) * p.V + vbase + 4 * tid;
+    if (p.vec4) {
+      float4* d = reinterpret_cast<float4*>(p.matrix + plane0);
+      const long long pstride = p.V >> 2;
+      if (!any_occ) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int ch = 0; ch < cc; ++ch, d += pstride) {
+#pragma unroll
+          for (int k = 0; k < kGPT; ++k)
+            if (mine[k]) __stcs(d + kThreads * k, z4);
+        }
+      } else {
+        for (int ch = 0; ch < cc; ++ch, d += pstride) {
+#pragma unroll
+          for (int k = 0; k < kGPT; ++k) {
+            if (!mine[k]) continue;
+            float vv[4] = {0.f, 0.f, 0.f, 0.f};
+            int s = gbase[k] - r * kSlotsRound;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((nib[k] >> q) & 1u) vv[q] = sums[(s++) * p.CCp + ch];
+            __stcs(d + kThreads * k, make_float4(vv[0], vv[1], vv[2], vv[3]));
+          }
+        }
+      }
+      if (chunk == 0) {
+#pragma unroll
+        for (int k = 0; k < kGPT; ++k) {
+          if (!mine[k]) continue;
+          int cv[4] = {0, 0, 0, 0};
+          int s = gbase[k] - r * kSlotsRound;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((nib[k] >> q) & 1u) cv[q] = cnt[s++];
+          *reinterpret_cast<int4*>(p.counts + (long long)b * p.V + vbase + 4 * (tid + kThreads * k)) =
+              make_int4(cv[0], cv[1], cv[2], cv[3]);
+        }
+      }
     } else {
-#pragma unroll 8
-      for (int ch = 0; ch < cc; ++ch) __stcs(o + (long long)ch * p.V, 0.f);
+      // ragged / unaligned planes: scalar stores, tail guarded
+#pragma unroll
+      for (int k = 0; k < kGPT; ++k) {
+        if (!mine[k]) continue;
+        int s = gbase[k] - r * kSlotsRound;
+        for (int q = 0; q < 4; ++q) {
+          const int v = 4 * (tid + kThreads * k) + q;
+          const bool occv = (nib[k] >> q) & 1u;
+          const int sl = occv ? s++ : -1;
+          if (v >= vt) continue;
+          float* dst = p.matrix + ((long long)b * p.C + c0) * p.V + vbase + v;
+          for (int ch = 0; ch < cc; ++ch)
+            dst[(long long)ch * p.V] = sl < 0 ? 0.f : sums[sl * p.CCp + ch];
+          if (chunk == 0) p.counts[(long long)b * p.V + vbase + v] = sl < 0 ? 0 : cnt[sl];
+        }
+      }
     }
-  }
-  if (chunk == 0) {
-    int* oc = p.counts + (long long)b * p.V + vbase;
-    for (int v = tid; v < vt; v += kThreads) oc[v] = cnt[v];
-  }
-  __syncthreads();                                           // shared tile is reused by the next item
+    __syncthreads();                                           // sums / cnt are reused by the next round
   }
 }
 
@@ -465,21 +434,22 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 using namespace mf;
 
-// workspace layout (T = voxel tiles of this call, W = B*V/32 bitmap words):
-//   region A, memset 0xFF : hdr[4] | seg_start[B] | seg_end[B]          (reserved: 4 + 2*65536 ints)
-//   region B, memset 0x00 : flags | tile_list_n | done | mode | tile_count[T] | occ_bits[W]
-//                                                           (reserved: 4 + 2^20 + 2^21 ints)
-//   tile_list[2^20] | keys[N]
-constexpr size_t kWsA = (4 + 2 * 65536) * sizeof(int);
-constexpr size_t kMaxTiles = 1 << 20;
-constexpr size_t kMaxBitWords = 1 << 21;                     // B*V <= 2^26 voxels
-constexpr size_t kWsListOff = kWsA + (4 + kMaxTiles + kMaxBitWords) * sizeof(int);
-constexpr size_t kWsKeysOff = kWsListOff + kMaxTiles * sizeof(int);
+// workspace layout (nothing in it needs initialising):
+//   [0]      int   flag word of the last call (mf_average_voxelization_3d_flags_offset)
+//   [256]    int   seg_start[65536] | seg_end[65536]
+//   [kWsCtaOff]    cta_flags[ceil(N/256)] | keys[N]
+constexpr size_t kWsSegOff = 256;
+constexpr size_t kWsCtaOff = kWsSegOff + 2 * 65536 * sizeof(int);
 
-extern "C" size_t mf_average_voxelization_3d_flags_offset(void) { return kWsA; }
+extern "C" size_t mf_average_voxelization_3d_flags_offset(void) { return 0; }
+
+static size_t avg_cta_bytes(int64_t n_points) {
+  return align_up((size_t)((n_points > 0 ? n_points : 1) + 255) / 256 * 4, 256);
+}
 
 extern "C" size_t mf_average_voxelization_3d_workspace_bytes(int64_t n_points) {
-  return kWsKeysOff + align_up((size_t)(n_points > 0 ? n_points : 1) * 4, 256);
+  return kWsCtaOff + avg_cta_bytes(n_points) +
+         align_up((size_t)(n_points > 0 ? n_points : 1) * 4, 256);
 }
 
 extern "C" int mf_average_voxelization_3d_fwd(
@@ -496,93 +466,46 @@ extern "C" int mf_average_voxelization_3d_fwd(
   if (B > 65535) return MF_E_TOOLARGE;
   if (workspace_bytes < mf_average_voxelization_3d_workspace_bytes(N)) return MF_E_WORKSPACE;
 
-  AvgParams p;
-  p.VT = 256;
-  if (V < 256) p.VT = (int)V;
-  p.tiles_per_batch = (int)((V + p.VT - 1) / p.VT);
-  if ((long long)p.tiles_per_batch * B > (1 << 20)) return MF_E_TOOLARGE;
-
-  int* hdr = (int*)workspace;
-  int* seg_start = hdr + 4;
-  int* seg_end = seg_start + B;
-  int* regB = (int*)((char*)workspace + kWsA);
-  int* flags2 = regB;            // internal copy of the flag word (workspace-resident)
-  int* tile_list_n = regB + 1;
-  int* done = regB + 2;
-  int* mode = regB + 3;
-  int* tile_count = regB + 4;
-  const long long n_tiles_ws = (long long)p.tiles_per_batch * B;
-  int* tile_list = (int*)((char*)workspace + kWsListOff);
-  int* keys = (int*)((char*)workspace + kWsKeysOff);
-  // hdr = all ones (sorted bit set), seg_* = -1 (empty); flags/counter/tile counts = 0
-  MF_CUDA_TRY(cudaMemsetAsync(hdr, 0xFF, (4 + 2 * (size_t)B) * sizeof(int), stream));
-  MF_CUDA_TRY(cudaMemsetAsync(regB, 0, (4 + (size_t)n_tiles_ws) * sizeof(int), stream));
+  char* ws = (char*)workspace;
+  int* flags_ws = (int*)ws;
+  int* seg_start = (int*)(ws + kWsSegOff);
+  int* seg_end = seg_start + 65536;
+  int* cta_flags = (int*)(ws + kWsCtaOff);
+  int* keys = (int*)(ws + kWsCtaOff + avg_cta_bytes(N));
   VoxGeom g{ox, oy, oz, pitch, X, Y, Z, B};
-  p.values = values; p.keys = keys; p.hdr = hdr; p.seg_start = seg_start; p.seg_end = seg_end;
+  const int n_key_ctas = (int)div_up(N, kThreads);
+  if (N > 0) {
+    k_avg_prepass<<<n_key_ctas, kThreads, 0, stream>>>(points, batch_indices, N, g, keys,
+                                                        seg_start, seg_end, cta_flags);
+    MF_LAUNCH_CHECK();
+  }
+  AvgParams p;
+  p.values = values; p.keys = keys; p.bi = batch_indices;
+  p.seg_start = seg_start; p.seg_end = seg_end; p.cta_flags = cta_flags;
+  p.n_key_ctas = N > 0 ? n_key_ctas : 0;
   p.N = N; p.C = C; p.B = B; p.V = (int)V;
-  int nChunks = (C + 63) / 64;
+  p.segs_per_batch = (int)((V + kVS - 1) / kVS);
+  // channels per CTA: enough CTAs to fill the GPU several times over (each streams CC x 16 KiB),
+  // at most 64 channels (shared-memory rows)
+  int nChunks = (int)((768 + (long long)B * p.segs_per_batch - 1) / ((long long)B * p.segs_per_batch));
+  if (nChunks > C) nChunks = C;
+  if (nChunks < (C + 63) / 64) nChunks = (C + 63) / 64;
   p.CC = (C + nChunks - 1) / nChunks;
   nChunks = (C + p.CC - 1) / p.CC;
   p.CCp = p.CC | 1;
-  p.G = kThreads / p.CC;
-  if (p.G < 1) p.G = 1;
-  if (p.G > 32) p.G = 32;
+  p.LWs = 2;
+  while ((1 << p.LWs) < p.CC) ++p.LWs;
+  p.vec4 = (V % 4 == 0) && (((uintptr_t)matrix & 15) == 0) && (((uintptr_t)counts & 15) == 0);
   p.matrix = matrix; p.counts = counts;
-  p.tile_count = tile_count; p.tile_list = tile_list; p.tile_list_n = tile_list_n;
-  p.n_chunks = nChunks;
-  const long long n_tiles = (long long)p.tiles_per_batch * B;
-  p.n_items = (int)n_tiles;
-  size_t smem = (size_t)p.VT * p.CCp * 4 + (size_t)p.VT * 4 + (size_t)kListCap * 8 +
-                (size_t)kStage * p.CCp * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MF_CUDA_TRY(cudaFuncSetAttribute(k_avg_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     100 * 1024));
-    attr_set = true;
-  }
-  p.mode = mode;
-  p.zero_groups = 0;
-  p.n_lead_ctas = 0;
-  const bool sparse_ok = (V * B <= (1LL << 26)) && (p.VT == 256) && (V % 4096 == 0) && C <= 256 &&
-                         N > 0;
-  if (sparse_ok) {
-    // 1. prepass + dense zero fill in one launch; 2. per-point leader scatter (fast mode);
-    // 3. occupied tiles through shared memory (general mode).  2 and 3 are mutually exclusive
-    // (device-side mode word) and overwrite only occupied voxels / tiles.
-    p.zero_groups = (int)(V / 4096);                           // 16 KiB segments per plane
-    const long long n_fill = (long long)B * (C + 1) * p.zero_groups;
-    const long long n_key = div_up(N, 256);
-    const long long n_lead = (N * 32 + 255) / 256;
-    if (n_fill + n_key >= (1LL << 31) || n_lead >= (1LL << 31)) return MF_E_TOOLARGE;
-    p.n_lead_ctas = (int)n_lead;
-    KeysArgs ka{points, batch_indices, g, keys, hdr, seg_start, seg_end, flags, tile_count,
-                flags2, tile_list, tile_list_n, done, mode, (int)n_key};
-    k_avg_keys_fill<<<(unsigned)(n_key + n_fill), 256, 0, stream>>>(p, ka);
-    MF_LAUNCH_CHECK();
-    k_avg_leaders<<<(unsigned)n_lead, 256, 0, stream>>>(p);
-    MF_LAUNCH_CHECK();
-    long long occ_max = n_tiles < N ? n_tiles : N;             // at most one new tile per point
-    if (occ_max > 592) occ_max = 592;                          // 4 x 148: grid-stride inside
-    if (occ_max > 0) {
-      dim3 grid((unsigned)occ_max, nChunks, 1);
-      k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
-      MF_LAUNCH_CHECK();
-    }
-  } else {
-    if (N > 0) {
-      k_vox_keys<<<div_up(N, 256), 256, 0, stream>>>(points, batch_indices, N, g, keys, hdr,
-                                                     seg_start, seg_end, flags, tile_count, p.VT,
-                                                     flags2, tile_list, tile_list_n, nullptr, done,
-                                                     mode);
-      MF_LAUNCH_CHECK();
-    }
-    // ragged shapes: every tile through the shared-memory path
-    p.tile_list = nullptr;
-    p.mode = nullptr;
-    dim3 grid((unsigned)n_tiles, nChunks, 1);
-    k_avg_tiles<<<grid, kThreads, smem, stream>>>(p);
-    MF_LAUNCH_CHECK();
-  }
+  p.flags_ws = flags_ws; p.flags_user = flags;
+  const long long n_cta = (long long)B * p.segs_per_batch;
+  if (n_cta >= (1LL << 31) || nChunks > 65535) return MF_E_TOOLARGE;
+  const size_t smem = (size_t)(kSlots + kStage) * p.CCp * 4 + (size_t)kListCap * 8 +
+                      (size_t)kSlots * 4 + (size_t)(kVS / 4) * 4 + (size_t)(kVS / 32) * 4;
+  MF_ENSURE_DYN_SMEM(k_avg_fused, 112 * 1024);
+  dim3 grid((unsigned)n_cta, (unsigned)nChunks, 1);
+  k_avg_fused<<<grid, kThreads, smem, stream>>>(p);
+  MF_LAUNCH_CHECK();
   return MF_OK;
 }
 

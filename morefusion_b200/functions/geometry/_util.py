@@ -12,18 +12,56 @@ def expect(cond, msg):
         raise InvalidType(msg)
 
 
-def as_f32(x, device=None, name="array"):
-    """Accept torch tensors (kept on their device) and numpy / python data (moved to the
-    current CUDA device): the reference accepts numpy, cupy and Variables alike."""
+def as_tensor(x, device=None):
+    """torch tensors are kept as they are; numpy / python data moves to the CUDA device with
+    its own dtype.  For the operators whose reference has a ``check_type_forward`` (the dtype is
+    then validated, not converted: voxelization_3d.py:18-32, interpolate_voxel_grid.py:117-130)."""
     if isinstance(x, torch.Tensor):
         return x
     return torch.as_tensor(np.asarray(x), device=device or "cuda")
 
 
+def as_f32(x, device=None, name="array"):
+    """float32 CUDA view of `x` for the operators the reference runs in whatever float dtype it
+    is given (no type check there: compose_transform, translation_matrix, transform_points,
+    truncated_distance_function, pseudo_occupancy_voxelization, average_distance): float64 /
+    float16 tensors and numpy / python data are converted -- the kernels read float32."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype == torch.float32:
+            return x
+        if not x.is_floating_point():
+            raise InvalidType(f"{name}.dtype.kind == 'f'")
+        return x.to(torch.float32)
+    a = np.asarray(x)
+    if a.dtype.kind not in "fiub":
+        raise InvalidType(f"{name}.dtype.kind == 'f'")
+    return torch.as_tensor(a.astype(np.float32), device=device or "cuda")
+
+
+# Scalars / origins given as CUDA tensors have to reach the host once (the C ABI takes them by
+# value).  The value is cached per (storage, version): calling an operator in a loop with the
+# same pitch / origin tensor -- the ROS node pattern -- costs one device->host read in total, not
+# one per call; an in-place update of the tensor bumps its version and refreshes the entry.
+_HOST_CACHE = {}
+
+
+def _host_values(t):
+    if not t.is_cuda:
+        return t.detach().numpy()
+    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+    v = _HOST_CACHE.get(key)
+    if v is None:
+        if len(_HOST_CACHE) > 256:
+            _HOST_CACHE.clear()
+        v = t.detach().cpu().numpy()
+        _HOST_CACHE[key] = v
+    return v
+
+
 def origin3(origin):
     """origin -> three python floats rounded to float32, as cupy.asarray(origin, float32)."""
     if isinstance(origin, torch.Tensor):
-        origin = origin.detach().cpu().numpy()
+        origin = _host_values(origin)
     o = np.asarray(origin, dtype=np.float32).reshape(-1)
     if o.shape != (3,):
         raise ValueError("origin must have 3 elements")
@@ -32,7 +70,7 @@ def origin3(origin):
 
 def scalar32(x):
     if isinstance(x, torch.Tensor):
-        x = x.detach().cpu().item()
+        x = _host_values(x).reshape(-1)[0]
     return float(np.float32(x))
 
 

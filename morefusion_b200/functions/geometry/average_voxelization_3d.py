@@ -62,9 +62,9 @@ def average_voxelization_3d(
     return_counts=False,
 ):
     _util.check_dimensions(dimensions)
-    values = _util.as_f32(values)
-    points = _util.as_f32(points, values.device)
-    batch_indices = _util.as_f32(batch_indices, values.device)
+    values = _util.as_tensor(values)
+    points = _util.as_tensor(points, values.device)
+    batch_indices = _util.as_tensor(batch_indices, values.device)
     _util.check_voxelization_types(values, points, batch_indices)
     voxel, counts = AverageVoxelization3D.apply(
         values, points, batch_indices, batch_size, _util.origin3(origin),

@@ -49,9 +49,9 @@ class InterpolateVoxelGrid(torch.autograd.Function):
 
 
 def interpolate_voxel_grid(voxelized, points, batch_indices):
-    voxelized = _util.as_f32(voxelized)
-    points = _util.as_f32(points, voxelized.device)
-    batch_indices = _util.as_f32(batch_indices, voxelized.device)
+    voxelized = _util.as_tensor(voxelized)
+    points = _util.as_tensor(points, voxelized.device)
+    batch_indices = _util.as_tensor(batch_indices, voxelized.device)
     # interpolate_voxel_grid.py:117-130
     _util.expect(voxelized.dtype == torch.float32, "voxelized.dtype == float32")
     _util.expect(voxelized.dim() == 5, "voxelized.ndim == 5")

@@ -57,10 +57,10 @@ def max_voxelization_3d(
     return_indices=False,
 ):
     _util.check_dimensions(dimensions)
-    values = _util.as_f32(values)
-    points = _util.as_f32(points, values.device)
-    batch_indices = _util.as_f32(batch_indices, values.device)
-    intensities = _util.as_f32(intensities, values.device)
+    values = _util.as_tensor(values)
+    points = _util.as_tensor(points, values.device)
+    batch_indices = _util.as_tensor(batch_indices, values.device)
+    intensities = _util.as_tensor(intensities, values.device)
     _util.check_voxelization_types(values, points, batch_indices)
     voxelized, indices = MaxVoxelization3D.apply(
         values, points, batch_indices, intensities, batch_size, _util.origin3(origin),

@@ -44,7 +44,7 @@ class OccupancyGrid3D(torch.autograd.Function):
 
 
 def occupancy_grid_3d(points, *, pitch, origin, dims, threshold=1):
-    points = _util.as_f32(points)
+    points = _util.as_tensor(points)
     # occupancy_grid_3d.py:8-29
     pitch_a = np.asarray(_util.scalar32(pitch), dtype=np.float32)
     assert pitch_a.ndim == 0

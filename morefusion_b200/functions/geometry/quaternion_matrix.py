@@ -37,7 +37,7 @@ class QuaternionMatrix(torch.autograd.Function):
 
 
 def quaternion_matrix(quaternion):
-    quaternion = _util.as_f32(quaternion)
+    quaternion = _util.as_tensor(quaternion)
     squeeze_axis0 = False
     if quaternion.dim() == 1:
         squeeze_axis0 = True

@@ -27,33 +27,11 @@ VOXEL_DIM = 32
 
 
 def init_weights(n_fg_class=21, seed=0, with_occupancy=True):
-    """Seeded LeCun-normal weights (chainer's default initialiser) and small random biases,
-    keyed by the reference's link names (model.py:62-91)."""
-    rs = np.random.RandomState(seed)
-    w = {}
-
-    def conv(name, cout, cin, *k):
-        fan_in = cin * int(np.prod(k)) if k else cin
-        shape = (cout, cin) + tuple(k)
-        w[name + "/W"] = (rs.normal(0, 1.0 / np.sqrt(fan_in), shape)).astype(np.float32)
-        w[name + "/b"] = rs.uniform(-0.05, 0.05, cout).astype(np.float32)
-
-    conv("conv1_rgb", 64, 32, 1)
-    conv("conv1_pcd", 8, 3, 1)
-    conv("conv2_rgb", 128, 64, 1)
-    conv("conv2_pcd", 16, 8, 1)
-    if with_occupancy:
-        conv("conv1_occ", 8, 1, 3, 3, 3)
-        conv("conv2_occ", 16, 8, 3, 3, 3)
-    cin3 = 144 + (16 if with_occupancy else 0)
-    conv("conv3", 256, cin3, 4, 4, 4)
-    conv("conv4", 512, 256, 4, 4, 4)
-    for head, cout in (("rot", n_fg_class * 4), ("trans", n_fg_class * 3), ("conf", n_fg_class)):
-        conv(f"conv1_{head}", 640, 984, 1)
-        conv(f"conv2_{head}", 256, 640, 1)
-        conv(f"conv3_{head}", 128, 256, 1)
-        conv(f"conv4_{head}", cout, 128, 1)
-    return w
+    """Seeded LeCun-normal weights keyed by the reference's link names (model.py:62-91); the
+    generator lives with the other synthetic-data helpers so that the product bench does not
+    need this package."""
+    from morefusion_b200.synthetic import init_weights as gen
+    return gen(n_fg_class, seed, with_occupancy)
 
 
 def _r(x, bf16):

@@ -50,6 +50,8 @@ def test_average_voxelization_golden(cuda_device, case):
     dict(P=3000, C=70, B=3, D=(7, 9, 11), sorted=False),  # non-cubic, V % 4 != 0, 2 chunks
     dict(P=0, C=3, B=2, D=8, sorted=True),          # empty input
     dict(P=20000, C=3, B=1, D=4, sorted=True),      # heavy collisions: ~300 points per voxel
+    dict(P=60000, C=5, B=2, D=16, sorted=True),     # > 125 occupied voxels per segment (slot rounds), > 1024 keys per scan
+    dict(P=40000, C=65, B=3, D=16, sorted=False),   # the same unsorted, 2 channel chunks
 ])
 def test_average_voxelization_vs_oracle(cuda_device, shape):
     rs = np.random.RandomState(0)
@@ -76,6 +78,35 @@ def test_average_voxelization_vs_oracle(cuda_device, shape):
         want = vo.average_voxelization_3d_bwd(gy, c, pts, bi, origin=origin, pitch=pitch,
                                               dimensions=dims)
         assert np.array_equal(v.grad.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_average_voxelization_oob_points_at_batch_boundaries(cuda_device, seed):
+    """sorted batches whose boundary points are out of the grid, segment
+    lengths not multiples of 8, on a workspace full of garbage (nothing in it may need
+    initialising).  Seeds 1, 2 and 4 broke the round-1 leader kernel."""
+    from morefusion_b200.functions.geometry import _util
+    rs = np.random.RandomState(seed)
+    P, C, B, D = 8000, 6, 8, 32
+    pts = rs.uniform(-1.3, 1.3, (P, 3)).astype(F32)
+    vals = rs.uniform(-1, 1, (P, C)).astype(F32)
+    bi = np.sort(rs.randint(0, B, P)).astype(np.int32)
+    if seed % 2:
+        bi[bi == 3] = 4                               # an absent batch in the middle
+    edges = np.flatnonzero(np.diff(bi)) + 1
+    for e in edges:                                   # out-of-grid points either side of a boundary
+        pts[max(e - rs.randint(1, 6), 0):e + rs.randint(1, 6)] = 5.0
+    origin = np.array([-1, -1, -1], F32)
+    pitch = F32(2.0 / D)
+    m, c = vo.average_voxelization_3d_fwd(vals, pts, bi, batch_size=B, origin=origin, pitch=pitch,
+                                          dimensions=(D, D, D))
+    ws = _util.workspace(1 << 20, cuda_device)
+    ws.view(torch.int32).fill_(int(rs.randint(-2 ** 31, 2 ** 31 - 1)))   # dirty workspace
+    y, counts = F().average_voxelization_3d(
+        cu(vals, cuda_device), cu(pts, cuda_device), cu(bi, cuda_device), batch_size=B,
+        origin=origin, pitch=pitch, dimensions=(D, D, D), return_counts=True)
+    assert np.array_equal(counts.cpu().numpy(), c)
+    assert np.array_equal(y.cpu().numpy(), m)
 
 
 def test_average_voxelization_properties_full_size(cuda_device):

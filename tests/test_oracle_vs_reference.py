@@ -20,7 +20,10 @@ def test_goldens_regenerate_bit_identically(tmp_path, monkeypatch):
     committed = gg.OUT
     monkeypatch.setattr(gg, "OUT", str(tmp_path))
     gg.main()
-    names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
+    # icc_closed_loop_* are ORACLE trajectories (oracle/ref_harness/gen_icc_closed_loop.py, minutes
+    # of NumPy each); their reference-derived inputs are checked below
+    names = sorted(f for f in os.listdir(committed)
+                   if f.endswith(".npz") and not f.startswith("icc_closed_loop_"))
     assert names == sorted(os.listdir(tmp_path)), "generator and committed fixture sets differ"
     for f in names:
         a, b = np.load(tmp_path / f, allow_pickle=True), np.load(os.path.join(committed, f),
@@ -31,3 +34,19 @@ def test_goldens_regenerate_bit_identically(tmp_path, monkeypatch):
                 assert np.array_equal(a[k], b[k], equal_nan=True), (f, k)
             else:
                 assert np.array_equal(a[k], b[k]), (f, k)
+
+
+def test_icc_ref3_fixture_inputs_come_from_the_reference():
+    """tests/golden/icc_closed_loop_ref3.npz carries the reference's committed 3-object scene
+    (examples/ycb_video/pose_refinement/data/0000000{0,1,2}.npz) verbatim."""
+    from oracle.ref_harness import gen_icc_closed_loop as gen
+    g = np.load(os.path.join(gen.OUT, "icc_closed_loop_ref3.npz"))
+    sc = gen.ref3_scene()
+    assert gen.inputs_checksum(sc) == str(g["inputs_sha1"])
+    for i in range(3):
+        d = np.load(os.path.join(gen.REF_DATA, f"{i:08d}.npz"))
+        assert np.array_equal(g["transform_init"][i], d["transform_init"])
+        assert np.array_equal(g["grid_target"][i], d["grid_target"])
+        assert np.array_equal(g["grid_nontarget_empty"][i], d["grid_nontarget_empty"])
+        assert np.array_equal(g["origin"][i], d["origin"])
+        assert g["pitch"][i] == np.float32(d["pitch"])
