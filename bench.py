@@ -233,7 +233,7 @@ def bench_avg_vox(dev, pk, flush):
         byts = 4 * (B * Pn * C + 4 * B * Pn) + 4 * (B * C * D ** 3 + B * D ** 3)
         out[tag] = dict(us=us, min_us=mn, algorithmic_bytes=byts, achieved_gbs=byts / us / 1e3,
                         frac_of_hbm_peak=byts / us / 1e3 / pk["hbm"])
-    out.update(bound="hbm", peak_gbs=pk["hbm"], kernels="k_avg_prepass + k_avg_fused",
+    out.update(bound="hbm", peak_gbs=pk["hbm"], kernels="k_avg_prepass + k_avg_fused (gather + single-pass fill)",
                timed="CUDA-graph replay of the public operator, 192 MiB L2 flush between replays, median of 20")
     return out
 

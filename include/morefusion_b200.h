@@ -50,8 +50,9 @@ int mf_device_sm_count(int device);
  *     replaces AverageVoxelization3D.forward_gpu / backward_gpu
  *     (morefusion/functions/geometry/average_voxelization_3d.py:43-118, :147-220)
  * values [N,C] points [N,3] batch_indices [N] -> matrix [B,C,X,Y,Z], counts [B,X,Y,Z]
- * One pass: every output voxel is written exactly once (no memset, no atomics
- * on HBM); per-voxel sums are taken in ascending point order (deterministic).
+ * Two launches (keys; gather + fill): every output voxel is written exactly once (no
+ * memset, no atomics on HBM, nothing in `workspace` needs initialising); per-voxel sums
+ * are taken in ascending point order (deterministic).
  * ------------------------------------------------------------------------ */
 size_t mf_average_voxelization_3d_workspace_bytes(int64_t n_points);
 /* byte offset inside `workspace` of an int32 copy of the MF_FLAG_* word of the last call (so a
@@ -64,6 +65,9 @@ int mf_average_voxelization_3d_fwd(
     int X, int Y, int Z,
     float* matrix, int32_t* counts,
     void* workspace, size_t workspace_bytes, int32_t* flags, void* stream);
+/* diagnostics: writes B*planes*V zero floats with one of five store patterns (see
+ * csrc/voxelization.cu, scripts/fill_patterns.py) */
+int mf_debug_fill_probe(float* out, int batch_size, int planes, int64_t V, int mode, void* stream);
 int mf_average_voxelization_3d_bwd(
     const float* gmatrix, const int32_t* counts,
     const float* points, const int32_t* batch_indices,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "mf_average_voxelization_3d_workspace_bytes": (c_sz, [c_i64]),
     "mf_average_voxelization_3d_flags_offset": (c_sz, []),
     "mf_average_voxelization_3d_fwd": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_i] + _geom + [c_p, c_p, c_p, c_sz, c_p, c_p]),
+    "mf_debug_fill_probe": (c_i, [c_p, c_i, c_i, c_i64, c_i, c_p]),
     "mf_average_voxelization_3d_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i] + _geom + [c_p, c_p]),
     "mf_max_voxelization_3d_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "mf_max_voxelization_3d_fwd": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i] + _geom + [c_p, c_p, c_p, c_sz, c_p, c_p]),

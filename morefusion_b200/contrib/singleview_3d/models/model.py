@@ -1,9 +1,15 @@
 """singleview_3d pose model: the 3D-CNN section on hand-written sm_100a kernels.
 
-Mirrors morefusion/contrib/singleview_3d/models/model.py (class Model :11-481):
-same constructor keywords (:19-27), the same link names for every layer (:62-91) so a
-reference snapshot maps 1:1 onto ``state_dict`` keys, ``_extract`` (:93-141) and the
-heads / pose assembly of ``predict`` (:239-273).
+Mirrors morefusion/contrib/singleview_3d/models/model.py (class Model :11-481): same constructor
+keywords (:19-27), the same link names for every layer (:62-91) so a reference snapshot maps 1:1
+onto ``state_dict`` keys, and the same public methods:
+  * ``predict(class_id, rgb, pcd, pitch, origin, grid_nontarget_empty)`` (:166-275): NaN mask,
+    2-D extractor (torch / cuDNN: the adjacent row SURVEY.md 8f-1), per-object 1000-point
+    sampling with the reference's RandomState(1234) permutation, default pitch / origin,
+    voxel-frame transform, then ``forward_features`` -- the hot path proper: everything after
+    the 2-D extractor on this library's kernels;
+  * ``evaluate`` (:325-375), ``loss`` (:377-481, without the "+occupancy" terms the reference
+    itself calls with a stale signature) and ``__call__`` (:277-323).
 
 Internal layout is B200-first, not a translation: activations are channels-last bf16 in
 persistent buffers, the two k4/s2 Conv3Ds and all Conv1D heads are GEMMs on one kernel
@@ -94,6 +100,14 @@ class Model(torch.nn.Module):
             setattr(self, f"conv2_{head}", nn.Conv1d(640, 256, 1))
             setattr(self, f"conv3_{head}", nn.Conv1d(256, 128, 1))
             setattr(self, f"conv4_{head}", nn.Conv1d(128, cout, 1))
+        # 2-D feature extractor (model.py:42-60) and the CAD model source (:29)
+        from ....models import ResNet18Extractor
+        from ....models.dense_fusion import PSPNetExtractor
+        from .... import synthetic
+        self.resnet_extractor = ResNet18Extractor()
+        self.pspnet_extractor = PSPNetExtractor()
+        self._models = synthetic.SyntheticYCBModels()
+        self.reported = {}
         self._packed = None
         self._packed_ver = None
         self._wbufs = {}
@@ -233,6 +247,167 @@ class Model(torch.nn.Module):
                 _lib.check(rc, "gemm_bf16_tc_grouped")
         _lib.check(L.mf_gemm_bf16_simt_grouped(arr, n, _lib.stream()), "gemm_bf16_simt_grouped")
         self.n_launches += 1
+
+    # ------------------------------------------------------------------ reference API
+    def _keep_indices(self, n_point):
+        """model.py:206-219: which of the n valid pixels feed the network."""
+        n_point = int(n_point)
+        if n_point <= 0:
+            raise ValueError("an object has no valid (non-NaN) point")
+        rs = np.random.mtrand._rand if self.training else np.random.RandomState(1234)
+        if n_point >= self._n_point:
+            return rs.permutation(n_point)[:self._n_point]
+        return np.r_[np.arange(n_point), rs.randint(0, n_point, self._n_point - n_point)]
+
+    def predict(self, *, class_id, rgb, pcd, pitch=None, origin=None, grid_nontarget_empty=None):
+        """rgb [B,H,W,3] uint8, pcd [B,H,W,3] f32 with NaN at invalid pixels, class_id [B],
+        pitch [B] / origin [B,3] (entries or the whole argument may be None -> YCB voxel pitch,
+        median of the object's points - 15.5 pitch), grid_nontarget_empty [B,32,32,32].
+        Returns rot [B,P,4], trans [B,P,3], conf [B,P] (model.py:166-275).
+
+        One device->host read per call (the valid-pixel counts of the batch, which size the
+        reference's host-side permutation); the reference syncs several times per object."""
+        dev = self.conv3.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("Model runs on CUDA only (no CPU fallback); call .cuda() first")
+        f32 = torch.float32
+        rgb = torch.as_tensor(rgb, device=dev)
+        pcd = torch.as_tensor(pcd, device=dev).to(f32)
+        B, H, W, _ = rgb.shape
+        P = self._n_point
+        class_id_h = None if isinstance(class_id, torch.Tensor) and class_id.is_cuda \
+            else np.asarray(class_id).reshape(B)
+        if class_id_h is not None and ((class_id_h < 1) | (class_id_h > self._n_fg_class)).any():
+            raise IndexError("class_id out of range for n_fg_class")     # fancy index at :266-269
+        mask = ~torch.isnan(pcd).any(dim=3)                              # [B,H,W]   (:178)
+        h_rgb = self.pspnet_extractor(self.resnet_extractor(rgb.permute(0, 3, 1, 2).to(f32)))
+        flat_mask = mask.flatten(1)
+        n_point = flat_mask.sum(1).cpu().numpy()                         # the one host read
+        keep = torch.as_tensor(np.stack([self._keep_indices(n) for n in n_point]), device=dev)
+        cums = flat_mask.to(torch.int64).cumsum(1)
+        pix = torch.searchsorted(cums, keep + 1)                         # k-th valid pixel, row-major
+        pcd_f = pcd.permute(0, 3, 1, 2).flatten(2)                       # [B,3,HW]
+        points = pcd_f.gather(2, pix[:, None, :].expand(B, 3, P))
+        values = h_rgb.flatten(2).gather(2, pix[:, None, :].expand(B, h_rgb.shape[1], P))
+        # defaults (:197-205)
+        pitch_l = [None] * B if pitch is None else list(pitch)
+        if any(p is None for p in pitch_l):
+            if class_id_h is None:
+                class_id_h = class_id.cpu().numpy()
+            pitch_l = [self._models.get_voxel_pitch(self._voxel_dim, class_id_h[i])
+                       if pitch_l[i] is None else float(pitch_l[i]) for i in range(B)]
+            pitch_t = torch.tensor(pitch_l, dtype=f32, device=dev)
+        else:
+            pitch_t = torch.as_tensor(pitch, device=dev).to(f32).reshape(B)
+        origin_l = [None] * B if origin is None else list(origin)
+        if any(o is None for o in origin_l):
+            # extra/_cupy.py:47-62 median over the object's valid points, per axis
+            srt = torch.where(flat_mask[:, None, :], pcd_f, torch.full_like(pcd_f, float("inf")))
+            srt = srt.sort(dim=2).values
+            n = torch.as_tensor(n_point, device=dev)
+            hi = srt.gather(2, (n // 2)[:, None, None].expand(B, 3, 1))[:, :, 0]
+            lo = srt.gather(2, ((n - 1) // 2)[:, None, None].expand(B, 3, 1))[:, :, 0]
+            center = torch.where((n % 2 == 1)[:, None], hi, (hi + lo) / 2)
+            auto = center - pitch_t[:, None] * (self._voxel_dim / 2.0 - 0.5)
+            given = torch.stack([auto[i] if origin_l[i] is None
+                                 else torch.as_tensor(origin_l[i], device=dev).to(f32)
+                                 for i in range(B)])
+            origin_t = given
+        else:
+            origin_t = torch.as_tensor(origin, device=dev).to(f32).reshape(B, 3)
+        points = (points - origin_t[:, :, None]) / pitch_t[:, None, None]      # (:236)
+        return self._features(class_id=class_id, values=values, points=points, pitch=pitch_t,
+                              origin=origin_t, grid_nontarget_empty=grid_nontarget_empty)
+
+    def _features(self, **kw):
+        """forward_features with autograd when gradients are enabled (training)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from . import training
+            return training.forward_features_with_grad(self, **kw)
+        return self.forward_features(**kw)
+
+    def evaluate(self, *, class_id, quaternion_true, translation_true, quaternion_pred,
+                 translation_pred):
+        """ADD / ADD-S of the predicted poses (model.py:325-375); the summary chainer would
+        ``report`` is kept in ``self.reported`` and returned."""
+        from .... import functions, metrics
+        dev = self.conv3.weight.device
+        t = lambda x: torch.as_tensor(x, device=dev).detach().to(torch.float32)   # noqa: E731
+        T_true = functions.transformation_matrix(t(quaternion_true), t(translation_true))
+        T_pred = functions.transformation_matrix(t(quaternion_pred), t(translation_pred))
+        cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
+        B = cid.shape[0]
+        adds, add_ss = metrics.average_distance(
+            [self._models.get_pcd(class_id=int(c)) for c in cid],
+            [T_true[i] for i in range(B)], [T_pred[i] for i in range(B)])
+        sym = np.isin(cid, self._models.class_ids_symmetric)
+        add_or = np.where(sym, add_ss, adds)
+        if self.training:
+            summary = {"add": float(adds.mean()), "add_s": float(add_ss.mean()),
+                       "add_or_add_s": float(add_or.mean())}
+        else:
+            summary = {}
+            for i in range(B):
+                key = f"{int(cid[i]):04d}/{i}"
+                summary[f"add/{key}"] = float(adds[i])
+                summary[f"add_s/{key}"] = float(add_ss[i])
+                summary[f"add_or_add_s/{key}"] = float(add_or[i])
+        self.reported.update(summary)
+        return summary
+
+    def loss(self, class_id, quaternion_true, translation_true, quaternion_pred,
+             translation_pred, confidence_pred, pitch=None, origin=None, grid_target=None,
+             grid_nontarget_empty=None):
+        """Confidence-weighted ADD / ADD-S loss (model.py:377-441, :475-481)."""
+        from .... import functions
+        if self._loss in ("add+occupancy", "add/add_s+occupancy"):
+            raise NotImplementedError(
+                "the '+occupancy' loss terms call pseudo_occupancy_voxelization with a stale "
+                "signature in the reference (model.py:454-459) and cannot run there either")
+        dev = quaternion_pred.device
+        t = lambda x: torch.as_tensor(x, device=dev).to(torch.float32)   # noqa: E731
+        quaternion_true, translation_true = t(quaternion_true), t(translation_true)
+        cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
+        B = cid.shape[0]
+        loss = 0
+        for i in range(B):
+            T_pred = functions.transformation_matrix(quaternion_pred[i], translation_pred[i])
+            T_true = functions.transformation_matrix(quaternion_true[i], translation_true[i])
+            cad = self._models.get_pcd(class_id=int(cid[i]))
+            cad = cad[np.random.permutation(cad.shape[0])[:500]]
+            cad = torch.as_tensor(np.ascontiguousarray(cad, dtype=np.float32), device=dev)
+            sym = int(cid[i]) in self._models.class_ids_symmetric
+            if self._loss == "add":
+                sym = False
+            elif self._loss == "add_s":
+                sym = True
+            add = functions.average_distance(cad, T_true, T_pred, symmetric=sym)
+            conf = confidence_pred[i]
+            keep = conf.detach() > 0
+            loss = loss + torch.mean(add[keep] * conf[keep]
+                                     - self._lambda_confidence * torch.log(conf[keep]))
+        loss = loss / B
+        self.reported["loss"] = float(loss.detach())
+        return loss
+
+    def forward(self, *, class_id, rgb, pcd, quaternion_true, translation_true, pitch=None,
+                origin=None, grid_target=None, grid_nontarget_empty=None):
+        """Training call (model.py:277-323): predict -> evaluate (argmax-confidence pose) -> loss."""
+        rot, trans, conf = self.predict(class_id=class_id, rgb=rgb, pcd=pcd, pitch=pitch,
+                                        origin=origin, grid_nontarget_empty=grid_nontarget_empty)
+        B = rot.shape[0]
+        idx = conf.detach().argmax(dim=1)
+        ar = torch.arange(B, device=rot.device)
+        with torch.no_grad():
+            self.evaluate(class_id=class_id, quaternion_true=quaternion_true,
+                          translation_true=translation_true,
+                          quaternion_pred=rot.detach()[ar, idx],
+                          translation_pred=trans.detach()[ar, idx])
+        return self.loss(class_id=class_id, quaternion_true=quaternion_true,
+                         translation_true=translation_true, quaternion_pred=rot,
+                         translation_pred=trans, confidence_pred=conf, pitch=pitch,
+                         origin=origin, grid_target=grid_target,
+                         grid_nontarget_empty=grid_nontarget_empty)
 
     def forward_features(self, *, class_id, values, points, pitch, origin,
                          grid_nontarget_empty=None):

@@ -19,12 +19,12 @@
 namespace mf {
 
 constexpr int kThreads = 256;
-constexpr int kListCap = 1024;           // keys scanned per round = 4 per thread
-constexpr int kStage = 64;               // list entries whose values are staged in smem at once
-constexpr int kGPT = 4;                  // 4-voxel groups per thread
-constexpr int kVS = kThreads * kGPT * 4; // voxels per CTA segment: 16 KiB of every plane
-constexpr int kSlots = 256;              // occupied voxels whose sums are resident per round
+constexpr int kListCap = 512;            // keys scanned per round = 2 per thread
+constexpr int kStage = 32;               // list entries whose values are staged in smem at once
+constexpr int kVS = 1024;                // voxels per CTA segment: one float4 per thread and plane
+constexpr int kSlots = 64;               // occupied voxels whose sums are resident per round
 constexpr int kSlotsRound = kSlots - 3;  // a 4-voxel group never straddles two rounds
+constexpr int kMaxCC = 48;               // channel planes per CTA
 
 struct VoxGeom {
   float ox, oy, oz, pitch;
@@ -96,19 +96,26 @@ struct AvgParams {
   int* flags_user;   // caller's flag word (OR-ed into), may be null
 };
 
-// A CTA owns (batch b, kVS = 4096 consecutive voxels, CC channels): 16 KiB of each of its planes.
-// Thread t owns the 4-voxel groups t, t+256, t+512, t+768 of the segment, i.e. per plane four
-// float4 stores that, over the CTA, cover four consecutive 4 KiB blocks.
-__global__ void __launch_bounds__(kThreads)
+// A CTA owns (batch b, kVS = 1024 consecutive voxels, CC <= 48 channels).
+//   gather  find the points of b that fall into its voxels (ordered compaction of the keys), sum
+//           them per occupied voxel in ascending point order in shared memory, divide.  A handful
+//           of dependent L2 round trips; every load batch is issued before its first use, and the
+//           kernel is sized so that all CTAs are resident at once: the gathers of the whole grid
+//           run while the memory system is still idle (the same loads take microseconds each
+//           once 150 MB of stores are in flight).
+//   stream  4 KiB of every channel plane of the chunk: one 16-byte store per thread and plane,
+//           zeros straight from registers, occupied voxels patched in from shared memory.
+// Every output element is written exactly once.
+__global__ void __launch_bounds__(kThreads, 6)
 k_avg_fused(AvgParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sums = reinterpret_cast<float*>(smem_raw);                 // [kSlots][CCp]
-  float* stage = sums + (size_t)kSlots * p.CCp;                     // [kStage][CCp]
+  float* sums = reinterpret_cast<float*>(smem_raw);                 // [kSlots + 1][CCp], last = zeros
+  float* stage = sums + (size_t)(kSlots + 1) * p.CCp;               // [kStage][CCp]
   int* list_n = reinterpret_cast<int*>(stage + (size_t)kStage * p.CCp);  // [kListCap] point id
   int* list_s = list_n + kListCap;                                  // [kListCap] slot
-  int* cnt = list_s + kListCap;                                     // [kSlots]
-  int* base_s = cnt + kSlots;                                       // [kVS/4] first slot of a group
-  unsigned* occ = reinterpret_cast<unsigned*>(base_s + kVS / 4);    // [kVS/32] occupancy bits
+  int* cnt = list_s + kListCap;                                     // [kSlots + 1], last = 0
+  int* base_s = cnt + kSlots + 1;                                   // [kThreads] first slot of a group
+  unsigned* occ = reinterpret_cast<unsigned*>(base_s + kThreads);   // [kVS/32] occupancy bits
   __shared__ int s_warp[kThreads / 32];
   __shared__ int s_total, s_lo, s_hi;
 
@@ -120,9 +127,21 @@ k_avg_fused(AvgParams p) {
   const int c0 = chunk * p.CC;
   const int cc = min(p.CC, p.C - c0);
 
-  // ---- flag word of the call (per-CTA words of the prepass, OR-ed)
+  // ---- flag word of the call (per-CTA words of the prepass, OR-ed) and, in the same round
+  // trip, the candidate run [seg_start, seg_end) of batch b with the entries that validate it
   int f = 0;
   for (int i = tid; i < p.n_key_ctas; i += kThreads) f |= __ldg(p.cta_flags + i);
+  int cand_s = 0, cand_e = 0;
+  bool okse = false;
+  if (tid == 0 && p.N > 0) {
+    const int s = p.seg_start[b], e = p.seg_end[b];
+    const bool s_in = s >= 0 && s < p.N, e_in = e > 0 && e <= p.N;
+    const int bs0 = s_in ? __ldg(p.bi + s) : -1, bs1 = (s_in && s > 0) ? __ldg(p.bi + s - 1) : -1;
+    const int be0 = e_in ? __ldg(p.bi + e - 1) : -1, be1 = (e_in && e < p.N) ? __ldg(p.bi + e) : -1;
+    okse = s_in && e_in && bs0 == b && (s == 0 || bs1 != b) && be0 == b && (e == p.N || be1 != b) && s < e;
+    cand_s = s;
+    cand_e = e;
+  }
   const int unsorted = __syncthreads_or(f & MF_FLAG_UNSORTED_BATCH);
   if (blockIdx.x == 0 && blockIdx.y == 0) {
     const int fn = __syncthreads_or(f & MF_FLAG_NAN_POINTS) ? MF_FLAG_NAN_POINTS : 0;
@@ -133,22 +152,19 @@ k_avg_fused(AvgParams p) {
       if (p.flags_user && all) atomicOr(p.flags_user, all);
     }
   }
-  // ---- the points of batch b: its run [lo, hi) when batch_indices are sorted, else all points
+  // the points of batch b: its run when batch_indices are sorted, else all points
   if (tid == 0) {
     long long lo = 0, hi = p.N;
     if (!unsorted) {
       lo = hi = 0;
-      if (p.N > 0) {
-        const int s = p.seg_start[b], e = p.seg_end[b];
-        const bool oks = s >= 0 && s < p.N && __ldg(p.bi + s) == b && (s == 0 || __ldg(p.bi + s - 1) != b);
-        const bool oke = e > 0 && e <= p.N && __ldg(p.bi + e - 1) == b && (e == p.N || __ldg(p.bi + e) != b);
-        if (oks && oke && s < e) { lo = s; hi = e; }
-      }
+      if (okse) { lo = cand_s; hi = cand_e; }
     }
     s_lo = (int)lo;
     s_hi = (int)hi;
   }
   for (int i = tid; i < kVS / 32; i += kThreads) occ[i] = 0u;
+  for (int i = tid; i < p.CCp; i += kThreads) sums[kSlots * p.CCp + i] = 0.f;   // the zero row
+  if (tid == 0) cnt[kSlots] = 0;
   __syncthreads();
   const int lo = s_lo, hi = s_hi;
   const int klo = b * p.V + vbase, khi = klo + vt;
@@ -159,62 +175,51 @@ k_avg_fused(AvgParams p) {
     if (k >= klo && k < khi) atomicOr(&occ[(k - klo) >> 5], 1u << ((k - klo) & 31));
   }
   __syncthreads();
-  // slots are numbered in voxel order: exclusive scan of the per-group popcounts, group
-  // G = t + 256*k scanned k-major so that the numbering follows the voxel index
-  unsigned nib[kGPT];
-  int gbase[kGPT];
-  int n_occ = 0;                                              // occupied voxels of the segment
+  // thread t owns voxel group t (voxels 4t..4t+3): slots are numbered in voxel order
+  const unsigned nib = (occ[tid >> 3] >> ((tid & 7) * 4)) & 0xFu;
+  int my_base;
   {
-    int carry = 0;
+    const int m = __popc(nib);
+    int incl = m;
 #pragma unroll
-    for (int k = 0; k < kGPT; ++k) {
-      const int G = tid + kThreads * k;
-      nib[k] = (occ[G >> 3] >> ((G & 7) * 4)) & 0xFu;
-      const int m = __popc(nib[k]);
-      int incl = m;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      __syncthreads();                                        // s_warp reuse
-      if (lane == 31) s_warp[warp] = incl;
-      __syncthreads();
-      int woff = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) {
-        woff += (w < warp) ? s_warp[w] : 0;
-        tot += s_warp[w];
-      }
-      gbase[k] = carry + woff + incl - m;
-      base_s[G] = gbase[k];
-      carry += tot;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    n_occ = carry;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) woff += (w < warp) ? s_warp[w] : 0;
+    my_base = woff + incl - m;
+    base_s[tid] = my_base;
+    if (tid == kThreads - 1) s_total = woff + incl;
   }
   __syncthreads();
+  const int n_occ = s_total;
   // trailing empty groups carry base == n_occ: they need a round of their own when n_occ is a
   // multiple of kSlotsRound
   const int n_rounds = n_occ / kSlotsRound + 1;
+  const int my_round = my_base / kSlotsRound;
   // thread roles of the staging / accumulate / divide loops: NR rows x LW channel lanes
   const int LW = 1 << p.LWs, NR = kThreads >> p.LWs;
   const int g = tid >> p.LWs, c = tid & (LW - 1);
   const bool c_ok = c < cc;
 
   for (int r = 0; r < n_rounds; ++r) {
-    const int n_used = min(kSlots, n_occ - r * kSlotsRound + 3);   // slots this round can touch
+    const int n_used = min(kSlots, n_occ - r * kSlotsRound);   // slots this round can touch
     if (c_ok)
       for (int sl = g; sl < n_used; sl += NR) sums[sl * p.CCp + c] = 0.f;
     for (int e = tid; e < n_used; e += kThreads) cnt[e] = 0;
     __syncthreads();
-    if (n_occ > 0)
+    if (n_used > 0)
     for (int base = lo; base < hi; base += kListCap) {
       // ---- ordered compaction of the keys in [base, base+kListCap) that belong to round r
-      const int i0 = base + 4 * tid;
-      int sl[4];
+      const int i0 = base + 2 * tid;
+      int sl[2];
       int m = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         sl[j] = -1;
         if (i0 + j < hi) {
           const int k = __ldg(p.keys + i0 + j);
@@ -242,7 +247,7 @@ k_avg_fused(AvgParams p) {
       if (tid == kThreads - 1) s_total = woff + incl;
       int pos = woff + incl - m;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 2; ++j)
         if (sl[j] >= 0) {
           list_n[pos] = i0 + j;          // point id (N < 2^31 checked on host)
           list_s[pos] = sl[j];
@@ -250,13 +255,25 @@ k_avg_fused(AvgParams p) {
         }
       __syncthreads();
       const int L = s_total;
-      // values of the listed points are staged through shared memory in batches of kStage rows
-      // (independent, coalesced loads), then added per slot in ascending point order
+      // values of the listed points go through shared memory in batches of kStage rows; a thread
+      // issues all its loads of a batch before the first store (independent L2 round trips)
       for (int l0 = 0; l0 < L; l0 += kStage) {
         const int nl = min(kStage, L - l0);
-        if (c_ok)
-          for (int l = g; l < nl; l += NR)
-            stage[l * p.CCp + c] = __ldg(p.values + (long long)list_n[l0 + l] * p.C + c0 + c);
+        if (c_ok) {
+          float tmp[8];
+          for (int lb = g; lb < nl; lb += 8 * NR) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int l = lb + u * NR;
+              tmp[u] = l < nl ? __ldg(p.values + (long long)list_n[l0 + l] * p.C + c0 + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int l = lb + u * NR;
+              if (l < nl) stage[l * p.CCp + c] = tmp[u];
+            }
+          }
+        }
         __syncthreads();
         if (c_ok) {
           // row group g owns the slots s % NR == g: a slot's points are added in list order
@@ -278,68 +295,51 @@ k_avg_fused(AvgParams p) {
         if (n > 0) sums[sl * p.CCp + c] = __fdiv_rn(sums[sl * p.CCp + c], (float)n);
       }
     __syncthreads();
-    // ---- stream this segment's piece of every plane of the chunk: groups of round r only
-    bool mine[kGPT];
-    bool any_occ = false;
+    // ---- stream this segment's piece of every plane of the chunk: groups of round r only.
+    // One uniform loop: every lane reads its four voxels' values from shared memory -- empty
+    // voxels point at an all-zero row -- so a warp never diverges and a plane costs four LDS,
+    // one 16-byte store and no address arithmetic beyond the plane stride.
+    if (my_round == r && 4 * tid < vt) {
+      uint32_t a4[4];
+      int c4[4];
+      {
+        int s = my_base - r * kSlotsRound;
+        const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(sums));
 #pragma unroll
-    for (int k = 0; k < kGPT; ++k) {
-      mine[k] = (gbase[k] / kSlotsRound == r) && (4 * (tid + kThreads * k) < vt);
-      any_occ |= mine[k] && nib[k] != 0u;
-    }
-    const long long plane0 = ((long long)b * p.C + c0) * p.V + vbase + 4 * tid;
-    if (p.vec4) {
-      float4* d = reinterpret_cast<float4*>(p.matrix + plane0);
-      const long long pstride = p.V >> 2;
-      if (!any_occ) {
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int ch = 0; ch < cc; ++ch, d += pstride) {
-#pragma unroll
-          for (int k = 0; k < kGPT; ++k)
-            if (mine[k]) __stcs(d + kThreads * k, z4);
+        for (int k = 0; k < 4; ++k) {
+          const int slot = ((nib >> k) & 1u) ? s++ : kSlots;          // kSlots = the zero row
+          a4[k] = sb + (uint32_t)(slot * p.CCp) * 4u;
+          c4[k] = cnt[slot];
         }
+      }
+      const long long plane0 = ((long long)b * p.C + c0) * p.V + vbase + 4 * tid;
+      if (p.vec4) {
+        float4* d = reinterpret_cast<float4*>(p.matrix + plane0);
+        const long long pstride = p.V >> 2;
+#pragma unroll 8
+        for (int ch = 0; ch < cc; ++ch, d += pstride) {
+          float4 v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.x) : "r"(a4[0] + 4u * ch));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.y) : "r"(a4[1] + 4u * ch));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.z) : "r"(a4[2] + 4u * ch));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.w) : "r"(a4[3] + 4u * ch));
+          __stcs(d, v);
+        }
+        if (chunk == 0)
+          *reinterpret_cast<int4*>(p.counts + (long long)b * p.V + vbase + 4 * tid) =
+              make_int4(c4[0], c4[1], c4[2], c4[3]);
       } else {
-        for (int ch = 0; ch < cc; ++ch, d += pstride) {
+        // ragged / unaligned planes: scalar stores, tail guarded
 #pragma unroll
-          for (int k = 0; k < kGPT; ++k) {
-            if (!mine[k]) continue;
-            float vv[4] = {0.f, 0.f, 0.f, 0.f};
-            int s = gbase[k] - r * kSlotsRound;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if ((nib[k] >> q) & 1u) vv[q] = sums[(s++) * p.CCp + ch];
-            __stcs(d + kThreads * k, make_float4(vv[0], vv[1], vv[2], vv[3]));
+        for (int k = 0; k < 4; ++k) {
+          if (4 * tid + k >= vt) break;
+          float* dst = p.matrix + plane0 + k;
+          for (int ch = 0; ch < cc; ++ch) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a4[k] + 4u * ch));
+            dst[(long long)ch * p.V] = v;
           }
-        }
-      }
-      if (chunk == 0) {
-#pragma unroll
-        for (int k = 0; k < kGPT; ++k) {
-          if (!mine[k]) continue;
-          int cv[4] = {0, 0, 0, 0};
-          int s = gbase[k] - r * kSlotsRound;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if ((nib[k] >> q) & 1u) cv[q] = cnt[s++];
-          *reinterpret_cast<int4*>(p.counts + (long long)b * p.V + vbase + 4 * (tid + kThreads * k)) =
-              make_int4(cv[0], cv[1], cv[2], cv[3]);
-        }
-      }
-    } else {
-      // ragged / unaligned planes: scalar stores, tail guarded
-#pragma unroll
-      for (int k = 0; k < kGPT; ++k) {
-        if (!mine[k]) continue;
-        int s = gbase[k] - r * kSlotsRound;
-        for (int q = 0; q < 4; ++q) {
-          const int v = 4 * (tid + kThreads * k) + q;
-          const bool occv = (nib[k] >> q) & 1u;
-          const int sl = occv ? s++ : -1;
-          if (v >= vt) continue;
-          float* dst = p.matrix + ((long long)b * p.C + c0) * p.V + vbase + v;
-          for (int ch = 0; ch < cc; ++ch)
-            dst[(long long)ch * p.V] = sl < 0 ? 0.f : sums[sl * p.CCp + ch];
-          if (chunk == 0) p.counts[(long long)b * p.V + vbase + v] = sl < 0 ? 0 : cnt[sl];
+          if (chunk == 0) p.counts[(long long)b * p.V + vbase + 4 * tid + k] = c4[k];
         }
       }
     }
@@ -430,6 +430,44 @@ __global__ void k_max_bwd(const float* __restrict__ gmatrix, const int* __restri
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- store-pattern probe (diagnostics; scripts/fill_patterns.py).  All variants write the same
+// B*(C+1)*V floats of zeros:
+//   0  linear: CTA i streams 16 KiB contiguous (4 float4 per thread), st.cs
+//   1  plane-strided: CTA = (1024 voxels, 48 planes), one float4 per thread and plane, st.cs
+//   2  as 1 with default write-back stores
+//   3  as 0 with default stores
+//   4  plane-strided, CTA = (4096 voxels, 12 planes): 4 float4 per thread and plane, st.cs
+__global__ void __launch_bounds__(256)
+k_fill_probe(float* out, long long V, int planes, int mode) {
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mode == 0 || mode == 3) {
+    float4* dst = reinterpret_cast<float4*>(out) + (long long)blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (mode == 0) __stcs(dst + k * 256, z4); else dst[k * 256] = z4;
+    }
+    return;
+  }
+  if (mode == 4) {
+    const int segs = (int)(V / 4096);
+    const int seg = blockIdx.x % segs, b = blockIdx.x / segs;
+    const int c0 = blockIdx.y * 12;
+    float4* d = reinterpret_cast<float4*>(out + ((long long)b * planes + c0) * V + seg * 4096) + threadIdx.x;
+    for (int ch = 0; ch < 12 && c0 + ch < planes; ++ch, d += V / 4)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) __stcs(d + k * 256, z4);
+    return;
+  }
+  const int segs = (int)(V / 1024);
+  const int seg = blockIdx.x % segs, b = blockIdx.x / segs;
+  const int c0 = blockIdx.y * 48;
+  float4* d = reinterpret_cast<float4*>(out + ((long long)b * planes + c0) * V + seg * 1024) + threadIdx.x;
+#pragma unroll 8
+  for (int ch = 0; ch < 48 && c0 + ch < planes; ++ch, d += V / 4) {
+    if (mode == 1) __stcs(d, z4); else *d = z4;
+  }
+}
+
 }  // namespace mf
 
 using namespace mf;
@@ -440,6 +478,23 @@ using namespace mf;
 //   [kWsCtaOff]    cta_flags[ceil(N/256)] | keys[N]
 constexpr size_t kWsSegOff = 256;
 constexpr size_t kWsCtaOff = kWsSegOff + 2 * 65536 * sizeof(int);
+
+extern "C" int mf_debug_fill_probe(float* out, int B, int planes, int64_t V, int mode, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!out || B <= 0 || planes <= 0 || V % 4096 != 0 || mode < 0 || mode > 4) return MF_E_BADARG;
+  const long long total = (long long)B * planes * V;
+  if (mode == 0 || mode == 3) {
+    k_fill_probe<<<(unsigned)(total / 4096), 256, 0, stream>>>(out, V, planes, mode);
+  } else if (mode == 4) {
+    dim3 g((unsigned)(B * (V / 4096)), (unsigned)((planes + 11) / 12));
+    k_fill_probe<<<g, 256, 0, stream>>>(out, V, planes, mode);
+  } else {
+    dim3 g((unsigned)(B * (V / 1024)), (unsigned)((planes + 47) / 48));
+    k_fill_probe<<<g, 256, 0, stream>>>(out, V, planes, mode);
+  }
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
 
 extern "C" size_t mf_average_voxelization_3d_flags_offset(void) { return 0; }
 
@@ -484,27 +539,22 @@ extern "C" int mf_average_voxelization_3d_fwd(
   p.seg_start = seg_start; p.seg_end = seg_end; p.cta_flags = cta_flags;
   p.n_key_ctas = N > 0 ? n_key_ctas : 0;
   p.N = N; p.C = C; p.B = B; p.V = (int)V;
-  p.segs_per_batch = (int)((V + kVS - 1) / kVS);
-  // channels per CTA: enough CTAs to fill the GPU several times over (each streams CC x 16 KiB),
-  // at most 64 channels (shared-memory rows)
-  int nChunks = (int)((768 + (long long)B * p.segs_per_batch - 1) / ((long long)B * p.segs_per_batch));
-  if (nChunks > C) nChunks = C;
-  if (nChunks < (C + 63) / 64) nChunks = (C + 63) / 64;
+  int nChunks = (C + kMaxCC - 1) / kMaxCC;
   p.CC = (C + nChunks - 1) / nChunks;
   nChunks = (C + p.CC - 1) / p.CC;
   p.CCp = p.CC | 1;
   p.LWs = 2;
   while ((1 << p.LWs) < p.CC) ++p.LWs;
+  p.segs_per_batch = (int)((V + kVS - 1) / kVS);
   p.vec4 = (V % 4 == 0) && (((uintptr_t)matrix & 15) == 0) && (((uintptr_t)counts & 15) == 0);
   p.matrix = matrix; p.counts = counts;
   p.flags_ws = flags_ws; p.flags_user = flags;
   const long long n_cta = (long long)B * p.segs_per_batch;
   if (n_cta >= (1LL << 31) || nChunks > 65535) return MF_E_TOOLARGE;
-  const size_t smem = (size_t)(kSlots + kStage) * p.CCp * 4 + (size_t)kListCap * 8 +
-                      (size_t)kSlots * 4 + (size_t)(kVS / 4) * 4 + (size_t)(kVS / 32) * 4;
-  MF_ENSURE_DYN_SMEM(k_avg_fused, 112 * 1024);
+  const size_t smem = (size_t)(kSlots + 1 + kStage) * p.CCp * 4 + (size_t)kListCap * 8 +
+                      (size_t)(kSlots + 1) * 4 + (size_t)kThreads * 4 + (size_t)(kVS / 32) * 4;
   dim3 grid((unsigned)n_cta, (unsigned)nChunks, 1);
-  k_avg_fused<<<grid, kThreads, smem, stream>>>(p);
+  k_avg_fused<<<grid, kThreads, smem, stream>>>(p);      // <= 25 KB of dynamic shared memory
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

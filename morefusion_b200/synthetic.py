@@ -106,6 +106,35 @@ def surface_points(kind, half, n, rs):
     return p
 
 
+class SyntheticYCBModels:
+    """Stand-in for morefusion.datasets.YCBVideoModels (a multi-GB download, unavailable
+    offline) with the three methods the pose model touches (model.py:199, :353, :416):
+    YCB-shaped primitives whose bounding-box diagonal is 32 x the class voxel pitch."""
+
+    # datasets/ycb_video/class_names.py:32-46: bowl, wood_block, large_clamp, extra_large_clamp,
+    # foam_brick
+    class_ids_symmetric = np.array([13, 16, 19, 20, 21], dtype=np.int32)
+
+    def __init__(self, n_pcd=2000, kinds=("box", "cylinder", "sphere")):
+        self._n_pcd = n_pcd
+        self._kinds = kinds
+        self._pcd = {}
+
+    def get_voxel_pitch(self, dimension, class_id):
+        return 32.0 * YCB_VOXEL_PITCH_32[int(class_id)] / dimension
+
+    def get_pcd(self, class_id):
+        class_id = int(class_id)
+        if class_id not in self._pcd:
+            kind, half = _primitive(class_id, self._kinds)
+            rs = np.random.RandomState(class_id)
+            self._pcd[class_id] = surface_points(kind, half, self._n_pcd, rs).astype(F32)
+        return self._pcd[class_id]
+
+    def get_sdf(self, class_id):
+        return sdf_lattice(int(class_id), self._kinds)
+
+
 def sdf_lattice(class_id, kinds=("box", "cylinder", "sphere")):
     """Stand-in for YCBVideoModels.get_sdf (models.py:66-79): interior lattice points at the
     class pitch with their signed distance (positive inside)."""
