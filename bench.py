@@ -497,6 +497,119 @@ def run_ours(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ training arm (BASELINE config 3)
+def run_train(args, rank, world, local):
+    """singleview_3d training step, data parallel (train.py:229-233,342-344,361): global batch 16
+    split over the ranks, forward + CUDA backward of the 3-D section, bucketed NCCL gradient
+    all-reduce overlapped with the backward, fused 1/world + Chainer-Adam update.  Per-point
+    features stand in for the 2-D extractor's output (as in the inference line)."""
+    assert torch.cuda.is_available(), "bench.py --mode train needs a CUDA device"
+    import morefusion_b200 as mf
+    from morefusion_b200 import _lib, synthetic
+    from morefusion_b200.contrib.singleview_3d.models import Model, training
+    mf.config.check_nan = False
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    G = 16
+    assert G % world == 0
+    Bl = G // world
+    model = Model(n_fg_class=21, with_occupancy=True).to(dev).load_reference_weights(
+        synthetic.init_weights(21, seed=1)).train()
+    tr = training.Trainer(model, alpha=1e-4)
+    rs = np.random.RandomState(100 + rank)
+    batches = []
+    models = synthetic.SyntheticYCBModels()
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
+    for i in range(2):
+        b = synthetic.make_cnn_batch(Bl, P, seed=1000 * rank + i)
+        q = rs.normal(size=(Bl, 4)).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        cam = b["points"] * b["pitch"][:, None, None] + b["origin"][:, :, None]
+        batches.append(dict(dev={k: t(v) for k, v in b.items()}, class_id=b["class_id"],
+                            q=q, tt=cam.mean(axis=2).astype(np.float32)))
+    cur = {}
+
+    def predict(**kw):
+        d = cur["b"]["dev"]
+        return training.forward_features_with_grad(
+            model, class_id=cur["b"]["class_id"], values=d["values"], points=d["points"],
+            pitch=d["pitch"], origin=d["origin"], grid_nontarget_empty=d["grid_nontarget_empty"])
+    model.predict = predict
+
+    def step(i):
+        cur["b"] = batches[i % 2]
+        return tr.step(class_id=cur["b"]["class_id"], rgb=None, pcd=None,
+                       quaternion_true=cur["b"]["q"], translation_true=cur["b"]["tt"])
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    K = args.steps
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    # ---- tensor-pipe fractions of the four conv gradient GEMMs (events around single launches)
+    L = _lib.lib()
+    tb = training._train_buffers(model, Bl, P, dev)
+    buf = model._work_buffers(Bl, P, dev)
+    tw = training._train_pack(model)
+
+    def timed(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    ptr, s = _lib.ptr, _lib.stream
+    gemms = {}
+    for name, flops, fn in (
+        ("conv3_wgrad", 2.0 * Bl * 4096 * 256 * 10240, lambda: L.mf_train_conv_wgrad(
+            ptr(tb["dY3p"]), ptr(buf["x3"]), Bl, 16, 256, 1280, ptr(tb["gw3"]), 1, s())),
+        ("conv3_dgrad", 2.0 * Bl * 4096 * 256 * 10240, lambda: L.mf_train_conv_dgrad(
+            ptr(tb["dY3p"]), ptr(tw["conv3/Wd"]), Bl, 16, 256, 160, 2, ptr(tb["dx3"]), 160,
+            Bl * 4096 * 160, s())),
+        ("conv4_wgrad", 2.0 * Bl * 512 * 512 * 16384, lambda: L.mf_train_conv_wgrad(
+            ptr(tb["dY4p"]), ptr(buf["x4"]), Bl, 8, 512, 2048, ptr(tb["gw4"]), 1, s())),
+        ("conv4_dgrad", 2.0 * Bl * 512 * 512 * 16384, lambda: L.mf_train_conv_dgrad(
+            ptr(tb["dY4p"]), ptr(tw["conv4/Wd"]), Bl, 8, 512, 256, 1, ptr(tb["dgrid3"]), 256, 0, s()))):
+        t_ms = timed(fn)
+        gemms[name] = dict(us=t_ms * 1e3, tflops=flops / (t_ms * 1e-3) / 1e12,
+                           frac_of_bf16_burst_peak=flops / (t_ms * 1e-3) / 1e12 / pk["bf16"])
+    if rank != 0:
+        return
+    n_params = int(tr.flat_p.numel())
+    line = dict(
+        metric="objects/sec training step, 3-D section of singleview_3d (global batch 16)",
+        value=G * K / (ms * 1e-3), unit="objects/s", n_gpus=world, steps=K,
+        warmup=max(args.warmup, 3), ms_per_step=ms / K, higher_is_better=True, scaling="strong",
+        vs_baseline=None, dtype="bf16", data="synthetic", mode="train",
+        config=dict(workload="singleview_3d training step: forward + backward of the 3-D section, "
+                             "Chainer-Adam(1e-4), global batch 16 x 1000 pts",
+                    per_gpu_batch=Bl, parallelism=f"dp{world}: fp32 gradient all-reduce over NCCL in "
+                    f"{len(tr.buckets)} buckets overlapped with the backward, fused unscale + Adam",
+                    parameters=n_params, allreduce_bytes_per_step=4 * n_params if world > 1 else 0,
+                    l2="working set (activations + 124 MB of gradients) exceeds L2"),
+        loss_last=float(loss), clocks=clocks, gemms=gemms,
+        roofline=dict(bound="tensor", kernel="k_gemm_train<256,4> conv3 wgrad (MN-major implicit GEMM)",
+                      achieved=gemms["conv3_wgrad"]["tflops"], peak=pk["bf16"], unit="TFLOP/s",
+                      frac=gemms["conv3_wgrad"]["frac_of_bf16_burst_peak"], traffic=None),
+        gpu_launches=None)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,6 +618,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--quick", action="store_true", help="shorter sub-records (icc / chain)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE config 2 (headline); train: config 3 (data-parallel step)")
     args = ap.parse_args()
     if args.impl == "reference":
         # host-CPU arm: rank 0 alone works; other ranks exit 0 without joining any group
@@ -514,6 +629,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args, rank, world)
+        elif args.mode == "train":
+            run_train(args, rank, world, local)
         else:
             run_ours(args, rank, world, local)
     finally:

@@ -332,6 +332,82 @@ int mf_icc_run_profiled(int n_scenes, int n_objects_total, int voxel_dim, float 
                void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream);
 
 /* ------------------------------------------------------------------------
+ * a10 / a11 backward: training step of the 3-D section of singleview_3d.Model
+ *     replaces chainer's reverse pass through morefusion/contrib/singleview_3d/models/model.py
+ *     :93-141 (_extract) and :239-273 (heads, pose) -- cuDNN backward-data / backward-filter,
+ *     interpolate_voxel_grid.py:216-268, average_voxelization_3d.py:147-220 -- and the
+ *     ChainerMN-side optimizer step (examples/ycb_video/singleview_3d/train.py:342-344).
+ * Activations are the forward's channels-last bf16 buffers; gradients that feed a GEMM are bf16,
+ * accumulators and parameter gradients fp32.  All outputs named d* that are described as
+ * "accumulated" must be zeroed by the caller once per step.
+ * ------------------------------------------------------------------------ */
+/* forward variant of mf_cnn_head4_pose that also saves the 8 selected pre-activation outputs */
+int mf_cnn_head4_pose_train(const void* hd3, int ld, const void* w_rot, const float* b_rot,
+                            const void* w_trans, const float* b_trans, const void* w_conf,
+                            const float* b_conf, const float* points, const int32_t* class_id,
+                            const float* pitch, const float* origin, int B, int P, int nfg,
+                            float* rot, float* trans, float* conf, float* raw8 /*[B*P,8]*/,
+                            void* stream);
+/* tcgen05, both operands MN-major: out[g][n, k] (+)= sum_m dZ[m, g*dz_group_cols + n] *
+ * X[m, g*x_group_cols + k]   (Conv1D weight gradients; bf16 operands, fp32 output) */
+int mf_train_gemm_tn(const void* dZ, long long ldz, const void* X, long long ldx, int m_rows,
+                     int n_out, int k_in, float* out, long long ldo, int n_groups,
+                     long long dz_group_cols, long long x_group_cols, long long out_group_stride,
+                     int accumulate, void* stream);
+/* k4 s2 p1 Conv3D weight gradient in the space-to-depth form of the forward: dYp bf16
+ * [B, Do+2, Do+2, Do+2, Co] (zero border), Xs2d bf16 [B, Do+1, Do+1, Do+1, C8]; out fp32
+ * [Co][8 * C8] in the packed K order of the forward weights (tap-major) */
+int mf_train_conv_wgrad(const void* dYp, const void* Xs2d, int batch, int Do, int Co, int C8,
+                        float* out, int accumulate, void* stream);
+/* k4 s2 p1 Conv3D input gradient: 8 parity GEMMs over the padded dY; Wd bf16 [8][Ci][8*Co]
+ * (per parity r: Wd[r][ci][a*Co+co] = W[co][ci][2a+r]).  epilogue 1: added into a channels-last
+ * fp32 grid [B,(2Do)^3,ldo]; epilogue 2: bf16 rows [8][B*Do^3][ldo] in parity order */
+int mf_train_conv_dgrad(const void* dYp, const void* Wd, int batch, int Do, int Co, int Ci,
+                        int epilogue, void* out, long long ldo, long long out_group_stride,
+                        void* stream);
+int mf_train_head4_bwd(const float* g_rot, const float* g_trans, const float* g_conf,
+                       const float* raw8, const void* hd3, int ld, const void* w_rot,
+                       const void* w_trans, const void* w_conf, const int32_t* class_id,
+                       const float* pitch, int B, int P, int nfg, void* dhd3 /*bf16, masked*/,
+                       float* dw_rot, float* db_rot, float* dw_trans, float* db_trans,
+                       float* dw_conf, float* db_conf /*accumulated*/, void* stream);
+int mf_train_relu_mask(void* x /*bf16 in/out*/, long long ldx, const void* act, long long lda,
+                       long long M, int N, void* stream);
+int mf_train_colsum(const void* x /*bf16*/, long long ldx, long long M, int N,
+                    float* out /*accumulated*/, void* stream);
+int mf_train_interp_bwd(const void* g /*bf16 [B*P, ldg]*/, long long ldg, int col_off,
+                        const float* points /*[B,3,P]*/, int B, int P, int C, int D,
+                        float divisor, float* dgrid /*[B,D^3,C] accumulated*/, void* stream);
+int mf_train_mask_pack(const float* dgrid, const void* act, int act_s2d, int B, int D, int C,
+                       void* out /*bf16 [B,(D+2)^3,C], interior written*/,
+                       float* dbias /*accumulated, may be NULL*/, void* stream);
+int mf_train_vox_bwd(const void* dx3 /*bf16 parity rows*/, long long ldp, const int32_t* keys,
+                     int B, int P, int C, int D, const void* g_direct, long long ldg, int col_off,
+                     float* dfeat2 /*[B*P, C]*/, void* stream);
+int mf_train_point_mlp_bwd(const float* values, const float* points, const void* feat,
+                           long long ldf, const void* dfeat, long long ldd, const float* feat2,
+                           const float* g2, const float* w1r, const float* w1p, const float* w2r,
+                           const float* w2p, int B, int P, float center, float* dw1r,
+                           float* db1r, float* dw1p, float* db1p, float* dw2r, float* db2r,
+                           float* dw2p, float* db2p /*accumulated*/,
+                           float* dvalues /*[B,32,P], may be NULL*/, void* stream);
+/* fused gradient unscale (x grad_scale, e.g. 1/world after a sum all-reduce) + chainer Adam on
+ * flat fp32 buffers */
+int mf_train_adam(float* params, const float* grads, float* m, float* v, int64_t n,
+                  float alpha_t, double beta1, double beta2, double eps, double eta,
+                  float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------
+ * f2  per-frame front end: replaces the host NumPy helpers
+ *     morefusion/geometry/pointcloud_from_depth.py:4-26 and masks_to_bboxes.py:4-38
+ * depth [H,W] f32 metres (NaN = invalid) -> pcd [H,W,3]; masks [N,H,W] u8 -> bboxes [N,4] int32
+ * (y1, x1, y2, x2), upper bounds exclusive, zeros for an empty mask.
+ * ------------------------------------------------------------------------ */
+int mf_pointcloud_from_depth(const float* depth, int H, int W, float fx, float fy, float cx,
+                             float cy, int euclidean, float* pcd, void* stream);
+int mf_masks_to_bboxes(const uint8_t* masks, int N, int H, int W, int32_t* bboxes, void* stream);
+
+/* ------------------------------------------------------------------------
  * a12  average_distance (ADD / ADD-S training loss) + nearest neighbour
  *     replaces morefusion/functions/loss/average_distance.py:40-85 and, for symmetric=1,
  *     morefusion/geometry/knn/nn.py:17-48 + cuComputeDistanceGlobal.cu:20-86 (matrix-free here)

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmorefusion_sm100a.so")
 c_f, c_i, c_i64, c_p, c_sz = (ctypes.c_float, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                               ctypes.c_size_t)
 c_d = ctypes.c_double
+c_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes); must list every symbol the header declares
 # (tests/test_abi.py cross-checks this table against include/morefusion_b200.h)
@@ -62,6 +63,20 @@ SIGNATURES = {
     "mf_cnn_interp_cl": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_i, c_p]),
     "mf_cnn_pose": (c_i, [c_p] * 7 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "mf_cnn_head4_pose": (c_i, [c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "mf_cnn_head4_pose_train": (c_i, [c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "mf_train_gemm_tn": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_ll, c_i, c_ll, c_ll, c_ll, c_i, c_p]),
+    "mf_train_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    "mf_train_conv_dgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_ll, c_p]),
+    "mf_train_head4_bwd": (c_i, [c_p] * 5 + [c_i] + [c_p] * 5 + [c_i, c_i, c_i] + [c_p] * 8),
+    "mf_train_relu_mask": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p]),
+    "mf_train_colsum": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p]),
+    "mf_train_interp_bwd": (c_i, [c_p, c_ll, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
+    "mf_train_mask_pack": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "mf_train_vox_bwd": (c_i, [c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_p, c_ll, c_i, c_p, c_p]),
+    "mf_train_point_mlp_bwd": (c_i, [c_p, c_p, c_p, c_ll, c_p, c_ll] + [c_p] * 6 + [c_i, c_i, c_f] + [c_p] * 10),
+    "mf_train_adam": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_f, c_d, c_d, c_d, c_d, c_f, c_p]),
+    "mf_pointcloud_from_depth": (c_i, [c_p, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_p, c_p]),
+    "mf_masks_to_bboxes": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "mf_icc_max_group_size": (c_i, [c_i]),
     "mf_icc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
     "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9

@@ -35,6 +35,9 @@ SOURCES = {
     "loss.cu": ["-fmad=false"],
     "cnn.cu": [],
     "conv3d_tc.cu": [],
+    "gemm_train.cu": [],
+    "train.cu": [],
+    "frontend.cu": ["-fmad=false"],
 }
 
 

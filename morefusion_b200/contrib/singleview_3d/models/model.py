@@ -108,6 +108,7 @@ class Model(torch.nn.Module):
         self.pspnet_extractor = PSPNetExtractor()
         self._models = synthetic.SyntheticYCBModels()
         self.reported = {}
+        self._raw8 = None
         self._packed = None
         self._packed_ver = None
         self._wbufs = {}
@@ -423,7 +424,8 @@ class Model(torch.nn.Module):
             class_id=torch.as_tensor(class_id).to(device=dev, dtype=torch.int32).contiguous(),
             pitch=torch.as_tensor(pitch, dtype=torch.float32, device=dev).contiguous(),
             origin=torch.as_tensor(origin, dtype=torch.float32, device=dev).contiguous(),
-            gne=None if grid_nontarget_empty is None else grid_nontarget_empty)
+            gne=None if grid_nontarget_empty is None
+            else torch.as_tensor(grid_nontarget_empty, device=dev))
         B, _, P = values.shape
         out = dict(rot=torch.empty((B, P, 4), dtype=torch.float32, device=dev),
                    trans=torch.empty((B, P, 3), dtype=torch.float32, device=dev),
@@ -619,6 +621,19 @@ class Model(torch.nn.Module):
                 A=buf["hd2"][:, i * 256:], W=w[f"conv3_{h}/W"], bias=w[f"conv3_{h}/b"],
                 out=buf["hd3"], M=NP, N=128, K=256, lda=768, ldo=384, col_off=i * 128)
                 for i, h in enumerate(heads)])
+            if self.fused_head4 and getattr(self, "_raw8", None) is not None:
+                # training forward: also keep the 8 selected pre-activation outputs
+                _lib.check(L.mf_cnn_head4_pose_train(
+                    _lib.ptr(buf["hd3"]), 384,
+                    _lib.ptr(w["conv4_rot/W"]), _lib.ptr(w["conv4_rot/b"]),
+                    _lib.ptr(w["conv4_trans/W"]), _lib.ptr(w["conv4_trans/b"]),
+                    _lib.ptr(w["conv4_conf/W"]), _lib.ptr(w["conv4_conf/b"]),
+                    _lib.ptr(points), _lib.ptr(st["class_id"]), _lib.ptr(st["pitch"]),
+                    _lib.ptr(st["origin"]), B, P, nfg,
+                    _lib.ptr(out["rot"]), _lib.ptr(out["trans"]), _lib.ptr(out["conf"]),
+                    _lib.ptr(self._raw8), s()), "head4_pose_train")
+                self.n_launches += 1
+                return
             if self.fused_head4:
                 # layer 4 + class selection + pose epilogue in one kernel (only the object's
                 # class rows are evaluated)

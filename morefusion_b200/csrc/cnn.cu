@@ -831,7 +831,7 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
              const float* __restrict__ points, const int* __restrict__ class_id,
              const float* __restrict__ pitch, const float* __restrict__ origin, int B, int P,
              int nfg, float* __restrict__ rot, float* __restrict__ trans,
-             float* __restrict__ conf) {
+             float* __restrict__ conf, float* __restrict__ raw8) {
   __shared__ __align__(16) float w[8][132];
   __shared__ float bias[8];
   const int b = blockIdx.y;
@@ -879,6 +879,7 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = __shfl_sync(0xffffffffu, acc, base + j);
   if (!ok) return;
+  if (raw8) raw8[n * 8 + r] = acc;              // training: the 8 selected pre-activation outputs
   if (r == 0) {
     float nrm = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]) + 1e-5f;  // F.normalize
     *reinterpret_cast<float4*>(rot + n * 4) =
@@ -1071,12 +1072,39 @@ extern "C" int mf_cnn_pose(const float* out_rot, const float* out_trans, const f
   return MF_OK;
 }
 
+static int head4_pose(const void* hd3, int ld, const void* w_rot, const float* b_rot,
+                      const void* w_trans, const float* b_trans, const void* w_conf,
+                      const float* b_conf, const float* points, const int32_t* class_id,
+                      const float* pitch, const float* origin, int B, int P, int nfg, float* rot,
+                      float* trans, float* conf, float* raw8, void* stream_);
+
 extern "C" int mf_cnn_head4_pose(const void* hd3, int ld, const void* w_rot, const float* b_rot,
                                  const void* w_trans, const float* b_trans, const void* w_conf,
                                  const float* b_conf, const float* points,
                                  const int32_t* class_id, const float* pitch, const float* origin,
                                  int B, int P, int nfg, float* rot, float* trans, float* conf,
                                  void* stream_) {
+  return head4_pose(hd3, ld, w_rot, b_rot, w_trans, b_trans, w_conf, b_conf, points, class_id,
+                    pitch, origin, B, P, nfg, rot, trans, conf, nullptr, stream_);
+}
+
+extern "C" int mf_cnn_head4_pose_train(const void* hd3, int ld, const void* w_rot,
+                                       const float* b_rot, const void* w_trans,
+                                       const float* b_trans, const void* w_conf,
+                                       const float* b_conf, const float* points,
+                                       const int32_t* class_id, const float* pitch,
+                                       const float* origin, int B, int P, int nfg, float* rot,
+                                       float* trans, float* conf, float* raw8, void* stream_) {
+  if (!raw8) return MF_E_BADARG;
+  return head4_pose(hd3, ld, w_rot, b_rot, w_trans, b_trans, w_conf, b_conf, points, class_id,
+                    pitch, origin, B, P, nfg, rot, trans, conf, raw8, stream_);
+}
+
+static int head4_pose(const void* hd3, int ld, const void* w_rot, const float* b_rot,
+                      const void* w_trans, const float* b_trans, const void* w_conf,
+                      const float* b_conf, const float* points, const int32_t* class_id,
+                      const float* pitch, const float* origin, int B, int P, int nfg, float* rot,
+                      float* trans, float* conf, float* raw8, void* stream_) {
   if (B <= 0 || P <= 0 || nfg <= 0 || ld < 384 || (ld & 7) || B > 65535) return MF_E_BADARG;
   if (!hd3 || !w_rot || !b_rot || !w_trans || !b_trans || !w_conf || !b_conf || !points ||
       !class_id || !pitch || !origin || !rot || !trans || !conf)
@@ -1084,7 +1112,8 @@ extern "C" int mf_cnn_head4_pose(const void* hd3, int ld, const void* w_rot, con
   dim3 grid((unsigned)div_up(P, kH4Pts), (unsigned)B);
   k_head4_pose<<<grid, 256, 0, (cudaStream_t)stream_>>>(
       (const bf16*)hd3, ld, (const bf16*)w_rot, b_rot, (const bf16*)w_trans, b_trans,
-      (const bf16*)w_conf, b_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
+      (const bf16*)w_conf, b_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf,
+      raw8);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

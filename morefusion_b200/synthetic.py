@@ -185,6 +185,61 @@ def make_cnn_batch(B=8, P=1000, seed=0, D=32):
                 grid_nontarget_empty=gne)
 
 
+CAMERA_K = np.array([[619.44, 0, 326.82], [0, 619.32, 239.52], [0, 0, 1.0]])   # pose_refinement/data/camera_info.yaml
+
+
+def make_rgbd_batch(B=8, H=256, W=256, seed=0, D=32):
+    """Synthetic stand-in for one batch of the RGB-D pose-estimation datasets
+    (datasets/rgbd_pose_estimation/base.py:125-156): per object a centred H x W crop with
+    ``rgb`` uint8, ``pcd`` float32 camera-frame points (NaN where there is no depth: background,
+    5 % dropout), the ground-truth pose, class id, pitch, origin and a non-target/empty grid --
+    the keyword arguments of Model.__call__ (model.py:277-288)."""
+    rs = np.random.RandomState(seed)
+    class_id = ((np.arange(B) * 3 + seed) % 21 + 1).astype(np.int32)
+    rgb = rs.randint(0, 255, (B, H, W, 3)).astype(np.uint8)
+    pcd = np.full((B, H, W, 3), np.nan, F32)
+    q_true = np.zeros((B, 4), F32)
+    t_true = np.zeros((B, 3), F32)
+    pitch = np.zeros(B, F32)
+    origin = np.zeros((B, 3), F32)
+    gne = np.zeros((B, D, D, D), bool)
+    f = CAMERA_K[0, 0] * 2.2           # crop magnification: the object fills most of the crop
+    for i in range(B):
+        kind, half = _primitive(int(class_id[i]))
+        pitch[i] = YCB_VOXEL_PITCH_32[int(class_id[i])]
+        R = _rot(rs)
+        t = np.array([rs.uniform(-0.02, 0.02), rs.uniform(-0.02, 0.02), rs.uniform(0.55, 0.75)])
+        sp = surface_points(kind, half, 60000, rs)
+        cam = sp @ R.T + t
+        cam = cam[((cam - t) * (-cam)).sum(1) > 0]                      # camera-facing side
+        cam += rs.normal(0, 0.003, cam.shape) * (cam / np.linalg.norm(cam, axis=1, keepdims=True))
+        u = np.round(f * cam[:, 0] / cam[:, 2] + W / 2 - f * t[0] / t[2]).astype(int)
+        v = np.round(f * cam[:, 1] / cam[:, 2] + H / 2 - f * t[1] / t[2]).astype(int)
+        ok = (u >= 0) & (u < W) & (v >= 0) & (v < H)
+        order = np.argsort(-cam[ok, 2])                                 # nearest point wins
+        uu, vv, cc = u[ok][order], v[ok][order], cam[ok][order]
+        pcd[i, vv, uu] = cc.astype(F32)
+        drop = rs.rand(H, W) < 0.05
+        pcd[i][drop] = np.nan
+        rgb[i][~np.isnan(pcd[i, :, :, 2])] //= 2
+        # quaternion (w, x, y, z) of R
+        tr = np.trace(R)
+        w_ = np.sqrt(max(1 + tr, 1e-12)) / 2
+        q = np.array([w_, (R[2, 1] - R[1, 2]) / (4 * w_), (R[0, 2] - R[2, 0]) / (4 * w_),
+                      (R[1, 0] - R[0, 1]) / (4 * w_)])
+        q_true[i] = (q / np.linalg.norm(q)).astype(F32)
+        t_true[i] = t.astype(F32)
+        valid = pcd[i][~np.isnan(pcd[i]).any(axis=2)]
+        origin[i] = (np.median(valid, axis=0) - pitch[i] * (D / 2.0 - 0.5)).astype(F32)
+        ijk = np.stack(np.meshgrid(*(np.arange(D),) * 3, indexing="ij"), -1).astype(F32)
+        centres = ijk * pitch[i] + origin[i]
+        inside = sdf_primitive(kind, half, (centres - t) @ R) > 0
+        front = np.linalg.norm(centres, axis=-1) < np.linalg.norm(t) - 0.3 * half.max()
+        gne[i] = front & ~inside
+    return dict(class_id=class_id, rgb=rgb, pcd=pcd, quaternion_true=q_true, translation_true=t_true,
+                pitch=pitch, origin=origin, grid_nontarget_empty=gne)
+
+
 def make_icc_scene(N=8, seed=0, D=32, t_noise=0.01, rot_noise_deg=10.0,
                    kinds=("box", "cylinder", "sphere")):
     """Synthetic stand-in for examples/ycb_video/pose_refinement/data (BASELINE config 4):

@@ -67,3 +67,15 @@ dist.destroy_process_group()
         capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "MAXOK" in out.stdout
+
+
+def test_gloo_trainer_buckets_and_allreduce():
+    """Data-parallel Trainer host logic on gloo, world_size 2 (tests/_gloo_trainer_worker.py)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29541",
+         os.path.join(ROOT, "tests", "_gloo_trainer_worker.py")],
+        capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "TRAINEROK" in out.stdout

@@ -150,3 +150,30 @@ def test_occupancy_registration_recovers_translation(cuda_device):
                                 threshold=2, transform_init=T0, gpu=cuda_device.index or 0, alpha=0.01)
     T = reg.register(iteration=60)
     assert np.linalg.norm(T[:3, 3]) < 0.6 * np.linalg.norm(T0[:3, 3])
+
+
+def test_frontend_pointcloud_and_bboxes(cuda_device):
+    """geometry.pointcloud_from_depth / masks_to_bboxes vs the reference's NumPy definitions
+    (pointcloud_from_depth.py:16-25, masks_to_bboxes.py:27-33)."""
+    from morefusion_b200 import geometry
+    rs = np.random.RandomState(0)
+    H, W = 480, 640
+    depth = rs.uniform(0.4, 1.2, (H, W)).astype(F32)
+    depth[rs.rand(H, W) < 0.1] = np.nan
+    fx, fy, cx, cy = 619.44, 619.32, 326.82, 239.52
+    for dtype in ("z", "euclidean"):
+        got = geometry.pointcloud_from_depth(depth, fx, fy, cx, cy, dtype)
+        c, r = np.meshgrid(np.arange(W), np.arange(H), sparse=True)
+        z = depth.astype(np.float64)
+        pc = np.dstack((z * (c - cx) / fx, z * (r - cy) / fy, z * np.ones_like(c)))
+        if dtype == "euclidean":
+            pc = pc * (z / np.linalg.norm(pc, axis=2))[:, :, None]
+        assert got.shape == (H, W, 3) and np.array_equal(np.isnan(got), np.isnan(pc))
+        np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(pc), rtol=2e-6, atol=1e-7)
+    masks = np.zeros((3, H, W), bool)
+    masks[0, 10:50, 100:300] = True
+    masks[2, 479, 0] = True
+    bb = geometry.masks_to_bboxes(masks)
+    assert bb.dtype == np.float64
+    np.testing.assert_array_equal(bb, [[10, 100, 50, 300], [0, 0, 0, 0], [479, 0, 480, 1]])
+    np.testing.assert_array_equal(geometry.masks_to_bboxes(masks[0]), [10, 100, 50, 300])
