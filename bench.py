@@ -527,7 +527,7 @@ def run_train(args, rank, world, local):
         q /= np.linalg.norm(q, axis=1, keepdims=True)
         cam = b["points"] * b["pitch"][:, None, None] + b["origin"][:, :, None]
         batches.append(dict(dev={k: t(v) for k, v in b.items()}, class_id=b["class_id"],
-                            q=q, tt=cam.mean(axis=2).astype(np.float32)))
+                            q=t(q), tt=t(cam.mean(axis=2).astype(np.float32))))
     cur = {}
 
     def predict(**kw):

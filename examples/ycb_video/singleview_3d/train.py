@@ -90,6 +90,7 @@ def main():
             t0 = time.time()
             loss = trainer.step(**kw)
             if rank == 0:
+                model.flush_reports()
                 rec = dict(epoch=epoch, iteration=trainer.t, loss=float(loss), elapsed=time.time() - t0,
                            **{k: v for k, v in model.reported.items() if k in ("add", "add_s", "add_or_add_s")})
                 log.append(rec)

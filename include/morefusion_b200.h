@@ -417,6 +417,12 @@ int mf_masks_to_bboxes(const uint8_t* masks, int N, int H, int W, int32_t* bboxe
 int mf_average_distance_fwd(const float* points, int n_points, const float* transform_true,
                             const float* transforms_pred, int n_pred, int symmetric, float* out,
                             int32_t* nn_indices, void* stream);
+/* same forward with the query points split over n_parts CTAs per pose (few poses, many points:
+ * the evaluation metrics); out_parts [n_pred, n_parts] holds partial means, their sum is the
+ * distance */
+int mf_average_distance_fwd_parts(const float* points, int n_points, const float* transform_true,
+                                  const float* transforms_pred, int n_pred, int symmetric,
+                                  int n_parts, float* out_parts, int32_t* nn_indices, void* stream);
 int mf_average_distance_bwd(const float* gout, const float* points, int n_points,
                             const float* transform_true, const float* transforms_pred, int n_pred,
                             const int32_t* nn_indices /*NULL: identity*/,

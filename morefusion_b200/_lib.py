@@ -82,6 +82,7 @@ SIGNATURES = {
     "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
                    + [c_i, c_i, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_i, c_p, c_sz, c_p]),
     "mf_average_distance_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
+    "mf_average_distance_fwd_parts": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "mf_average_distance_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     "mf_icc_run_profiled": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
                             + [c_i, c_i, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_i, c_p, c_sz, c_p, c_p]),

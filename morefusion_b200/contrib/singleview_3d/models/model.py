@@ -108,6 +108,7 @@ class Model(torch.nn.Module):
         self.pspnet_extractor = PSPNetExtractor()
         self._models = synthetic.SyntheticYCBModels()
         self.reported = {}
+        self._pending_eval = None
         self._raw8 = None
         self._packed = None
         self._packed_ver = None
@@ -330,25 +331,62 @@ class Model(torch.nn.Module):
     def evaluate(self, *, class_id, quaternion_true, translation_true, quaternion_pred,
                  translation_pred):
         """ADD / ADD-S of the predicted poses (model.py:325-375); the summary chainer would
-        ``report`` is kept in ``self.reported`` and returned."""
+        ``report`` is kept in ``self.reported`` and returned.  In training mode the metric
+        kernels run on a side stream and the summary is materialised by ``flush_reports()`` (or
+        the next ``evaluate``): no device->host read inside the training step."""
         from .... import functions, metrics
+        from ....metrics.average_distance import average_distance_device
         dev = self.conv3.weight.device
         t = lambda x: torch.as_tensor(x, device=dev).detach().to(torch.float32)   # noqa: E731
-        T_true = functions.transformation_matrix(t(quaternion_true), t(translation_true))
-        T_pred = functions.transformation_matrix(t(quaternion_pred), t(translation_pred))
         cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
         B = cid.shape[0]
-        adds, add_ss = metrics.average_distance(
-            [self._models.get_pcd(class_id=int(c)) for c in cid],
-            [T_true[i] for i in range(B)], [T_pred[i] for i in range(B)])
+        self.flush_reports()
+        main = torch.cuda.current_stream(dev)
+        side = self._side(dev, 2) if self.training else main
+        q_t, t_t, q_p, t_p = t(quaternion_true), t(translation_true), t(quaternion_pred), t(translation_pred)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            T_true = functions.transformation_matrix(q_t, t_t)
+            T_pred = functions.transformation_matrix(q_p, t_p)
+            res = average_distance_device(
+                [self._pcd_device(int(c), dev) for c in cid],
+                [T_true[i] for i in range(B)], [T_pred[i] for i in range(B)], device=dev)
+            done = torch.cuda.Event()
+            done.record(side)
+        for x in (q_t, t_t, q_p, t_p):
+            x.record_stream(side)
+        self._pending_eval = (res, cid, done, self.training)
+        if self.training:
+            return None
+        return self.flush_reports()
+
+    def _pcd_device(self, class_id, dev):
+        """CAD point cloud of a class, cached on the device (uploaded once)."""
+        key = (class_id, dev)
+        cache = self.__dict__.setdefault("_pcd_cache", {})
+        if key not in cache:
+            cache[key] = torch.as_tensor(np.ascontiguousarray(
+                self._models.get_pcd(class_id=class_id), dtype=np.float32), device=dev)
+        return cache[key]
+
+    def flush_reports(self):
+        """Materialise a pending ``evaluate`` summary into ``self.reported`` (one host read)."""
+        pend = getattr(self, "_pending_eval", None)
+        if pend is None:
+            return None
+        res, cid, done, training = pend
+        self._pending_eval = None
+        done.synchronize()
+        r = res.cpu().numpy().astype(float)
+        adds, add_ss = r[:, 0], r[:, 1]
         sym = np.isin(cid, self._models.class_ids_symmetric)
         add_or = np.where(sym, add_ss, adds)
-        if self.training:
+        if training:
             summary = {"add": float(adds.mean()), "add_s": float(add_ss.mean()),
                        "add_or_add_s": float(add_or.mean())}
         else:
             summary = {}
-            for i in range(B):
+            for i in range(len(cid)):
                 key = f"{int(cid[i]):04d}/{i}"
                 summary[f"add/{key}"] = float(adds[i])
                 summary[f"add_s/{key}"] = float(add_ss[i])
@@ -359,7 +397,9 @@ class Model(torch.nn.Module):
     def loss(self, class_id, quaternion_true, translation_true, quaternion_pred,
              translation_pred, confidence_pred, pitch=None, origin=None, grid_target=None,
              grid_nontarget_empty=None):
-        """Confidence-weighted ADD / ADD-S loss (model.py:377-441, :475-481)."""
+        """Confidence-weighted ADD / ADD-S loss (model.py:377-441, :475-481): per object
+        mean over the points with conf > 0 of add * conf - lambda log(conf), averaged over the
+        batch.  No boolean indexing (no host read): masked sums."""
         from .... import functions
         if self._loss in ("add+occupancy", "add/add_s+occupancy"):
             raise NotImplementedError(
@@ -369,26 +409,33 @@ class Model(torch.nn.Module):
         t = lambda x: torch.as_tensor(x, device=dev).to(torch.float32)   # noqa: E731
         quaternion_true, translation_true = t(quaternion_true), t(translation_true)
         cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
-        B = cid.shape[0]
-        loss = 0
+        B, P = confidence_pred.shape
+        T_pred = functions.transformation_matrix(
+            quaternion_pred.reshape(B * P, 4), translation_pred.reshape(B * P, 3)).reshape(B, P, 4, 4)
+        T_true = functions.transformation_matrix(quaternion_true, translation_true)     # [B,4,4]
+        # 500 random CAD points per object (model.py:416-418): indices drawn on the host with
+        # numpy's global RNG as in the reference, one upload for the batch, gather on the device
+        pcds = [self._pcd_device(int(cid[i]), dev) for i in range(B)]
+        sel = torch.as_tensor(np.stack([np.random.permutation(p.shape[0])[:500] for p in pcds]),
+                              device=dev)
+        cads = torch.stack([pcds[i][sel[i]] for i in range(B)])
+        adds = []
         for i in range(B):
-            T_pred = functions.transformation_matrix(quaternion_pred[i], translation_pred[i])
-            T_true = functions.transformation_matrix(quaternion_true[i], translation_true[i])
-            cad = self._models.get_pcd(class_id=int(cid[i]))
-            cad = cad[np.random.permutation(cad.shape[0])[:500]]
-            cad = torch.as_tensor(np.ascontiguousarray(cad, dtype=np.float32), device=dev)
             sym = int(cid[i]) in self._models.class_ids_symmetric
             if self._loss == "add":
                 sym = False
             elif self._loss == "add_s":
                 sym = True
-            add = functions.average_distance(cad, T_true, T_pred, symmetric=sym)
-            conf = confidence_pred[i]
-            keep = conf.detach() > 0
-            loss = loss + torch.mean(add[keep] * conf[keep]
-                                     - self._lambda_confidence * torch.log(conf[keep]))
-        loss = loss / B
-        self.reported["loss"] = float(loss.detach())
+            adds.append(functions.average_distance(cads[i], T_true[i], T_pred[i], symmetric=sym))
+        add = torch.stack(adds)                                              # [B,P]
+        conf = confidence_pred
+        keep = conf.detach() > 0
+        safe = torch.where(keep, conf, torch.ones_like(conf))
+        term = torch.where(keep, add * conf - self._lambda_confidence * torch.log(safe),
+                           torch.zeros_like(conf))
+        loss_i = term.sum(dim=1) / keep.sum(dim=1).clamp(min=1)
+        loss = loss_i.mean()
+        self.reported["loss"] = loss.detach()      # a tensor: float() it when reporting
         return loss
 
     def forward(self, *, class_id, rgb, pcd, quaternion_true, translation_true, pitch=None,

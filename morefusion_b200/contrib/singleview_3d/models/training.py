@@ -159,14 +159,14 @@ def forward_features_with_grad(model, *, class_id, values, points, pitch, origin
     return _PoseNet3D.apply(model, st, values, *params)
 
 
-def _out_grad(model, name):
-    """fp32 gradient destination of a parameter: its .grad if the Trainer pre-allocated one (a view
-    into the flat gradient buffer, already zeroed), else a fresh zero tensor."""
-    p = dict(model.named_parameters())[name]
+def _out_grads(model):
+    """fp32 gradient destinations: the Trainer's views into the flat gradient buffer (already
+    zeroed) if there is one, else fresh zero tensors."""
     tg = getattr(model, "_train_grad_views", None)
-    if tg is not None and name in tg:
-        return tg[name]
-    return torch.zeros_like(p, dtype=torch.float32)
+    if tg is not None:
+        return dict(tg)
+    named = dict(model.named_parameters())
+    return {n: torch.zeros_like(named[n], dtype=torch.float32) for n in flat_param_order(model)}
 
 
 def backward_3d(model, st, g_rot, g_trans, g_conf, needs_values=False, on_bucket=None):
@@ -184,7 +184,7 @@ def backward_3d(model, st, g_rot, g_trans, g_conf, needs_values=False, on_bucket
     tw = _train_pack(model)
     buf = model._work_buffers(B, P, dev)
     tb = _train_buffers(model, B, P, dev)
-    G = {n: _out_grad(model, n) for n in flat_param_order(model)}
+    G = _out_grads(model)
     on_bucket = on_bucket or getattr(model, "_on_bucket", None)
     chk = _lib.check
     with torch.cuda.device(dev):

@@ -57,7 +57,11 @@ k_avg_dist_fwd(const float* __restrict__ points, int P, const float* __restrict_
   __syncthreads();
   const float* T = Tpred + 16 * (long long)m;
   float acc[1] = {0.f};
-  for (int p = threadIdx.x; p < P; p += kAdThreads) {
+  // gridDim.y > 1 (few poses, many points: the metrics): the query points are split over
+  // blockIdx.y and out receives one partial mean per part, out[m * gridDim.y + y]
+  const int per = (P + gridDim.y - 1) / gridDim.y;
+  const int p_lo = blockIdx.y * per, p_hi = min(P, p_lo + per);
+  for (int p = p_lo + threadIdx.x; p < p_hi; p += kAdThreads) {
     float bx, by, bz;
     tf3(T, points[3 * p], points[3 * p + 1], points[3 * p + 2], bx, by, bz);
     int best = p;
@@ -77,7 +81,7 @@ k_avg_dist_fwd(const float* __restrict__ points, int P, const float* __restrict_
     if (idx_out) idx_out[(long long)m * P + p] = best;
   }
   ad_block_sum<1>(acc, sred);
-  if (threadIdx.x == 0) out[m] = acc[0] / (float)P;
+  if (threadIdx.x == 0) out[(long long)m * gridDim.y + blockIdx.y] = acc[0] / (float)P;
 }
 
 // gTpred[m][:3,:] = sum_p g_b (x) [p,1];   part_true[m][:3,:] = sum_p (-g_b) (x) [p_idx,1]
@@ -157,6 +161,23 @@ extern "C" int mf_average_distance_fwd(const float* points, int n_points, const 
   MF_ENSURE_DYN_SMEM(k_avg_dist_fwd, 200 * 1024);
   k_avg_dist_fwd<<<n_pred, kAdThreads, smem, (cudaStream_t)stream_>>>(
       points, n_points, transform_true, transforms_pred, symmetric, out, nn_indices);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_average_distance_fwd_parts(const float* points, int n_points,
+                                             const float* transform_true,
+                                             const float* transforms_pred, int n_pred,
+                                             int symmetric, int n_parts, float* out_parts,
+                                             int32_t* nn_indices, void* stream_) {
+  if (n_points <= 0 || n_pred <= 0 || n_parts <= 0 || n_parts > 65535) return MF_E_BADARG;
+  if (!points || !transform_true || !transforms_pred || !out_parts) return MF_E_BADARG;
+  size_t smem = (size_t)n_points * 12;
+  if (smem > 200 * 1024) return MF_E_UNSUPPORTED;
+  MF_ENSURE_DYN_SMEM(k_avg_dist_fwd, 200 * 1024);
+  dim3 grid((unsigned)n_pred, (unsigned)n_parts);
+  k_avg_dist_fwd<<<grid, kAdThreads, smem, (cudaStream_t)stream_>>>(
+      points, n_points, transform_true, transforms_pred, symmetric, out_parts, nn_indices);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

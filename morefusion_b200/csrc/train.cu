@@ -227,9 +227,19 @@ k_mask_pack(const float* __restrict__ dgrid, const bf16* __restrict__ act, int a
     }
     *reinterpret_cast<uint4*>(out + ((((b * Dp + x + 1) * Dp + y + 1) * Dp + z + 1) * (long long)C + cb * 8)) = ov;
   }
-  if (dbias && vs < vper) {
+  // bias gradient: the CTA's threads that share a channel block are summed in shared memory
+  // first (one atomic per CTA and channel instead of one per thread)
+  __shared__ float sb[256 * 8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(dbias + cb * 8 + k, acc[k]);
+  for (int k = 0; k < 8; ++k) sb[threadIdx.x * 8 + k] = (vs < vper) ? acc[k] : 0.f;
+  __syncthreads();
+  if (dbias && threadIdx.x < C8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = 0.f;
+      for (int j = 0; j < vper; ++j) a += sb[(j * C8 + threadIdx.x) * 8 + k];
+      atomicAdd(dbias + threadIdx.x * 8 + k, a);
+    }
   }
 }
 
