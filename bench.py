@@ -442,6 +442,13 @@ def run_ours(args, rank, world, local):
         records["chain"] = bench_chain(dev, model, runner, rank, world, args.quick)
     except Exception as e:
         records["chain"] = dict(error=f"{type(e).__name__}: {e}")
+    # ---- training step (BASELINE config 3): data parallel, NCCL gradient all-reduce at N > 1
+    try:
+        tl = train_bench(rank, world, local, 6 if args.quick else 12, 3)
+        records["train"] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling",
+                                                 "n_gpus", "steps", "config", "gemms", "loss_last")}
+    except Exception as e:
+        records["train"] = dict(error=f"{type(e).__name__}: {e}")
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (conv3 tcgen05 implicit GEMM)
@@ -498,7 +505,7 @@ def run_ours(args, rank, world, local):
 
 
 # ------------------------------------------------------------------ training arm (BASELINE config 3)
-def run_train(args, rank, world, local):
+def train_bench(rank, world, local, steps, warmup):
     """singleview_3d training step, data parallel (train.py:229-233,342-344,361): global batch 16
     split over the ranks, forward + CUDA backward of the 3-D section, bucketed NCCL gradient
     all-reduce overlapped with the backward, fused 1/world + Chainer-Adam update.  Per-point
@@ -541,10 +548,10 @@ def run_train(args, rank, world, local):
         cur["b"] = batches[i % 2]
         return tr.step(class_id=cur["b"]["class_id"], rgb=None, pcd=None,
                        quaternion_true=cur["b"]["q"], translation_true=cur["b"]["tt"])
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step(i)
     torch.cuda.synchronize()
-    K = args.steps
+    K = steps
     sampler = ClockSampler(local)
     barrier(world)
     torch.cuda.synchronize()
@@ -588,13 +595,12 @@ def run_train(args, rank, world, local):
         t_ms = timed(fn)
         gemms[name] = dict(us=t_ms * 1e3, tflops=flops / (t_ms * 1e-3) / 1e12,
                            frac_of_bf16_burst_peak=flops / (t_ms * 1e-3) / 1e12 / pk["bf16"])
-    if rank != 0:
-        return
+    model.flush_reports()
     n_params = int(tr.flat_p.numel())
     line = dict(
         metric="objects/sec training step, 3-D section of singleview_3d (global batch 16)",
         value=G * K / (ms * 1e-3), unit="objects/s", n_gpus=world, steps=K,
-        warmup=max(args.warmup, 3), ms_per_step=ms / K, higher_is_better=True, scaling="strong",
+        warmup=max(warmup, 3), ms_per_step=ms / K, higher_is_better=True, scaling="strong",
         vs_baseline=None, dtype="bf16", data="synthetic", mode="train",
         config=dict(workload="singleview_3d training step: forward + backward of the 3-D section, "
                              "Chainer-Adam(1e-4), global batch 16 x 1000 pts",
@@ -607,7 +613,15 @@ def run_train(args, rank, world, local):
                       achieved=gemms["conv3_wgrad"]["tflops"], peak=pk["bf16"], unit="TFLOP/s",
                       frac=gemms["conv3_wgrad"]["frac_of_bf16_burst_peak"], traffic=None),
         gpu_launches=None)
-    print(json.dumps(line), flush=True)
+    del tr, model
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_train(args, rank, world, local):
+    line = train_bench(rank, world, local, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def main():

@@ -332,6 +332,33 @@ int mf_icc_run_profiled(int n_scenes, int n_objects_total, int voxel_dim, float 
                void* workspace, size_t workspace_bytes, unsigned long long* phase_ns, void* stream);
 
 /* ------------------------------------------------------------------------
+ * a10 / a11 fp32-class parity mode ("bf16x3"): every GEMM operand is split hi + lo (bf16 each)
+ * and A.W is evaluated as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo on the tcgen05 GEMMs into fp32
+ * slices (mf_gemm_bf16_tc with OUT_F32); these helpers split / combine / gather in fp32
+ * (csrc/precise.cu).  Same reference lines as the bf16 path (model.py:93-141, :239-273).
+ * ------------------------------------------------------------------------ */
+int mf_cnn_point_mlp_f32(const float* values, const float* points, const float* w1_rgb,
+                         const float* b1_rgb, const float* w1_pcd, const float* b1_pcd,
+                         const float* w2_rgb, const float* b2_rgb, const float* w2_pcd,
+                         const float* b2_pcd, int B, int P, float center, void* feat_bf16, int ldf,
+                         float* feat2 /*[B*P,144]*/, float* feat1 /*[B*P,72]*/, void* stream);
+int mf_px_split(const float* src, long long lds, long long M, int N, void* hi, void* lo,
+                long long ldd, int col_off, void* stream);
+int mf_px_combine(const float* ws /*[n_slices][M][N]*/, int n_slices, long long M, int N,
+                  const float* bias, int relu, int out_mode /*OUT_BF16 | OUT_S2D_BF16*/, int Do,
+                  void* hi, void* lo, long long ldo, int col_off, void* stream);
+int mf_px_pack_s2d(const float* vox, const float* hocc, int B, int C, int Cocc, int D, void* X_hi,
+                   void* X_lo, void* stream);
+int mf_px_interp(const void* grid_hi, const void* grid_lo, int s2d, const float* points, int B,
+                 int P, int C, int D, float divisor, void* feat_hi, void* feat_lo, int ldf,
+                 int col_off, void* stream);
+int mf_px_head4_pose(const void* hd3_hi, const void* hd3_lo, int ld, const float* w_rot,
+                     const float* b_rot, const float* w_trans, const float* b_trans,
+                     const float* w_conf, const float* b_conf, const float* points,
+                     const int32_t* class_id, const float* pitch, const float* origin, int B, int P,
+                     int nfg, float* rot, float* trans, float* conf, void* stream);
+
+/* ------------------------------------------------------------------------
  * a10 / a11 backward: training step of the 3-D section of singleview_3d.Model
  *     replaces chainer's reverse pass through morefusion/contrib/singleview_3d/models/model.py
  *     :93-141 (_extract) and :239-273 (heads, pose) -- cuDNN backward-data / backward-filter,

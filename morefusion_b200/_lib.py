@@ -63,6 +63,12 @@ SIGNATURES = {
     "mf_cnn_interp_cl": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_i, c_p]),
     "mf_cnn_pose": (c_i, [c_p] * 7 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "mf_cnn_head4_pose": (c_i, [c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "mf_cnn_point_mlp_f32": (c_i, [c_p] * 10 + [c_i, c_i, c_f, c_p, c_i, c_p, c_p, c_p]),
+    "mf_px_split": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p]),
+    "mf_px_combine": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p]),
+    "mf_px_pack_s2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "mf_px_interp": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_i, c_i, c_p]),
+    "mf_px_head4_pose": (c_i, [c_p, c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "mf_cnn_head4_pose_train": (c_i, [c_p, c_i] + [c_p] * 10 + [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "mf_train_gemm_tn": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_ll, c_i, c_ll, c_ll, c_ll, c_i, c_p]),
     "mf_train_conv_wgrad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),

@@ -114,6 +114,10 @@ class Model(torch.nn.Module):
         self._packed_ver = None
         self._wbufs = {}
         self.use_tensor_cores = True
+        # "bf16": throughput mode (bf16 operands / stored activations, fp32 accumulation);
+        # "bf16x3": fp32-class parity mode -- every GEMM operand split hi + lo and each product
+        # evaluated as A_hi W_hi + A_lo W_hi + A_hi W_lo on the same tcgen05 kernels
+        self.precision = "bf16"
         self.fused_voxelize = True
         # independent branches (occupancy stencil || point MLP + voxelisation; conv3-level gather
         # || conv4) run on a second stream; captured into the CUDA graphs as parallel branches
@@ -477,10 +481,126 @@ class Model(torch.nn.Module):
         out = dict(rot=torch.empty((B, P, 4), dtype=torch.float32, device=dev),
                    trans=torch.empty((B, P, 3), dtype=torch.float32, device=dev),
                    conf=torch.empty((B, P), dtype=torch.float32, device=dev))
+        if self.precision == "bf16x3":
+            self._forward_precise(st, out)
+            return out["rot"], out["trans"], out["conf"]
+        assert self.precision == "bf16", self.precision
         self._stage_pre(st)
         self._stage_conv3(st)
         self._stage_post(st, out)
         return out["rot"], out["trans"], out["conf"]
+
+    # ------------------------------------------------------------------ fp32-class parity mode
+    def _pack_precise(self):
+        ver = tuple(p._version for p in self.parameters())
+        pk = getattr(self, "_packed_px", None)
+        if pk is not None and pk["ver"] == ver:
+            return pk
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def hilo(W):
+            hi = W.to(bf)
+            return hi.contiguous(), (W - hi.to(f32)).to(bf).contiguous()
+        p = dict(ver=ver)
+        for n in ("conv3", "conv4"):
+            W = getattr(self, n).weight.detach().float()
+            Co, Ci = W.shape[:2]
+            Wp = W.reshape(Co, Ci, 2, 2, 2, 2, 2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(Co, 64 * Ci)
+            p[n + "/hi"], p[n + "/lo"] = hilo(Wp)
+        heads = ("rot", "trans", "conf")
+        W1 = torch.cat([getattr(self, f"conv1_{h}").weight.detach().float().reshape(640, 984)
+                        for h in heads], 0)
+        p["head1/hi"], p["head1/lo"] = hilo(torch.nn.functional.pad(W1, (0, FEAT_LD - 984)))
+        for h in heads:
+            for layer in (2, 3):
+                m = getattr(self, f"conv{layer}_{h}")
+                p[f"conv{layer}_{h}/hi"], p[f"conv{layer}_{h}/lo"] = hilo(
+                    m.weight.detach().float().reshape(m.weight.shape[0], -1))
+            m = getattr(self, f"conv4_{h}")
+            p[f"conv4_{h}/W32"] = m.weight.detach().float().reshape(m.weight.shape[0], -1).contiguous()
+        self._packed_px = p
+        return p
+
+    def _forward_precise(self, st, out):
+        """model.py:93-141,:239-273 at fp32-class accuracy (see csrc/precise.cu)."""
+        from .... import config
+        L, dev, B, P, w, _ = self._ctx(st)
+        px = self._pack_precise()
+        D, NP, nfg = self._voxel_dim, B * P, self._n_fg_class
+        Cocc = 16 if self._with_occupancy else 0
+        Ct = 144 + Cocc
+        s, ptr, chk = _lib.stream, _lib.ptr, _lib.check
+        key = ("px", B, P, dev)
+        if key not in self._wbufs:
+            bf, f32 = torch.bfloat16, torch.float32
+            z = lambda *sh, dt=bf: torch.zeros(*sh, dtype=dt, device=dev)     # noqa: E731
+            self._wbufs[key] = dict(
+                feat=[z(NP, FEAT_LD), z(NP, FEAT_LD)], feat1=z(NP, 72, dt=f32), feat2=z(NP, 144, dt=f32),
+                x3=[z(B, 17, 17, 17, 8 * Ct), z(B, 17, 17, 17, 8 * Ct)],
+                x4=[z(B, 9, 9, 9, 8 * 256), z(B, 9, 9, 9, 8 * 256)],
+                h4=[z(B, 512, 512), z(B, 512, 512)],
+                hd1=[z(NP, 1920), z(NP, 1920)], hd2=[z(NP, 768), z(NP, 768)], hd3=[z(NP, 384), z(NP, 384)],
+                occ1=z(B, D ** 3, 8, dt=f32), occ2=z(B, D ** 3, 16, dt=f32),
+                ws=z(3 * max(B * 4096 * 256, NP * 1920), dt=f32),
+                bi=torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P))
+        b = self._wbufs[key]
+        points = st["points"]
+
+        def gemm3(A, W, bias, relu, M, N, K, out, *, mode=GEMM_LINEAR, lda=0, Do=0, Ci8=0,
+                  out_mode=OUT_BF16, ldo=0, col_off=0):
+            """out(hi, lo) = act(A.W^T + bias) from three bf16 GEMMs with fp32 slices."""
+            for k, (a, ww) in enumerate(((A[0], W[0]), (A[1], W[0]), (A[0], W[1]))):
+                sl = b["ws"][k * M * N:(k + 1) * M * N]
+                self._gemm(L, a, ww, None, sl, M, N, K, mode=mode, lda=lda, Do=Do, Ci8=Ci8, relu=0,
+                           out_mode=OUT_F32, ldo=N)
+            chk(L.mf_px_combine(ptr(b["ws"]), 3, M, N, ptr(bias), relu, out_mode, Do, ptr(out[0]),
+                                ptr(out[1]), ldo, col_off, s()), "px_combine")
+            self.n_launches += 1
+
+        with torch.cuda.device(dev):
+            chk(L.mf_cnn_point_mlp_f32(
+                ptr(st["values"]), ptr(points), ptr(w["conv1_rgb/W"]), ptr(w["conv1_rgb/b"]),
+                ptr(w["conv1_pcd/W"]), ptr(w["conv1_pcd/b"]), ptr(w["conv2_rgb/W"]), ptr(w["conv2_rgb/b"]),
+                ptr(w["conv2_pcd/W"]), ptr(w["conv2_pcd/b"]), B, P, D / 2.0 - 0.5, ptr(b["feat"][0]),
+                FEAT_LD, ptr(b["feat2"]), ptr(b["feat1"]), s()), "point_mlp_f32")
+            chk(L.mf_px_split(ptr(b["feat1"]), 72, NP, 72, ptr(b["feat"][0]), ptr(b["feat"][1]), FEAT_LD, 0, s()), "split")
+            chk(L.mf_px_split(ptr(b["feat2"]), 144, NP, 144, ptr(b["feat"][0]), ptr(b["feat"][1]), FEAT_LD, 72, s()), "split")
+            # _voxelize (model.py:143-164) through the public operator, occupancy stencils in fp32
+            pts_np = points.permute(0, 2, 1).reshape(NP, 3).contiguous()
+            with config.no_nan_check():
+                vox, _ = AverageVoxelization3D.apply(b["feat2"], pts_np, b["bi"], B, (0.0, 0.0, 0.0), 1.0, (D, D, D))
+            hocc = None
+            if self._with_occupancy:
+                g = st["gne"].to(torch.float32).contiguous()
+                chk(L.mf_cnn_occ_convs(ptr(g), ptr(w["conv1_occ/W"]), ptr(w["conv1_occ/b"]),
+                                       ptr(w["conv2_occ/W"]), ptr(w["conv2_occ/b"]), B, D, ptr(b["occ1"]),
+                                       ptr(b["occ2"]), None, 0, 0, s()), "occ_convs")
+                hocc = b["occ2"]
+            chk(L.mf_px_pack_s2d(ptr(vox), ptr(hocc), B, 144, Cocc, D, ptr(b["x3"][0]), ptr(b["x3"][1]), s()), "px_pack")
+            self.n_launches += 8
+            gemm3(b["x3"], (px["conv3/hi"], px["conv3/lo"]), w["conv3/b"], 1, B * 4096, 256, 64 * Ct,
+                  b["x4"], mode=GEMM_CONV_S2D, Do=16, Ci8=8 * Ct, out_mode=OUT_S2D_BF16)
+            chk(L.mf_px_interp(ptr(b["x4"][0]), ptr(b["x4"][1]), 1, ptr(points), B, P, 256, 16, 2.0,
+                               ptr(b["feat"][0]), ptr(b["feat"][1]), FEAT_LD, 216, s()), "px_interp3")
+            gemm3(b["x4"], (px["conv4/hi"], px["conv4/lo"]), w["conv4/b"], 1, B * 512, 512, 64 * 256,
+                  b["h4"], mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, ldo=512)
+            chk(L.mf_px_interp(ptr(b["h4"][0]), ptr(b["h4"][1]), 0, ptr(points), B, P, 512, 8, 4.0,
+                               ptr(b["feat"][0]), ptr(b["feat"][1]), FEAT_LD, 472, s()), "px_interp4")
+            gemm3(b["feat"], (px["head1/hi"], px["head1/lo"]), w["head1/b"], 1, NP, 1920, 984, b["hd1"],
+                  lda=FEAT_LD, ldo=1920)
+            heads = ("rot", "trans", "conf")
+            for i, h in enumerate(heads):
+                gemm3([t[:, i * 640:] for t in b["hd1"]], (px[f"conv2_{h}/hi"], px[f"conv2_{h}/lo"]),
+                      w[f"conv2_{h}/b"], 1, NP, 256, 640, b["hd2"], lda=1920, ldo=768, col_off=i * 256)
+            for i, h in enumerate(heads):
+                gemm3([t[:, i * 256:] for t in b["hd2"]], (px[f"conv3_{h}/hi"], px[f"conv3_{h}/lo"]),
+                      w[f"conv3_{h}/b"], 1, NP, 128, 256, b["hd3"], lda=768, ldo=384, col_off=i * 128)
+            chk(L.mf_px_head4_pose(
+                ptr(b["hd3"][0]), ptr(b["hd3"][1]), 384, ptr(px["conv4_rot/W32"]), ptr(w["conv4_rot/b"]),
+                ptr(px["conv4_trans/W32"]), ptr(w["conv4_trans/b"]), ptr(px["conv4_conf/W32"]),
+                ptr(w["conv4_conf/b"]), ptr(points), ptr(st["class_id"]), ptr(st["pitch"]), ptr(st["origin"]),
+                B, P, nfg, ptr(out["rot"]), ptr(out["trans"]), ptr(out["conf"]), s()), "px_head4_pose")
+            self.n_launches += 3
 
     # The forward is three fixed launch sequences (each CUDA-graph capturable):
     #   pre   : point MLP -> voxelise -> occupancy stencils -> s2d pack

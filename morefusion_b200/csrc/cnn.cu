@@ -38,7 +38,7 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
             const float* __restrict__ w2r, const float* __restrict__ b2r,   // [64,128]
             const float* __restrict__ w2p, const float* __restrict__ b2p,   // [8,16]
             int B, int P, float center, bf16* __restrict__ feat, int ldf,
-            float* __restrict__ feat2) {
+            float* __restrict__ feat2, float* __restrict__ feat1 /* [N,72] fp32 or null */) {
   extern __shared__ float sm[];
   float* t1r = sm;                 // [32][64]
   float* t1p = t1r + 32 * 64;      // [3][8]
@@ -101,7 +101,10 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
   for (int e = tid; e < kMlpPts * 72; e += 256) {
     int pt = e / 72, oc = e % 72;
     long long n = n0 + pt;
-    if (n < NP) feat[n * ldf + oc] = __float2bfloat16(h1[pt * 73 + oc]);
+    if (n < NP) {
+      feat[n * ldf + oc] = __float2bfloat16(h1[pt * 73 + oc]);
+      if (feat1) feat1[n * 72 + oc] = h1[pt * 73 + oc];
+    }
   }
   // stage 2 rgb: 128 oc x 64 pts; thread = 4 points x 4 consecutive oc (one LDS.128 of weights
   // feeds 16 FMAs): 32 oc-quads x 16 point-groups = 512 items, 2 per thread
@@ -898,11 +901,34 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
 
 using namespace mf;
 
+static int point_mlp(const float* values, const float* points, const float* w1r, const float* b1r,
+                     const float* w1p, const float* b1p, const float* w2r, const float* b2r,
+                     const float* w2p, const float* b2p, int B, int P, float center, void* feat,
+                     int ldf, float* feat2, float* feat1, void* stream_);
+
 extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const float* w1r,
                                 const float* b1r, const float* w1p, const float* b1p,
                                 const float* w2r, const float* b2r, const float* w2p,
                                 const float* b2p, int B, int P, float center, void* feat, int ldf,
                                 float* feat2, void* stream_) {
+  return point_mlp(values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, feat, ldf,
+                   feat2, nullptr, stream_);
+}
+
+extern "C" int mf_cnn_point_mlp_f32(const float* values, const float* points, const float* w1r,
+                                    const float* b1r, const float* w1p, const float* b1p,
+                                    const float* w2r, const float* b2r, const float* w2p,
+                                    const float* b2p, int B, int P, float center, void* feat,
+                                    int ldf, float* feat2, float* feat1, void* stream_) {
+  if (!feat1) return MF_E_BADARG;
+  return point_mlp(values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, feat, ldf,
+                   feat2, feat1, stream_);
+}
+
+static int point_mlp(const float* values, const float* points, const float* w1r, const float* b1r,
+                     const float* w1p, const float* b1p, const float* w2r, const float* b2r,
+                     const float* w2p, const float* b2p, int B, int P, float center, void* feat,
+                     int ldf, float* feat2, float* feat1, void* stream_) {
   if (B <= 0 || P <= 0 || ldf < 216) return MF_E_BADARG;
   if (!values || !points || !w1r || !b1r || !w1p || !b1p || !w2r || !b2r || !w2p || !b2p ||
       !feat || !feat2)
@@ -911,7 +937,7 @@ extern "C" int mf_cnn_point_mlp(const float* values, const float* points, const 
   MF_ENSURE_DYN_SMEM(k_point_mlp, kMlpSmemFloats * 4);
   k_point_mlp<<<div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(
       values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat, ldf,
-      feat2);
+      feat2, feat1);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

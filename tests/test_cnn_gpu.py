@@ -206,3 +206,36 @@ def test_interp_cl_equals_public_operator(cuda_device, D, C, s2d):
     got = feat[:, 8:8 + C].float()
     assert torch.all(feat[:, :8] == 0) and torch.all(feat[:, 8 + C:] == 0)
     torch.testing.assert_close(got, want, rtol=2 ** -7, atol=1e-6)
+
+
+@pytest.mark.parametrize("with_occ", [True, False])
+def test_cnn_precise_mode_meets_north_star_tolerance(cuda_device, with_occ):
+    """Model.precision = "bf16x3" (every GEMM operand split hi + lo, three tcgen05 GEMMs per
+    product, fp32 everywhere else): poses within 1e-4 abs of the reference's fp32 arithmetic
+    (oracle/cnn.py, bf16=False) -- north_star's R/t tolerance -- on every one of the B*P
+    per-point predictions, and the bf16 throughput mode bounded against the same oracle."""
+    B = 2
+    w = ocnn.init_weights(21, seed=1, with_occupancy=with_occ)
+    inp = make_inputs(B)
+    ref32 = ocnn.forward(w, n_fg_class=21, bf16=False, **inp)
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    m = Model(n_fg_class=21, with_occupancy=with_occ).to(cuda_device).load_reference_weights(w)
+    m.precision = "bf16x3"
+    args = dict(class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+                values=torch.as_tensor(inp["values"], device=cuda_device),
+                points=torch.as_tensor(inp["points"], device=cuda_device),
+                pitch=inp["pitch"], origin=inp["origin"],
+                grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device))
+    rot, trans, conf = (x.cpu().numpy() for x in m.forward_features(**args))
+    d_rot = np.abs(rot - ref32["rot"]).max()
+    d_trans = np.abs(trans - ref32["trans"]).max()
+    d_conf = np.abs(conf - ref32["conf"]).max()
+    print(f"bf16x3 vs fp32 oracle: max|d rot|={d_rot:.3g} max|d trans|={d_trans:.3g} max|d conf|={d_conf:.3g}")
+    assert d_rot <= 1e-4 and d_trans <= 1e-4 and d_conf <= 1e-4, (d_rot, d_trans, d_conf)
+    # throughput mode: a max-error bound (not only a mean) against the same fp32 oracle
+    m.precision = "bf16"
+    rot, trans, conf = (x.cpu().numpy() for x in m.forward_features(**args))
+    b_rot, b_trans, b_conf = (np.abs(rot - ref32["rot"]).max(), np.abs(trans - ref32["trans"]).max(),
+                              np.abs(conf - ref32["conf"]).max())
+    print(f"bf16   vs fp32 oracle: max|d rot|={b_rot:.3g} max|d trans|={b_trans:.3g} max|d conf|={b_conf:.3g}")
+    assert b_rot <= 0.15 and b_trans <= 5e-3 and b_conf <= 5e-2, (b_rot, b_trans, b_conf)
