@@ -34,6 +34,7 @@ namespace mf {
 
 constexpr int kIccThreads = 256;
 constexpr int kIccMaxObj = 32;
+constexpr int CHUNK_PTS = 256;          // points per work chunk (CHUNK in the host binding)
 constexpr unsigned long long kKeyEmpty = 0xFFFFFFFFFFFFFFFFull;
 
 struct IccParams {
@@ -223,10 +224,6 @@ k_icc_run(IccParams p, IccAlpha alpha) {
   }
   __syncthreads();
   const int warp_id = tid >> 5, lane_id = tid & 31;
-  const int pt0 = p.obj_pt_off[sc.o0];
-  const int pts_in_scene = p.obj_pt_off[sc.o0 + sc.N] - pt0;
-  const int n_tests = sc.N * pts_in_scene;                    // (target grid, point) pairs
-  const int n_units = (n_tests + 31) / 32;
 
   for (int it = 0; it < p.n_iter; ++it) {
     ICC_STAMP(0)
@@ -244,45 +241,97 @@ k_icc_run(IccParams p, IccAlpha alpha) {
     }
     __syncthreads();
 
-    // ---- P1: scatter.  Work unit = 32 consecutive (target grid, point) tests handled by one
-    // warp; warps of all CTAs are interleaved over the units so that every CTA sees the same mix
-    // of in-range (27 atomics per point) and out-of-range (rejected at once) tests.
-    for (int u = cta * (kIccThreads / 32) + warp_id; u < n_units; u += p.G * (kIccThreads / 32)) {
-      const int tt = u * 32 + lane_id;
-      if (tt >= n_tests) continue;
-      const int il = tt / pts_in_scene, pp = tt - il * pts_in_scene;
-      const int pt = pt0 + pp;
-      int jl = 0;
-      while (jl + 1 < sc.N && pt >= sPtEnd[jl]) ++jl;
-      const int gi = sc.o0 + il, gj = sc.o0 + jl;
-      float pitch = sPitch[il];
-      float trunc = p.threshold * pitch;
-      int ks = ksize_of(pitch, trunc), half = ks / 2;
-      float fx, fy, fz;
-      point_in_grid(sR[jl], sT[jl], p.points[3 * pt], p.points[3 * pt + 1], p.points[3 * pt + 2],
-                    sOrigin[il][0], sOrigin[il][1], sOrigin[il][2], pitch, fx, fy, fz);
-      float rx = roundf(fx), ry = roundf(fy), rz = roundf(fz);
-      if (!(rx >= (float)(-half) && rx <= (float)(D - 1 + half) && ry >= (float)(-half) &&
-            ry <= (float)(D - 1 + half) && rz >= (float)(-half) && rz <= (float)(D - 1 + half)))
-        continue;
-      unsigned long long* keys = p.keys + ((size_t)gi * 2 + (gi == gj ? 0 : 1)) * V;
-      for (int dx = -half; dx <= half; ++dx) {
-        int ix = (int)(rx + (float)dx);
-        if (ix < 0 || ix >= D) continue;
-        float ddx = fx - (float)ix;
-        for (int dy = -half; dy <= half; ++dy) {
-          int iy = (int)(ry + (float)dy);
-          if (iy < 0 || iy >= D) continue;
-          float ddy = fy - (float)iy;
-          for (int dz = -half; dz <= half; ++dz) {
-            int iz = (int)(rz + (float)dz);
-            if (iz < 0 || iz >= D) continue;
-            float ddz = fz - (float)iz;
-            float dist = pitch * sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-            if (dist < trunc) {
-              unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) |
-                                       (unsigned long long)(unsigned int)pt;
-              atomicMin(keys + (ix * D + iy) * D + iz, key);
+    // ---- P1: scatter.  Work unit = (target grid i, 32 consecutive points of one 256-point
+    // chunk): the source object j, its pose and the grid geometry are warp-uniform (registers /
+    // broadcast reads), no per-lane index arithmetic.  Units are interleaved over the warps of
+    // all CTAs of the scene.  Per point the 3 x ks per-axis voxel indices and squared offsets
+    // are formed once; a candidate voxel then costs two adds, the square root, one multiply and
+    // the 64-bit min.
+    {
+      const int n_units = sc.N * sc.C * (CHUNK_PTS / 32);
+      for (int u = cta * (kIccThreads / 32) + warp_id; u < n_units; u += p.G * (kIccThreads / 32)) {
+        const int sub = u & (CHUNK_PTS / 32 - 1);
+        const int ic = u / (CHUNK_PTS / 32);
+        const int il = ic / sc.C, c = ic - il * sc.C;
+        const int gj = __ldg(p.chunk_obj + sc.c0 + c), jl = gj - sc.o0;
+        const int pt = __ldg(p.chunk_start + sc.c0 + c) + sub * 32 + lane_id;
+        if (pt >= sPtEnd[jl]) continue;
+        const int gi = sc.o0 + il;
+        const float pitch = sPitch[il];
+        const float trunc = p.threshold * pitch;
+        const int ks = ksize_of(pitch, trunc), half = ks / 2;
+        float fx, fy, fz;
+        point_in_grid(sR[jl], sT[jl], p.points[3 * pt], p.points[3 * pt + 1], p.points[3 * pt + 2],
+                      sOrigin[il][0], sOrigin[il][1], sOrigin[il][2], pitch, fx, fy, fz);
+        const float rx = roundf(fx), ry = roundf(fy), rz = roundf(fz);
+        if (!(rx >= (float)(-half) && rx <= (float)(D - 1 + half) && ry >= (float)(-half) &&
+              ry <= (float)(D - 1 + half) && rz >= (float)(-half) && rz <= (float)(D - 1 + half)))
+          continue;
+        unsigned long long* keys = p.keys + ((size_t)gi * 2 + (gi == gj ? 0 : 1)) * V;
+        if (half == 1) {
+          // the common case (voxel_threshold = 2): 3 offsets per axis, fully unrolled
+          int vx[3], vy[3], vz[3];
+          float sx[3], sy[3], sz[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int ix = (int)(rx + (float)(k - 1)), iy = (int)(ry + (float)(k - 1)),
+                      iz = (int)(rz + (float)(k - 1));
+            const float dx = fx - (float)ix, dy = fy - (float)iy, dz = fz - (float)iz;
+            vx[k] = (ix >= 0 && ix < D) ? ix * D * D : -1;
+            vy[k] = (iy >= 0 && iy < D) ? iy * D : -1;
+            vz[k] = (iz >= 0 && iz < D) ? iz : -1;
+            sx[k] = dx * dx; sy[k] = dy * dy; sz[k] = dz * dz;
+          }
+          // x-slab of the point's own voxel first (the most likely winners), then the two
+          // neighbouring slabs.  Per slab the 9 current keys are loaded together (independent L2
+          // reads, one round trip) and a candidate only issues its 64-bit atomic if it beats the
+          // value it saw: the key of a voxel only ever decreases, so a stale read can cost a
+          // redundant atomic but never lose a winner.  L2 serves ~50 G 64-bit atomics/s; this
+          // cuts the candidates per voxel from ~27 to a handful.
+#pragma unroll
+          for (int ai = 0; ai < 3; ++ai) {
+            const int a = ai == 0 ? 1 : (ai == 1 ? 0 : 2);
+            if (vx[a] < 0) continue;
+            unsigned long long cur[9];
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2)
+#pragma unroll
+              for (int c2 = 0; c2 < 3; ++c2)
+                cur[b2 * 3 + c2] = (vy[b2] >= 0 && vz[c2] >= 0)
+                                       ? __ldcg(keys + vx[a] + vy[b2] + vz[c2]) : 0ull;
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2) {
+              const float sxy = sx[a] + sy[b2];
+#pragma unroll
+              for (int c2 = 0; c2 < 3; ++c2) {
+                const float dist = pitch * sqrtf(sxy + sz[c2]);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) |
+                                               (unsigned long long)(unsigned int)pt;
+                if (dist < trunc && key < cur[b2 * 3 + c2])
+                  atomicMin(keys + vx[a] + vy[b2] + vz[c2], key);
+              }
+            }
+          }
+        } else {
+          for (int dx = -half; dx <= half; ++dx) {
+            const int ix = (int)(rx + (float)dx);
+            if (ix < 0 || ix >= D) continue;
+            const float ddx = fx - (float)ix;
+            for (int dy = -half; dy <= half; ++dy) {
+              const int iy = (int)(ry + (float)dy);
+              if (iy < 0 || iy >= D) continue;
+              const float ddy = fy - (float)iy;
+              for (int dz = -half; dz <= half; ++dz) {
+                const int iz = (int)(rz + (float)dz);
+                if (iz < 0 || iz >= D) continue;
+                const float ddz = fz - (float)iz;
+                const float dist = pitch * sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+                if (dist < trunc) {
+                  const unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) |
+                                                 (unsigned long long)(unsigned int)pt;
+                  atomicMin(keys + (ix * D + iy) * D + iz, key);
+                }
+              }
             }
           }
         }
