@@ -584,12 +584,12 @@ def train_bench(rank, world, local, steps, warmup):
     gemms = {}
     for name, flops, fn in (
         ("conv3_wgrad", 2.0 * Bl * 4096 * 256 * 10240, lambda: L.mf_train_conv_wgrad(
-            ptr(tb["dY3p"]), ptr(buf["x3"]), Bl, 16, 256, 1280, ptr(tb["gw3"]), 1, s())),
+            ptr(tb["dY3p"]), ptr(buf["x3"]), Bl, 16, 256, 1280, ptr(tb["gw3"]), 0, s())),
         ("conv3_dgrad", 2.0 * Bl * 4096 * 256 * 10240, lambda: L.mf_train_conv_dgrad(
             ptr(tb["dY3p"]), ptr(tw["conv3/Wd"]), Bl, 16, 256, 160, 2, ptr(tb["dx3"]), 160,
             Bl * 4096 * 160, s())),
         ("conv4_wgrad", 2.0 * Bl * 512 * 512 * 16384, lambda: L.mf_train_conv_wgrad(
-            ptr(tb["dY4p"]), ptr(buf["x4"]), Bl, 8, 512, 2048, ptr(tb["gw4"]), 1, s())),
+            ptr(tb["dY4p"]), ptr(buf["x4"]), Bl, 8, 512, 2048, ptr(tb["gw4"]), 0, s())),
         ("conv4_dgrad", 2.0 * Bl * 512 * 512 * 16384, lambda: L.mf_train_conv_dgrad(
             ptr(tb["dY4p"]), ptr(tw["conv4/Wd"]), Bl, 8, 512, 256, 1, ptr(tb["dgrid3"]), 256, 0, s()))):
         t_ms = timed(fn)

@@ -246,9 +246,8 @@ def backward_3d(model, st, g_rot, g_trans, g_conf, needs_values=False, on_bucket
         # ---- conv4: ReLU mask + pad (+ bias gradient), weight gradient, input gradient
         chk(L.mf_train_mask_pack(ptr(tb["dgrid4"]), ptr(buf["h4"]), 0, B, 8, 512, ptr(tb["dY4p"]),
                                  ptr(G["conv4.bias"]), s()), "mask_pack4")
-        tb["gw4"].zero_()
         chk(L.mf_train_conv_wgrad(ptr(tb["dY4p"]), ptr(buf["x4"]), B, 8, 512, 8 * 256, ptr(tb["gw4"]),
-                                  1, s()), "conv4 wgrad")
+                                  0, s()), "conv4 wgrad")
         G["conv4.weight"].add_(unpack_conv_k4s2_grad(tb["gw4"], 512, 256))
         chk(L.mf_train_conv_dgrad(ptr(tb["dY4p"]), ptr(tw["conv4/Wd"]), B, 8, 512, 256, 1,
                                   ptr(tb["dgrid3"]), 256, 0, s()), "conv4 dgrad")
@@ -257,9 +256,8 @@ def backward_3d(model, st, g_rot, g_trans, g_conf, needs_values=False, on_bucket
         # ---- conv3
         chk(L.mf_train_mask_pack(ptr(tb["dgrid3"]), ptr(buf["x4"]), 1, B, 16, 256, ptr(tb["dY3p"]),
                                  ptr(G["conv3.bias"]), s()), "mask_pack3")
-        tb["gw3"].zero_()
         chk(L.mf_train_conv_wgrad(ptr(tb["dY3p"]), ptr(buf["x3"]), B, 16, 256, 8 * Ct, ptr(tb["gw3"]),
-                                  1, s()), "conv3 wgrad")
+                                  0, s()), "conv3 wgrad")
         G["conv3.weight"].add_(unpack_conv_k4s2_grad(tb["gw3"], 256, Ct))
         chk(L.mf_train_conv_dgrad(ptr(tb["dY3p"]), ptr(tw["conv3/Wd"]), B, 16, 256, Ct, 2,
                                   ptr(tb["dx3"]), Ct, B * 4096 * Ct, s()), "conv3 dgrad")

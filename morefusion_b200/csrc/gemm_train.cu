@@ -450,7 +450,7 @@ extern "C" int mf_train_conv_wgrad(const void* dYp, const void* Xs2d, int batch,
   if (rc) return rc;
   rc = tg_encode_vox(&a.tmB[0], Xs2d, batch, Do + 1, C8, Do, 64);
   if (rc) return rc;
-  return tg_finish(a, 256, 2 * 148, (cudaStream_t)stream_);
+  return tg_finish(a, 256, 4 * 148, (cudaStream_t)stream_);
 }
 
 extern "C" int mf_train_conv_dgrad(const void* dYp, const void* Wd, int batch, int Do, int Co,
