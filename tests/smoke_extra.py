@@ -58,3 +58,30 @@ def run(dev):
     assert abs(float(loss.detach()) - float(r["loss"])) < 1e-4 * max(1.0, abs(float(r["loss"]))), "ICC loss"
     gt_ = link.translation.grad.cpu().numpy()
     assert np.abs(gt_ - r["gt"]).max() < 1e-3 * max(1.0, np.abs(r["gt"]).max()), "ICC grad"
+
+    # ---- one training step of the 3-D section (forward + CUDA backward + fused Adam), 1 object:
+    # the conv3 weight gradient against the differentiable oracle
+    from oracle import cnn_train as ct
+    from morefusion_b200.contrib.singleview_3d.models import training
+    import morefusion_b200 as mf
+    m.train()
+    q_true = np.array([[1, 0, 0, 0]], np.float32)
+    cam = inp["points"] * inp["pitch"][:, None, None] + inp["origin"][:, :, None]
+    t_true = cam.mean(axis=2).astype(np.float32)
+    cad = [synthetic.SyntheticYCBModels().get_pcd(int(inp["class_id"][0]))[:500]]
+    want_loss, want, _ = ct.loss_and_grads(w, inp, quaternion_true=q_true, translation_true=t_true,
+                                           cad_points=cad, symmetric=[False])
+    rot, trans, conf = training.forward_features_with_grad(
+        m, class_id=inp["class_id"], values=t(inp["values"]), points=t(inp["points"]),
+        pitch=t(inp["pitch"]), origin=t(inp["origin"]),
+        grid_nontarget_empty=t(inp["grid_nontarget_empty"]))
+    F = mf.functions
+    T_pred = F.transformation_matrix(rot[0], trans[0])
+    T_true = F.transformation_matrix(t(q_true[0]), t(t_true[0]))
+    add = F.average_distance(t(cad[0]), T_true, T_pred, symmetric=False)
+    loss = torch.mean(add * conf[0] - 0.015 * torch.log(conf[0]))
+    loss.backward()
+    assert abs(float(loss.detach()) - want_loss) < 3e-2 * abs(want_loss) + 1e-4, "training loss"
+    g, r = m.conv3.weight.grad.float().cpu().numpy().ravel(), want["conv3/W"].ravel()
+    cos = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+    assert cos > 0.995, f"conv3 weight gradient (tcgen05 MN-major wgrad) cos={cos}"
