@@ -242,11 +242,32 @@ int mf_cnn_occ_convs_tc(const float* grid_nontarget_empty, const float* w1, cons
 int mf_cnn_occ_convs_tc_u8(const uint8_t* grid_nontarget_empty, const float* w1, const float* b1,
                            const float* w2, const float* b2, int B, int D,
                            void* h1_bf16 /*[B,V,8]*/, void* X, int Ct, int c_off, void* stream);
+/* conv1_occ + conv2_occ (model.py:69-70,114-125) in ONE kernel (D == 32): each x-slab CTA evaluates
+ * conv1_occ for the three slabs its dilated conv2_occ reads, in shared memory, then conv2_occ on
+ * mma.sync; no [B,V,8] intermediate in global memory.  Same bits as mf_cnn_occ_convs_tc. */
+int mf_cnn_occ_fused(const float* grid_nontarget_empty, const float* w1, const float* b1,
+                     const float* w2, const float* b2, int B, int D, void* X, int Ct, int c_off,
+                     void* stream);
+int mf_cnn_occ_fused_u8(const uint8_t* grid_nontarget_empty, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int B, int D, void* X, int Ct, int c_off,
+                        void* stream);
 /* average_voxelization_3d of model.py:143-164 (origin 0, pitch 1, D^3) fused with the s2d/bf16
- * packing: writes channels [0,C) of X.  prev_keys [B*P] int32 (in/out, initialise to -1) holds
- * the voxel keys of the previous call so that only those voxels are re-zeroed. */
+ * packing: writes channels [0,C) of X.  prev_keys [2*B*P] int32 (in/out, initialise to -1): the
+ * first B*P entries hold the voxel key of every point of the previous call (b*D^3 + voxel, -1 =
+ * dropped, bit 30 = shares its voxel) so that only those voxels are re-zeroed; the second B*P
+ * entries are scratch (each object's points sorted by voxel, then index). */
 int mf_cnn_voxelize_s2d(const float* feat2 /*[B*P,C]*/, const float* points /*[B,3,P]*/, int B,
                         int P, int C, int D, int Ct, int32_t* prev_keys, void* X, void* stream);
+/* mf_cnn_point_mlp + phase 1 of mf_cnn_voxelize_s2d_phase (sparse clear of the previous call's
+ * voxels + this call's keys / sorted order) in ONE launch: the bookkeeping CTAs are dispatched
+ * first and run beside the MLP CTAs.  P <= 4096 (else MF_E_UNSUPPORTED: use the two calls).
+ * Follow with mf_cnn_voxelize_s2d_phase(..., phases = 2). */
+int mf_cnn_point_mlp_voxkeys(const float* values, const float* points, const float* w1_rgb,
+                             const float* b1_rgb, const float* w1_pcd, const float* b1_pcd,
+                             const float* w2_rgb, const float* b2_rgb, const float* w2_pcd,
+                             const float* b2_pcd, int B, int P, float center, void* feat, int ldf,
+                             float* feat2, int C, int D, int Ct, int32_t* prev_keys, void* X,
+                             void* stream);
 /* the same in two halves so that a caller can overlap the first with the point MLP that produces
  * feat2: phases bit 0 = sparse clear + new keys (feat2 may be NULL), bit 1 = ordered scatter */
 int mf_cnn_voxelize_s2d_phase(const float* feat2, const float* points, int B, int P, int C, int D,

@@ -48,11 +48,14 @@ SIGNATURES = {
     "mf_transform_points_fwd": (c_i, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
     "mf_transform_points_bwd": (c_i, [c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),
     "mf_cnn_point_mlp": (c_i, [c_p] * 10 + [c_i, c_i, c_f, c_p, c_i, c_p, c_p]),
+    "mf_cnn_point_mlp_voxkeys": (c_i, [c_p] * 10 + [c_i, c_i, c_f, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "mf_cnn_occ_convs": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
     "mf_cnn_occ_convs_tc": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mf_cnn_voxelize_s2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "mf_cnn_voxelize_s2d_phase": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p]),
     "mf_cnn_occ_convs_tc_u8": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
+    "mf_cnn_occ_fused": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_i, c_i, c_p]),
+    "mf_cnn_occ_fused_u8": (c_i, [c_p] * 5 + [c_i, c_i, c_p, c_i, c_i, c_p]),
     "mf_cnn_pack_s2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "mf_gemm_bf16_simt": (c_i, [c_p, c_p]),
     "mf_gemm_bf16_tc_workspace_bytes": (c_sz, [c_i, c_i]),

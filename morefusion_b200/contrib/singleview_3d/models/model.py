@@ -123,6 +123,7 @@ class Model(torch.nn.Module):
         # || conv4) run on a second stream; captured into the CUDA graphs as parallel branches
         self.fused_head4 = True     # last head layer + class select + pose epilogue in one kernel
         self.concurrent_branches = True
+        self.fused_occ = True       # conv1_occ + conv2_occ in one kernel (no global intermediate)
         self._side_streams = {}
         self.launch_log = []
         self.n_launches = 0      # kernels of this library launched so far (bench's gpu_launches)
@@ -203,7 +204,7 @@ class Model(torch.nn.Module):
             out_trans=z(NP, self._n_fg_class * 3, dt=f32),
             out_conf=z(NP, self._n_fg_class, dt=f32),
             bi=torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P),
-            prev_keys=torch.full((NP,), -1, dtype=torch.int32, device=dev),
+            prev_keys=torch.full((2 * NP,), -1, dtype=torch.int32, device=dev),   # keys | sorted order
         )
         if self._with_occupancy:
             b["occ1"] = z(B, D ** 3, 8, dt=f32)
@@ -629,10 +630,18 @@ class Model(torch.nn.Module):
     def _occ_branch(self, L, st, w, buf, B, D, Ct):
         s = _lib.stream
         gne = st["gne"]
+        fused = self.fused_occ
         if self.use_tensor_cores and D == 32 and gne.dtype in (torch.uint8, torch.bool):
             # byte grids go straight into the stencil (no cast pass)
             g = gne.contiguous()
             g = g.view(torch.uint8) if g.dtype == torch.bool else g
+            if fused:
+                _lib.check(L.mf_cnn_occ_fused_u8(
+                    _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                    _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                    _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_fused_u8")
+                self.n_launches += 1
+                return g
             _lib.check(L.mf_cnn_occ_convs_tc_u8(
                 _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
                 _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
@@ -640,6 +649,13 @@ class Model(torch.nn.Module):
             self.n_launches += 2
             return g
         g = gne.to(torch.float32).contiguous()
+        if self.use_tensor_cores and D == 32 and fused:
+            _lib.check(L.mf_cnn_occ_fused(
+                _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
+                _lib.ptr(w["conv2_occ/W"]), _lib.ptr(w["conv2_occ/b"]), B, D,
+                _lib.ptr(buf["x3"]), Ct, 144, s()), "occ_fused")
+            self.n_launches += 1
+            return g
         if self.use_tensor_cores and D == 32:
             _lib.check(L.mf_cnn_occ_convs_tc(
                 _lib.ptr(g), _lib.ptr(w["conv1_occ/W"]), _lib.ptr(w["conv1_occ/b"]),
@@ -662,35 +678,57 @@ class Model(torch.nn.Module):
             if fused and buf.get("x3_dense_dirty", False):
                 buf["x3"].zero_()            # last call packed densely: sparse clear invalid
                 buf["x3_dense_dirty"] = False
+            def point_mlp():
+                _lib.check(L.mf_cnn_point_mlp(
+                    _lib.ptr(st["values"]), _lib.ptr(st["points"]),
+                    _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
+                    _lib.ptr(w["conv1_pcd/W"]), _lib.ptr(w["conv1_pcd/b"]),
+                    _lib.ptr(w["conv2_rgb/W"]), _lib.ptr(w["conv2_rgb/b"]),
+                    _lib.ptr(w["conv2_pcd/W"]), _lib.ptr(w["conv2_pcd/b"]),
+                    B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), FEAT_LD, _lib.ptr(buf["feat2"]),
+                    s()), "point_mlp")
+
             forked = None
-            if fused and self._with_occupancy and self.concurrent_branches:
-                # the occupancy stencil writes channels [144,160) of x3, the point branch
-                # channels [0,144): disjoint bytes, no ordering needed between them
-                main, side = torch.cuda.current_stream(dev), self._side(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    self._occ_branch(L, st, w, buf, B, D, 144 + 16)
-                forked = (main, side)
             forked2 = None
+            keys_done = False
             if fused and self.concurrent_branches:
-                # sparse clear of the previous call's voxels + this call's keys do not need the
-                # point MLP's output: third branch
-                side2 = self._side(dev, 1)
-                side2.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side2):
-                    _lib.check(L.mf_cnn_voxelize_s2d_phase(
-                        None, _lib.ptr(st["points"]), B, P, 144, D,
-                        144 + (16 if self._with_occupancy else 0), _lib.ptr(buf["prev_keys"]),
-                        _lib.ptr(buf["x3"]), 1, s()), "voxelize_s2d(clear+keys)")
-                forked2 = side2
-            _lib.check(L.mf_cnn_point_mlp(
-                _lib.ptr(st["values"]), _lib.ptr(st["points"]),
-                _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
-                _lib.ptr(w["conv1_pcd/W"]), _lib.ptr(w["conv1_pcd/b"]),
-                _lib.ptr(w["conv2_rgb/W"]), _lib.ptr(w["conv2_rgb/b"]),
-                _lib.ptr(w["conv2_pcd/W"]), _lib.ptr(w["conv2_pcd/b"]),
-                B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), FEAT_LD, _lib.ptr(buf["feat2"]), s()),
-                "point_mlp")
+                # two independent branches: [point MLP + voxel bookkeeping (sparse clear of the
+                # previous call's voxels, keys, sorted order) in one launch -> scatter] and the
+                # occupancy stencils (they write channels [144,160) of x3, the point branch
+                # channels [0,144): disjoint bytes).  The side stream forks from an event
+                # recorded BEFORE the MLP launch, so it does not wait for it.
+                main = torch.cuda.current_stream(dev)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                if P <= 4096:
+                    _lib.check(L.mf_cnn_point_mlp_voxkeys(
+                        _lib.ptr(st["values"]), _lib.ptr(st["points"]),
+                        _lib.ptr(w["conv1_rgb/W"]), _lib.ptr(w["conv1_rgb/b"]),
+                        _lib.ptr(w["conv1_pcd/W"]), _lib.ptr(w["conv1_pcd/b"]),
+                        _lib.ptr(w["conv2_rgb/W"]), _lib.ptr(w["conv2_rgb/b"]),
+                        _lib.ptr(w["conv2_pcd/W"]), _lib.ptr(w["conv2_pcd/b"]),
+                        B, P, D / 2.0 - 0.5, _lib.ptr(buf["feat"]), FEAT_LD, _lib.ptr(buf["feat2"]),
+                        144, D, 144 + (16 if self._with_occupancy else 0),
+                        _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "point_mlp_voxkeys")
+                    keys_done = True
+                else:
+                    side2 = self._side(dev, 1)
+                    side2.wait_event(fork)
+                    with torch.cuda.stream(side2):
+                        _lib.check(L.mf_cnn_voxelize_s2d_phase(
+                            None, _lib.ptr(st["points"]), B, P, 144, D,
+                            144 + (16 if self._with_occupancy else 0), _lib.ptr(buf["prev_keys"]),
+                            _lib.ptr(buf["x3"]), 1, s()), "voxelize_s2d(clear+keys)")
+                    forked2 = side2
+                    point_mlp()
+                if self._with_occupancy:
+                    side = self._side(dev)
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        self._occ_branch(L, st, w, buf, B, D, 144 + 16)
+                    forked = (main, side)
+            else:
+                point_mlp()
             self.n_launches += 1
             Cocc = 16 if self._with_occupancy else 0
             Ct = 144 + Cocc
@@ -699,8 +737,9 @@ class Model(torch.nn.Module):
             if fused:
                 # _voxelize (model.py:143-164) fused with the bf16 s2d packing; the occupancy
                 # stencil writes its 16 channels into the same buffer
-                if forked2 is not None:
-                    torch.cuda.current_stream(dev).wait_stream(forked2)
+                if forked2 is not None or keys_done:
+                    if forked2 is not None:
+                        torch.cuda.current_stream(dev).wait_stream(forked2)
                     _lib.check(L.mf_cnn_voxelize_s2d_phase(
                         _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
                         _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), 2, s()),
@@ -709,7 +748,7 @@ class Model(torch.nn.Module):
                     _lib.check(L.mf_cnn_voxelize_s2d(
                         _lib.ptr(buf["feat2"]), _lib.ptr(st["points"]), B, P, 144, D, Ct,
                         _lib.ptr(buf["prev_keys"]), _lib.ptr(buf["x3"]), s()), "voxelize_s2d")
-                self.n_launches += 3
+                self.n_launches += 1 if keys_done else 3
                 if forked:
                     forked[0].wait_stream(forked[1])
                 elif self._with_occupancy:
@@ -755,21 +794,29 @@ class Model(torch.nn.Module):
                 _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["x4"]), 1, _lib.ptr(points), B, P, 256,
                                               16, 2.0, _lib.ptr(buf["feat"]), FEAT_LD, 216, s()),
                            "interp3")
+            def conv4():
+                # conv4: 16^3 x 256 -> 8^3 x 512
+                self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
+                           64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
+                           ldo=512)
+
             forked = None
             if self.concurrent_branches:
-                # the conv3-level gather only reads x4: overlap it with conv4 (whose split-K
-                # launch leaves SMs idle)
+                # the conv3-level gather only reads x4: overlap it with conv4, whose split-K
+                # launch leaves SMs idle.  conv4 is issued FIRST (its persistent CTAs need whole
+                # SMs; behind the gather's 1000 CTAs it would start late) and the gather forks
+                # from an event recorded before it.
                 main, side = torch.cuda.current_stream(dev), self._side(dev)
-                side.wait_stream(main)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                conv4()
+                side.wait_event(fork)
                 with torch.cuda.stream(side):
                     interp3()
                 forked = (main, side)
             else:
                 interp3()
-            # conv4: 16^3 x 256 -> 8^3 x 512
-            self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
-                       64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
-                       ldo=512)
+                conv4()
             _lib.check(L.mf_cnn_interp_cl(_lib.ptr(buf["h4"]), 0, _lib.ptr(points), B, P, 512, 8,
                                           4.0, _lib.ptr(buf["feat"]), FEAT_LD, 472, s()), "interp4")
             self.n_launches += 2

@@ -25,21 +25,48 @@ namespace mf {
 using bf16 = __nv_bfloat16;
 
 // ------------------------------------------------------------------ per-point MLP
-// 64 points per CTA; weights staged transposed in shared memory ([k][oc]) so that lanes
-// (consecutive oc) read consecutive words and the activations are warp broadcasts.
-constexpr int kMlpPts = 64;
+// 32 points per CTA (250 CTAs at 8 x 1000 points, 4 resident per SM so that one CTA's loads hide
+// under another's FMAs); weights staged transposed in shared memory ([k][oc]) by cp.async - the
+// 32 KB second-layer block lands while layer 1 computes - so that lanes (consecutive oc) read
+// consecutive words and the activations are warp broadcasts.
+constexpr int kMlpPts = 32;
 constexpr int kMlpSmemFloats = 32 * 64 + 3 * 8 + 64 * 128 + 8 * 16 + 72 + 144 + kMlpPts * 36 + kMlpPts * 73;
 
-__global__ void __launch_bounds__(256)
-k_point_mlp(const float* __restrict__ values,  // [B,32,P]
-            const float* __restrict__ points,  // [B,3,P] voxel frame
-            const float* __restrict__ w1r, const float* __restrict__ b1r,   // [32,64] (k-major)
-            const float* __restrict__ w1p, const float* __restrict__ b1p,   // [3,8]
-            const float* __restrict__ w2r, const float* __restrict__ b2r,   // [64,128]
-            const float* __restrict__ w2p, const float* __restrict__ b2p,   // [8,16]
-            int B, int P, float center, bf16* __restrict__ feat, int ldf,
-            float* __restrict__ feat2, float* __restrict__ feat1 /* [N,72] fp32 or null */) {
-  extern __shared__ float sm[];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+struct PointMlpArgs {
+  const float* values;              // [B,32,P]
+  const float* points;              // [B,3,P] voxel frame
+  const float *w1r, *b1r;           // [32,64] (k-major)
+  const float *w1p, *b1p;           // [3,8]
+  const float *w2r, *b2r;           // [64,128]
+  const float *w2p, *b2p;           // [8,16]
+  int B, P;
+  float center;
+  bf16* feat;
+  int ldf;
+  float* feat2;
+  float* feat1;                     // [N,72] fp32 or null
+};
+
+__device__ __forceinline__ void point_mlp_body(const PointMlpArgs& a, int cta, float* sm) {
+  const float* __restrict__ values = a.values;
+  const float* __restrict__ points = a.points;
+  const float* __restrict__ w1r = a.w1r; const float* __restrict__ b1r = a.b1r;
+  const float* __restrict__ w1p = a.w1p; const float* __restrict__ b1p = a.b1p;
+  const float* __restrict__ w2r = a.w2r; const float* __restrict__ b2r = a.b2r;
+  const float* __restrict__ w2p = a.w2p; const float* __restrict__ b2p = a.b2p;
+  const int B = a.B, P = a.P, ldf = a.ldf;
+  const float center = a.center;
+  bf16* __restrict__ feat = a.feat;
+  float* __restrict__ feat2 = a.feat2;
+  float* __restrict__ feat1 = a.feat1;
   float* t1r = sm;                 // [32][64]
   float* t1p = t1r + 32 * 64;      // [3][8]
   float* t2r = t1p + 3 * 8;        // [64][128]  (16-byte aligned: 2048 + 24 floats before it)
@@ -50,30 +77,42 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
   float* h1 = xin + kMlpPts * 36;  // [kMlpPts][73]
   const int tid = threadIdx.x;
   // weights arrive pre-transposed ([k][oc], done once when the model packs its weights)
-  for (int e = tid; e < 64 * 32 / 4; e += 256)
-    reinterpret_cast<float4*>(t1r)[e] = __ldg(reinterpret_cast<const float4*>(w1r) + e);
-  for (int e = tid; e < 8 * 3; e += 256) t1p[e] = w1p[e];
-  for (int e = tid; e < 128 * 64 / 4; e += 256)
-    reinterpret_cast<float4*>(t2r)[e] = __ldg(reinterpret_cast<const float4*>(w2r) + e);
-  for (int e = tid; e < 16 * 8; e += 256) t2p[e] = w2p[e];
-  for (int e = tid; e < 72; e += 256) bb1[e] = e < 64 ? b1r[e] : b1p[e - 64];
-  for (int e = tid; e < 144; e += 256) bb2[e] = e < 128 ? b2r[e] : b2p[e - 128];
-  const long long n0 = (long long)blockIdx.x * kMlpPts;
-  const long long NP = (long long)B * P;
-  for (int e = tid; e < kMlpPts * 35; e += 256) {
-    int c = e / kMlpPts, pt = e % kMlpPts;      // pt fastest: coalesced along P
-    long long n = n0 + pt;
-    float v = 0.f;
-    if (n < NP) {
-      long long b = n / P, p = n % P;
-      v = (c < 32) ? values[(b * 32 + c) * P + p] : (center - points[(b * 3 + (c - 32)) * P + p]);
+  for (int e = tid; e < 64 * 32 / 4; e += 256) cp_async16(t1r + e * 4, w1r + e * 4);
+  cp_async_commit();
+  for (int e = tid; e < 128 * 64 / 4; e += 256) cp_async16(t2r + e * 4, w2r + e * 4);
+  cp_async_commit();
+  const int n0 = cta * kMlpPts;
+  const int NP = B * P;
+  {
+    // inputs: pt fastest (coalesced along P); a CTA's points span at most two objects
+    const int pt = tid & (kMlpPts - 1);
+    const int n = n0 + pt;
+    const int b = n / P, p = n - b * P;
+    const bool ok = n < NP;
+    const float* vsrc = values + ((long long)b * 32) * P + p;
+    const float* psrc = points + ((long long)b * 3) * P + p;
+    float v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c = (tid >> 5) + 8 * i;          // 8 warps x 5 = 40 >= 35 channels
+      v[i] = 0.f;
+      if (ok && c < 35) v[i] = c < 32 ? __ldg(vsrc + (long long)c * P) : center - __ldg(psrc + (long long)(c - 32) * P);
     }
-    xin[pt * 36 + c] = v;
+    for (int e = tid; e < 8 * 3; e += 256) t1p[e] = w1p[e];
+    for (int e = tid; e < 16 * 8; e += 256) t2p[e] = w2p[e];
+    for (int e = tid; e < 72; e += 256) bb1[e] = e < 64 ? b1r[e] : b1p[e - 64];
+    for (int e = tid; e < 144; e += 256) bb2[e] = e < 128 ? b2r[e] : b2p[e - 128];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c = (tid >> 5) + 8 * i;
+      if (c < 35) xin[pt * 36 + c] = v[i];
+    }
   }
+  cp_async_wait<1>();              // layer-1 weights landed (layer 2 still in flight)
   __syncthreads();
-  // stage 1: 64 points x 72 channels; thread = 4 points x 1 channel column group
-  //   rgb: 64 oc x 64 pts -> (16 pt-groups of 4) x 64 oc = 1024 work items, 4 per thread
-  for (int e = tid; e < 16 * 64; e += 256) {
+  // stage 1: 32 points x 72 channels; thread = 4 points x 1 channel
+  //   rgb: 64 oc x 32 pts -> (8 pt-groups of 4) x 64 oc = 512 work items, 2 per thread
+  for (int e = tid; e < (kMlpPts / 4) * 64; e += 256) {
     int oc = e % 64, pg = e / 64;
     float a0 = bb1[oc], a1 = a0, a2 = a0, a3 = a0;
     const float* x0 = xin + (pg * 4) * 36;
@@ -97,18 +136,20 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
     for (int k = 0; k < 3; ++k) acc = fmaf(t1p[k * 8 + o], xin[pt * 36 + 32 + k], acc);
     h1[pt * 73 + 64 + o] = fmaxf(acc, 0.f);
   }
+  cp_async_wait<0>();
   __syncthreads();
-  for (int e = tid; e < kMlpPts * 72; e += 256) {
-    int pt = e / 72, oc = e % 72;
-    long long n = n0 + pt;
+  for (int e = tid; e < kMlpPts * 36; e += 256) {      // 72 channels as bf16 pairs
+    int pt = e / 36, oc = (e % 36) * 2;
+    int n = n0 + pt;
     if (n < NP) {
-      feat[n * ldf + oc] = __float2bfloat16(h1[pt * 73 + oc]);
-      if (feat1) feat1[n * 72 + oc] = h1[pt * 73 + oc];
+      const float u0 = h1[pt * 73 + oc], u1 = h1[pt * 73 + oc + 1];
+      *reinterpret_cast<__nv_bfloat162*>(feat + (long long)n * ldf + oc) = __floats2bfloat162_rn(u0, u1);
+      if (feat1) *reinterpret_cast<float2*>(feat1 + (long long)n * 72 + oc) = make_float2(u0, u1);
     }
   }
-  // stage 2 rgb: 128 oc x 64 pts; thread = 4 points x 4 consecutive oc (one LDS.128 of weights
-  // feeds 16 FMAs): 32 oc-quads x 16 point-groups = 512 items, 2 per thread
-  for (int e = tid; e < 32 * 16; e += 256) {
+  // stage 2 rgb: 128 oc x 32 pts; thread = 4 points x 4 consecutive oc (one LDS.128 of weights
+  // feeds 16 FMAs): 32 oc-quads x 8 point-groups = 256 items, 1 per thread
+  for (int e = tid; e < 32 * (kMlpPts / 4); e += 256) {
     int oq = e % 32, pg = e / 32;
     float4 bq = *reinterpret_cast<const float4*>(bb2 + oq * 4);
     float acc[4][4];
@@ -153,6 +194,11 @@ k_point_mlp(const float* __restrict__ values,  // [B,32,P]
       feat2[n * 144 + 128 + o] = acc;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_point_mlp(PointMlpArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  point_mlp_body(a, blockIdx.x, sm);
 }
 
 // ------------------------------------------------------------------ occupancy stencils
@@ -315,51 +361,66 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 constexpr int kOccT = 36;                       // 32 + 2*2 halo
 constexpr int kOccTileBytes = 3 * kOccT * kOccT * 16;
+constexpr int kOccFragBytes = 14 * 2 * 2 * 32 * 4;     // conv2_occ weights in mma fragment order
+constexpr int kOccConv2Bytes = kOccTileBytes + kOccFragBytes;
 
-__global__ void __launch_bounds__(256)
-k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __restrict__ w /*OIDHW*/,
-                const float* __restrict__ bias, int B, bf16* __restrict__ X, int Ct, int c_off) {
+// conv2_occ's weights: read once per CTA, coalesced, and scattered as bf16 into mma fragment order
+// [s][nt][h][lane] in shared memory (each lane then fetches its 56 words conflict-free; 112
+// strided scalar loads per thread straight from global were 20 % of the kernel).  Call early: the
+// loads are independent of everything else the CTA stages.
+__device__ __forceinline__ void occ2_stage_weights(unsigned char* occ_smem, const float* __restrict__ w) {
+  const int tid = threadIdx.x;
+  bf16* wf = reinterpret_cast<bf16*>(occ_smem + kOccTileBytes);
+  float wv[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) {                 // 16*8*27 = 3456 = 13.5 x 256: loads first
+    const int e = tid + 256 * i;
+    wv[i] = e < 16 * 8 * 27 ? __ldg(w + e) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 14; ++i) {
+    const int e = tid + 256 * i;
+    if (e < 16 * 8 * 27) {
+      const int tap = e % 27, ci = (e / 27) & 7, co = e / (27 * 8);
+      const int idx = (((tap >> 1) * 2 + (co >> 3)) * 2 + (tap & 1)) * 32 + ((co & 7) * 4 + (ci >> 1));
+      wf[idx * 2 + (ci & 1)] = __float2bfloat16(wv[i]);
+    }
+  }
+  if (tid < 64) reinterpret_cast<uint32_t*>(wf)[((13 * 2 + (tid >> 5)) * 2 + 1) * 32 + (tid & 31)] = 0u;
+}
+
+// conv2_occ of one x-slab from the staged tile + weights (call with shared memory NOT yet
+// synchronised: the barrier is the first thing it does)
+__device__ __forceinline__ void occ2_mma_slab(const unsigned char* occ_smem, const float* __restrict__ /*w*/,
+                                              const float* __restrict__ bias, int b, int x,
+                                              bf16* __restrict__ X, int Ct, int c_off) {
   constexpr int D = 32;
-  extern __shared__ __align__(16) unsigned char occ_smem[];
-  uint4* tile = reinterpret_cast<uint4*>(occ_smem);          // [3][36][36] x 16 B
-  const int x = blockIdx.x % D, b = blockIdx.x / D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  // ---- stage the three input slabs (zero outside the grid)
-  for (int e = tid; e < 3 * kOccT * kOccT; e += 256) {
-    int zz = e % kOccT - 2, yy = (e / kOccT) % kOccT - 2, s = e / (kOccT * kOccT);
-    int xx = x + 2 * (s - 1);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (xx >= 0 && xx < D && yy >= 0 && yy < D && zz >= 0 && zz < D)
-      v = __ldg(reinterpret_cast<const uint4*>(h1) + ((long long)b * D * D * D + (xx * D + yy) * D + zz));
-    tile[e] = v;
-  }
-  // ---- B fragments: k = tap_in_step*8 + ci, step s covers taps 2s, 2s+1 (tap 27 = zero pad)
+  // ---- B fragments: k = tap_in_step*8 + ci, step s covers taps 2s, 2s+1 (tap 27 = zero pad),
+  // staged by occ2_stage_weights
+  const bf16* wf = reinterpret_cast<const bf16*>(occ_smem + kOccTileBytes);
+  __syncthreads();
   uint32_t bf[14][2][2];
 #pragma unroll
   for (int s = 0; s < 14; ++s)
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int tap = 2 * s + h, co = nt * 8 + g, ci = 2 * t;
-        float w0 = 0.f, w1 = 0.f;
-        if (tap < 27) {
-          w0 = w[(co * 8 + ci) * 27 + tap];
-          w1 = w[(co * 8 + ci + 1) * 27 + tap];
-        }
-        __nv_bfloat162 p = __floats2bfloat162_rn(w0, w1);
-        bf[s][nt][h] = *reinterpret_cast<uint32_t*>(&p);
-      }
+      for (int h = 0; h < 2; ++h)
+        bf[s][nt][h] = reinterpret_cast<const uint32_t*>(wf)[((s * 2 + nt) * 2 + h) * 32 + lane];
   float bias_r[2][2];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
     bias_r[nt][0] = bias[nt * 8 + 2 * t];
     bias_r[nt][1] = bias[nt * 8 + 2 * t + 1];
   }
-  __syncthreads();
-  const uint32_t* tw = reinterpret_cast<const uint32_t*>(occ_smem);
-  // 64 groups of 16 consecutive-z voxels (y = grp/2, z0 = (grp&1)*16); 8 per warp
+  // 64 groups of 16 consecutive-z voxels (y = grp/2, z0 = (grp&1)*16); 8 per warp.  One
+  // ldmatrix.x4 per k-step fetches the whole A fragment: matrices 0/1 = voxels z0+[0,8) / z0+[8,16)
+  // at tap 2s, matrices 2/3 = the same voxels at tap 2s+1; a matrix row is one voxel's 8 channels
+  // (16 B), which is exactly the (row g, k 2t..2t+1) ownership of the m16n8k16 A fragment.
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(occ_smem);
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhi = lane >> 4;
   for (int grp = warp; grp < 64; grp += 8) {
     const int y = grp >> 1, z0 = (grp & 1) * 16;
     float acc[2][4];
@@ -368,25 +429,18 @@ k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __res
       acc[nt][0] = bias_r[nt][0]; acc[nt][1] = bias_r[nt][1];
       acc[nt][2] = bias_r[nt][0]; acc[nt][3] = bias_r[nt][1];
     }
+    const uint32_t row_s = tile_s + (uint32_t)((y * kOccT + z0 + lrow) * 16);
 #pragma unroll
     for (int s = 0; s < 14; ++s) {
-      uint32_t a[4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int tap = 2 * s + h;
-        if (tap < 27) {
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          // tile coords: slab kd, y + 2*(kh-1) + 2, z + 2*(kw-1) + 2
-          const int base = (kd * kOccT + (y + 2 * kh)) * kOccT + (z0 + 2 * kw);
-          a[2 * h + 0] = tw[(base + g) * 4 + t];          // voxel z0+g   : ci 2t, 2t+1
-          a[2 * h + 1] = tw[(base + g + 8) * 4 + t];      // voxel z0+g+8
-        } else {
-          a[2 * h + 0] = 0u;
-          a[2 * h + 1] = 0u;
-        }
-      }
-      // register order of the m16n8k16 A fragment: (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi)
-      uint32_t af[4] = {a[0], a[1], a[2], a[3]};
+      // tile coords of a tap: slab kd, y + 2*(kh-1) + 2, z + 2*(kw-1) + 2.  Tap 27 does not
+      // exist (its weights are zero): its lanes re-read tap 26, any finite value will do.
+      const int ta = 2 * s, tb = 2 * s + 1 < 27 ? 2 * s + 1 : 26;
+      const int offa = (((ta / 9) * kOccT + 2 * ((ta / 3) % 3)) * kOccT + 2 * (ta % 3)) * 16;
+      const int offb = (((tb / 9) * kOccT + 2 * ((tb / 3) % 3)) * kOccT + 2 * (tb % 3)) * 16;
+      uint32_t af[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                   : "r"(row_s + (uint32_t)(lhi ? offb : offa)));
       mma_bf16_16816(acc[0], af, bf[s][0]);
       mma_bf16_16816(acc[1], af, bf[s][1]);
     }
@@ -406,6 +460,155 @@ k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __res
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_occ_conv2_mma(const bf16* __restrict__ h1 /*[B,V,8] bf16*/, const float* __restrict__ w /*OIDHW*/,
+                const float* __restrict__ bias, int B, bf16* __restrict__ X, int Ct, int c_off) {
+  constexpr int D = 32;
+  extern __shared__ __align__(16) unsigned char occ_smem[];
+  uint4* tile = reinterpret_cast<uint4*>(occ_smem);          // [3][36][36] x 16 B
+  const int x = blockIdx.x % D, b = blockIdx.x / D;
+  // ---- stage the three input slabs (zero outside the grid)
+  for (int e = threadIdx.x; e < 3 * kOccT * kOccT; e += 256) {
+    int zz = e % kOccT - 2, yy = (e / kOccT) % kOccT - 2, s = e / (kOccT * kOccT);
+    int xx = x + 2 * (s - 1);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (xx >= 0 && xx < D && yy >= 0 && yy < D && zz >= 0 && zz < D)
+      v = __ldg(reinterpret_cast<const uint4*>(h1) + ((long long)b * D * D * D + (xx * D + yy) * D + zz));
+    tile[e] = v;
+  }
+  occ2_stage_weights(occ_smem, w);
+  occ2_mma_slab(occ_smem, w, bias, b, x, X, Ct, c_off);
+}
+
+// conv1_occ + conv2_occ in one kernel: the CTA of slab x evaluates conv1_occ (1 -> 8, k3, p1, ReLU,
+// bf16) for the three slabs x-2, x, x+2 that the dilated conv2_occ reads, straight from the
+// occupancy grid (7 input slabs, 7 KB as bytes) into the shared-memory tile - conv1's output never
+// goes through global memory and there is no second launch.  Each conv1 slab is evaluated by the
+// three CTAs that consume it (3 x 0.06 GFMA in total, ~4 us of FFMA per SM) in exchange for the
+// 12.6 MB round trip and the launch boundary.  Tap order and arithmetic = k_occ_conv1_bf16
+// (out-of-grid taps contribute fmaf(w, 0, acc) = acc), so the result is bit-identical.
+constexpr int kOccG = 34;                        // rows per input slab: 32 + 2*1 halo
+constexpr int kOccGS = 40;                       // row stride: col -1 at element 3, col 0 at 4 (aligned)
+template <typename TIn>
+constexpr int occ_fused_bytes() {
+  return kOccConv2Bytes + (27 * 8 + 8) * 4 + 7 * kOccG * kOccGS * (int)sizeof(TIn);
+}
+
+// the 6 input values (columns 4zq-1 .. 4zq+4) of one staged row as floats
+__device__ __forceinline__ void occ_row6(const float* row, int zq, float (&in)[6]) {
+#pragma unroll
+  for (int q = 0; q < 6; ++q) in[q] = row[3 + 4 * zq + q];
+}
+__device__ __forceinline__ void occ_row6(const uint8_t* row, int zq, float (&in)[6]) {
+  // bytes -> float without I2F: 0x4B0000bb is 8388608 + bb exactly
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + zq;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  in[0] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7443)) - 8388608.f;
+  in[1] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7440)) - 8388608.f;
+  in[2] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7441)) - 8388608.f;
+  in[3] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7442)) - 8388608.f;
+  in[4] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7443)) - 8388608.f;
+  in[5] = __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7440)) - 8388608.f;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+k_occ_fused(const TIn* __restrict__ gne /*[B,32,32,32]*/, const float* __restrict__ w1,
+            const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+            int B, bf16* __restrict__ X, int Ct, int c_off) {
+  constexpr int D = 32;
+  extern __shared__ __align__(16) unsigned char occ_smem[];
+  uint4* tile = reinterpret_cast<uint4*>(occ_smem);                        // [3][36][36] x 16 B
+  float* sw = reinterpret_cast<float*>(occ_smem + kOccConv2Bytes);         // [27][8] + bias[8]
+  TIn* gs = reinterpret_cast<TIn*>(sw + 27 * 8 + 8);                       // [7][34][40]
+  const int x = blockIdx.x % D, b = blockIdx.x / D;
+  const int tid = threadIdx.x;
+  occ2_stage_weights(occ_smem, w2);
+  // ---- stage the 7 input slabs x-3 .. x+3 (zero outside the grid), 4-byte units
+  constexpr int kPer = 4 / (int)sizeof(TIn);           // elements per 4-byte unit
+  constexpr int kUnits = kOccGS / kPer;                // units per staged row
+  constexpr int kStageIters = (7 * kOccG * kUnits + 255) / 256;
+  for (int i0 = 0; i0 < kStageIters; i0 += 10) {       // loads of 10 units in flight, then stores
+    uint32_t v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int e = tid + 256 * (i0 + i);
+      const int u = e % kUnits, yy = (e / kUnits) % kOccG - 1, xx = x - 3 + e / (kUnits * kOccG);
+      const int z0 = u * kPer - 4;                     // first grid column of this unit
+      v[i] = 0u;
+      if (e < 7 * kOccG * kUnits && xx >= 0 && xx < D && yy >= 0 && yy < D && z0 >= 0 && z0 < D)
+        v[i] = __ldg(reinterpret_cast<const uint32_t*>(gne + (long long)b * D * D * D + (xx * D + yy) * D + z0));
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int e = tid + 256 * (i0 + i);
+      if (e < 7 * kOccG * kUnits) reinterpret_cast<uint32_t*>(gs)[e] = v[i];
+    }
+  }
+  for (int e = tid; e < 27 * 8; e += 256) sw[e] = w1[(e & 7) * 27 + (e >> 3)];   // [tap][c]
+  if (tid < 8) sw[27 * 8 + tid] = b1[tid];
+  // zero padding of conv2_occ: the tile's 2-voxel halo (4 rows x 36 + 32 rows x 4 columns per
+  // slab) and, at the grid boundary, the whole slab
+  for (int e = tid; e < 3 * 272; e += 256) {
+    const int s3 = e / 272, r = e % 272;
+    int row, col;
+    if (r < 144) { row = r / 36; row = row < 2 ? row : row + 32; col = r % 36; }
+    else { row = 2 + (r - 144) / 4; col = (r - 144) % 4; col = col < 2 ? col : col + 32; }
+    tile[(s3 * kOccT + row) * kOccT + col] = make_uint4(0, 0, 0, 0);
+  }
+  if (x < 2 || x >= D - 2) {
+    const int s3 = x < 2 ? 0 : 2;                      // slab x-2 < 0 or x+2 >= D
+    for (int e = tid; e < D * D; e += 256)
+      tile[(s3 * kOccT + 2 + e / D) * kOccT + 2 + e % D] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // ---- conv1: item = (slab s, row yy, 4 consecutive z): 3 x 32 x 8 = 768 items, 3 per thread
+  for (int it = tid; it < 3 * D * 8; it += 256) {
+    const int zq = it & 7, yy = (it >> 3) & 31, s = it >> 8;
+    const int xx = x + 2 * (s - 1);
+    if (xx < 0 || xx >= D) continue;                 // slab outside the grid: conv2's zero padding
+    float acc[4][8];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[v][c] = sw[27 * 8 + c];
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        // input slab (xx + kd - 1) - (x - 3) = 2s + kd; staged row (yy + kh - 1) + 1
+        float in[6];
+        occ_row6(gs + ((2 * s + kd) * kOccG + (yy + kh)) * kOccGS, zq, in);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4 wa = *reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * 8 + 4);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float a = in[v + kw];
+            acc[v][0] = fmaf(wa.x, a, acc[v][0]); acc[v][1] = fmaf(wa.y, a, acc[v][1]);
+            acc[v][2] = fmaf(wa.z, a, acc[v][2]); acc[v][3] = fmaf(wa.w, a, acc[v][3]);
+            acc[v][4] = fmaf(wb.x, a, acc[v][4]); acc[v][5] = fmaf(wb.y, a, acc[v][5]);
+            acc[v][6] = fmaf(wb.z, a, acc[v][6]); acc[v][7] = fmaf(wb.w, a, acc[v][7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint4 o;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(acc[v][0], 0.f), fmaxf(acc[v][1], 0.f));
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f));
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f));
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f));
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+      tile[(s * kOccT + (yy + 2)) * kOccT + (4 * zq + v + 2)] = o;
+    }
+  }
+  occ2_mma_slab(occ_smem, w2, b2, b, x, X, Ct, c_off);
 }
 
 // conv1_occ variant writing bf16 channels-last (input of k_occ_conv2_mma)
@@ -474,19 +677,21 @@ __global__ void k_s2d_clear(const int* __restrict__ prev_keys, int N, int C, int
   if (n >= N) return;
   int key = prev_keys[n];
   if (key < 0) return;
+  key &= MF_S2D_KEY_MASK;
   const int V = D * D * D;
   bf16* dst = X + s2d_voxel_offset(key / V, key % V, D, Ct);
   for (int c = lane * 2; c < C; c += 64)
     *reinterpret_cast<uint32_t*>(dst + c) = 0u;
 }
 
-__global__ void k_s2d_keys(const float* __restrict__ points /*[B,3,P]*/, int B, int P, int D,
-                           int* __restrict__ keys) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= B * P) return;
-  int b = n / P, p = n % P;
-  const float fx = points[(b * 3 + 0) * P + p], fy = points[(b * 3 + 1) * P + p],
-              fz = points[(b * 3 + 2) * P + p];
+// One CTA per object: voxel keys + the "shares its voxel" bit.  Two direct-addressed bit tables in
+// shared memory (D^3 / 8 bytes each: 4 KB at D = 32): `once` = some point fell into the voxel,
+// `twice` = a second one did.  When they do not fit (D > 96) every point is conservatively
+// marked as shared.
+__device__ __forceinline__ int s2d_flat_key(const float* __restrict__ points, int b, int p, int P,
+                                            int D) {
+  const float fx = points[((long long)b * 3 + 0) * P + p], fy = points[((long long)b * 3 + 1) * P + p],
+              fz = points[((long long)b * 3 + 2) * P + p];
   int ix = static_cast<int>(roundf(fx));   // (p - 0) / 1.0
   int iy = static_cast<int>(roundf(fy));
   int iz = static_cast<int>(roundf(fz));
@@ -494,39 +699,105 @@ __global__ void k_s2d_keys(const float* __restrict__ points /*[B,3,P]*/, int B, 
   // Model.predict masks them out before this point, model.py:178)
   bool ok = !(isnan(fx) || isnan(fy) || isnan(fz)) && ix >= 0 && ix < D && iy >= 0 && iy < D &&
             iz >= 0 && iz < D;
-  keys[n] = ok ? b * D * D * D + (ix * D + iy) * D + iz : -1;
+  return ok ? (ix * D + iy) * D + iz : -1;
 }
 
-// one warp per point: the lowest-index point of a voxel ("leader") sums the voxel's points in
-// ascending order, lanes over channels, and writes the averaged bf16 row
+__global__ void __launch_bounds__(1024)
+k_s2d_keys(const float* __restrict__ points /*[B,3,P]*/, int B, int P, int D,
+           int* __restrict__ keys, int use_table) {
+  extern __shared__ unsigned int bits[];     // once[W] | twice[W], W = ceil(D^3 / 32) words
+  const int b = blockIdx.x, V = D * D * D, W = (V + 31) / 32;
+  // the first 1024 points stay in registers across the barrier (P = 1000 in the model)
+  const int flat0 = threadIdx.x < P ? s2d_flat_key(points, b, threadIdx.x, P, D) : -1;
+  if (use_table) {
+    for (int e = threadIdx.x; e < 2 * W; e += 1024) bits[e] = 0u;
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += 1024) {
+      const int flat = p < 1024 ? flat0 : s2d_flat_key(points, b, p, P, D);
+      if (flat >= 0) {
+        const unsigned int m = 1u << (flat & 31);
+        if (atomicOr(&bits[flat >> 5], m) & m) atomicOr(&bits[W + (flat >> 5)], m);
+      }
+    }
+    __syncthreads();
+  }
+  for (int p = threadIdx.x; p < P; p += 1024) {
+    const int flat = p < 1024 ? flat0 : s2d_flat_key(points, b, p, P, D);
+    int key = -1;
+    if (flat >= 0) {
+      const bool dup = !use_table || ((bits[W + (flat >> 5)] >> (flat & 31)) & 1u);
+      key = (b * V + flat) | (dup ? MF_S2D_DUP_BIT : 0);
+    }
+    keys[(long long)b * P + p] = key;
+  }
+}
+
+// one warp per point, 8 consecutive points per CTA.  A point alone in its voxel (no DUP bit; the
+// overwhelmingly common case: 1000 points in 32^3 voxels) converts its own feature row.  For shared
+// voxels the lowest-index point ("leader") sums the voxel's points in ascending order, lanes over
+// channels; only CTAs that contain such a point stage their object's keys in shared memory for
+// the two scans (leader test over earlier points, member search over later ones).
+constexpr int kScatWarps = 8;
 __global__ void __launch_bounds__(256)
 k_s2d_scatter(const float* __restrict__ feat2 /*[N,C]*/, const int* __restrict__ keys, int B,
               int P, int C, int D, int Ct, bf16* __restrict__ X) {
-  int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (n >= B * P) return;
-  const int key = keys[n];
-  if (key < 0) return;
-  const int b = n / P, lo = b * P, hi = lo + P;
+  extern __shared__ int skeys[];               // keys[klo, khi): the objects this CTA touches
+  const int N = B * P;
+  const int nf = blockIdx.x * kScatWarps;
+  const int n = nf + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int raw = n < N ? keys[n] : -1;
+  const bool dup = raw >= 0 && (raw & MF_S2D_DUP_BIT);
+  const int V = D * D * D;
+  const int b = n / P;
+  if (raw >= 0 && !dup) {
+    // same arithmetic as the general path with one member: (0 + v) / 1
+    const float* src = feat2 + (long long)n * C;
+    bf16* dst = X + s2d_voxel_offset(b, (raw & MF_S2D_KEY_MASK) - b * V, D, Ct);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = lane + 32 * k;
+      v[k] = c < C ? __ldg(src + c) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = lane + 32 * k;
+      if (c < C) dst[c] = __float2bfloat16(__fdiv_rn(__fadd_rn(0.f, v[k]), 1.f));
+    }
+  }
+  if (!__syncthreads_or(dup)) return;
+  const int nl = min(nf + kScatWarps, N) - 1;
+  const int klo = (nf / P) * P, khi = min((nl / P + 1) * P, N);
+  for (int e = threadIdx.x; e < khi - klo; e += 256) skeys[e] = keys[klo + e];
+  __syncthreads();
+  if (!dup) return;
+  const int lo = b * P;
+  const int* sk = skeys + (lo - klo);          // this object's keys, indexed by j - lo
+  const int m = n - lo;
   // leader test: any earlier point of this object with the same key?
   bool earlier = false;
-  for (int j0 = lo; j0 < n && !earlier; j0 += 32) {
-    int j = j0 + lane;
-    bool m = (j < n) && (keys[j] == key);
-    earlier = __any_sync(0xffffffffu, m);
+  for (int j0 = 0; j0 < m; j0 += 128) {
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = j0 + 32 * u + lane;
+      any |= (j < m) && (sk[j] == raw);
+    }
+    if (__any_sync(0xffffffffu, any)) { earlier = true; break; }
   }
   if (earlier) return;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   int count = 0;
-  for (int j0 = n - (n - lo) % 32; j0 < hi; j0 += 32) {     // chunks aligned so that j ascends
+  for (int j0 = m - m % 32; j0 < P; j0 += 32) {     // chunks aligned so that j ascends
     int j = j0 + lane;
-    bool m = (j >= n) && (j < hi) && (keys[j] == key);
-    unsigned mask = __ballot_sync(0xffffffffu, m);
+    bool hit = (j >= m) && (j < P) && (sk[j] == raw);
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
     while (mask) {
       int l = __ffs(mask) - 1;
       mask &= mask - 1;
-      const float* src = feat2 + (long long)(j0 + l) * C;
+      const float* src = feat2 + (long long)(lo + j0 + l) * C;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         int c = lane + 32 * k;
@@ -535,8 +806,143 @@ k_s2d_scatter(const float* __restrict__ feat2 /*[N,C]*/, const int* __restrict__
       ++count;
     }
   }
+  bf16* dst = X + s2d_voxel_offset(b, (raw & MF_S2D_KEY_MASK) - b * V, D, Ct);
+  const float cf = (float)count;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = lane + 32 * k;
+    if (c < C) dst[c] = __float2bfloat16(__fdiv_rn(acc[k], cf));
+  }
+}
+
+// ---- sorted variant (P <= 4096): real objects put ~2/3 of their 1000 points into shared voxels,
+// so instead of searching per voxel, every point's position in the (voxel, point index) order is
+// computed up front by comparison counting - rank(p) = #{q : comp[q] < comp[p]} over the object's
+// keys in shared memory, two threads per point, no barriers, 64 points per CTA so that the work
+// spreads over B * P / 64 CTAs - while the point MLP runs on another branch.  A voxel's points
+// are then consecutive in `order`, already in ascending point order, and the scatter does no
+// search at all.  comp = voxel * n2 + point index (n2 = pow2 >= P) fits 31 bits (host-checked).
+constexpr int kRankPts = 64;
+// blockDim.x = 64 * tpp threads (tpp = 2, 4, ... threads per point, each counting a slice of the
+// object's keys).  With X != null the CTA first zeroes the C channels of the voxels that ITS 64
+// points occupied in the previous call (their old keys are still in keys[]: each CTA overwrites
+// only its own slice, after this), which makes the separate sparse-clear launch unnecessary.
+__device__ __forceinline__ void s2d_rank_body(int cta, const float* __restrict__ points, int B, int P,
+                                              int D, int n2, int chunks, int* __restrict__ keys,
+                                              int* __restrict__ order, bf16* __restrict__ X, int C,
+                                              int Ct, int* comp /* shared, [(P+7)&~7] */) {
+  const int b = cta / chunks, p0 = (cta % chunks) * kRankPts, V = D * D * D;
+  const int P8 = (P + 7) & ~7;
+  const int nthr = blockDim.x, tpp = nthr / kRankPts;
+  if (X) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = nthr >> 5;
+    for (int i = warp; i < kRankPts && p0 + i < P; i += nwarp) {
+      int key = keys[(long long)b * P + p0 + i];
+      if (key < 0) continue;
+      key &= MF_S2D_KEY_MASK;
+      bf16* dst = X + s2d_voxel_offset(key / V, key % V, D, Ct);
+      for (int c = lane * 2; c < C; c += 64) *reinterpret_cast<uint32_t*>(dst + c) = 0u;
+    }
+  }
+  for (int p = threadIdx.x; p < P8; p += nthr) {
+    int c = 0x7FFFFFFF;
+    if (p < P) {
+      const int flat = s2d_flat_key(points, b, p, P, D);
+      c = (flat < 0 ? V : flat) * n2 + p;             // dropped points sort behind every voxel
+    }
+    comp[p] = c;
+  }
+  __syncthreads();        // also orders the old-key reads above before the new-key writes below
+  const int p = p0 + threadIdx.x / tpp, part = threadIdx.x % tpp;
+  const int mine = p < P ? comp[p] : 0x7FFFFFFF;
+  const int sh = 31 - __clz(n2);                       // comp >> sh = voxel
+  const int vox = mine >> sh;
+  int rank = 0, same = 0;
+  // this thread's slice of the keys, 4 per shared-memory load
+  const int4* c4 = reinterpret_cast<const int4*>(comp);
+  const int q4 = P8 / 4, per = (q4 + tpp - 1) / tpp;
+  for (int q = part * per; q < min(q4, (part + 1) * per); ++q) {
+    const int4 c = c4[q];
+    rank += (c.x < mine) + (c.y < mine) + (c.z < mine) + (c.w < mine);
+    same += ((c.x >> sh) == vox) + ((c.y >> sh) == vox) + ((c.z >> sh) == vox) + ((c.w >> sh) == vox);
+  }
+  for (int o = 1; o < tpp; o <<= 1) {
+    rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    same += __shfl_xor_sync(0xffffffffu, same, o);
+  }
+  if (part == 0 && p < P) {
+    order[(long long)b * P + rank] = p;
+    keys[(long long)b * P + p] = vox >= V ? -1 : (b * V + vox) | (same > 1 ? MF_S2D_DUP_BIT : 0);
+  }
+}
+
+__global__ void __launch_bounds__(2 * kRankPts)
+k_s2d_rank(const float* __restrict__ points /*[B,3,P]*/, int B, int P, int D, int n2, int chunks,
+           int* __restrict__ keys, int* __restrict__ order) {
+  extern __shared__ __align__(16) int comp[];         // [P rounded up to 8], padding = INT_MAX
+  s2d_rank_body(blockIdx.x, points, B, P, D, n2, chunks, keys, order, nullptr, 0, 0, comp);
+}
+
+// point MLP + (sparse clear + rank) in ONE launch: CTAs [0, rank_ctas) do the voxel bookkeeping,
+// the rest the MLP.  Independent graph branches start in an order the runtime picks; as CTAs of
+// one grid the bookkeeping is dispatched first and runs beside the MLP by construction.
+__global__ void __launch_bounds__(256)
+k_point_mlp_vox(PointMlpArgs a, int rank_ctas, int D, int n2, int chunks, int* __restrict__ keys,
+                int* __restrict__ order, bf16* __restrict__ X, int C, int Ct) {
+  extern __shared__ __align__(16) float sm[];
+  if ((int)blockIdx.x < rank_ctas)
+    s2d_rank_body(blockIdx.x, a.points, a.B, a.P, D, n2, chunks, keys, order, X, C, Ct,
+                  reinterpret_cast<int*>(sm));
+  else
+    point_mlp_body(a, blockIdx.x - rank_ctas, sm);
+}
+
+// one warp per SORTED position: the first position of a voxel's run sums the run in order
+__global__ void __launch_bounds__(256)
+k_s2d_scatter_sorted(const float* __restrict__ feat2 /*[N,C]*/, const int* __restrict__ keys,
+                     const int* __restrict__ order, int B, int P, int C, int D, int Ct,
+                     bf16* __restrict__ X) {
+  const int gpos = blockIdx.x * kScatWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gpos >= B * P) return;
+  const int b = gpos / P, i = gpos - b * P, lo = b * P;
+  // lanes look at positions i-1+lane: lane 0 = the predecessor, lane 1 = this position, ...
+  const int pj = i - 1 + lane;
+  int oj = -1, kj = -2;
+  if (pj >= 0 && pj < P) {
+    oj = __ldg(order + lo + pj);
+    kj = __ldg(keys + lo + oj);
+  }
+  const int raw = __shfl_sync(0xffffffffu, kj, 1);
+  if (raw < 0 || __shfl_sync(0xffffffffu, kj, 0) == raw) return;     // dropped / not a run start
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  int count = 0;
+  int base = i;                                   // position held by lane 1
+  unsigned run = __ballot_sync(0xffffffffu, kj == raw) >> 1;          // bit m = position base+m
+  for (;;) {
+    const int len = run == 0x7FFFFFFFu ? 31 : __ffs(~run) - 1;        // leading run of ones
+    for (int m = 0; m < len; ++m) {
+      const float* src = feat2 + (long long)(lo + __shfl_sync(0xffffffffu, oj, m + 1)) * C;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = lane + 32 * k;
+        if (c < C) acc[k] = __fadd_rn(acc[k], __ldg(src + c));
+      }
+      ++count;
+    }
+    if (len < 31) break;
+    base += 31;                                   // the run may continue: next 31 positions
+    const int q = base - 1 + lane;
+    oj = -1; kj = -2;
+    if (q >= 0 && q < P) {
+      oj = __ldg(order + lo + q);
+      kj = __ldg(keys + lo + oj);
+    }
+    run = __ballot_sync(0xffffffffu, kj == raw) >> 1;
+  }
   const int V = D * D * D;
-  bf16* dst = X + s2d_voxel_offset(b, key % V, D, Ct);
+  bf16* dst = X + s2d_voxel_offset(b, (raw & MF_S2D_KEY_MASK) - b * V, D, Ct);
   const float cf = (float)count;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -935,9 +1341,35 @@ static int point_mlp(const float* values, const float* points, const float* w1r,
     return MF_E_BADARG;
   long long NP = (long long)B * P;
   MF_ENSURE_DYN_SMEM(k_point_mlp, kMlpSmemFloats * 4);
-  k_point_mlp<<<div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(
-      values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat, ldf,
-      feat2, feat1);
+  PointMlpArgs a{values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat,
+                 ldf, feat2, feat1};
+  k_point_mlp<<<div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(a);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_point_mlp_voxkeys(const float* values, const float* points, const float* w1r,
+                                        const float* b1r, const float* w1p, const float* b1p,
+                                        const float* w2r, const float* b2r, const float* w2p,
+                                        const float* b2p, int B, int P, float center, void* feat,
+                                        int ldf, float* feat2, int C, int D, int Ct,
+                                        int32_t* prev_keys, void* X, void* stream_) {
+  if (B <= 0 || P <= 0 || ldf < 216 || (ldf & 1)) return MF_E_BADARG;
+  if (!values || !points || !w1r || !b1r || !w1p || !b1p || !w2r || !b2r || !w2p || !b2p ||
+      !feat || !feat2 || !prev_keys || !X)
+    return MF_E_BADARG;
+  if (C <= 0 || C > 256 || (C & 1) || D <= 0 || (D & 1) || Ct < C) return MF_E_BADARG;
+  if ((long long)B * D * D * D >= (1LL << 30)) return MF_E_TOOLARGE;
+  int n2 = 32;
+  while (n2 < P) n2 <<= 1;
+  if (P > 4096 || ((long long)D * D * D + 1) * n2 >= (1LL << 31)) return MF_E_UNSUPPORTED;
+  const long long NP = (long long)B * P;
+  const int chunks = div_up(P, kRankPts), rank_ctas = B * chunks;
+  MF_ENSURE_DYN_SMEM(k_point_mlp_vox, kMlpSmemFloats * 4);
+  PointMlpArgs a{values, points, w1r, b1r, w1p, b1p, w2r, b2r, w2p, b2p, B, P, center, (bf16*)feat,
+                 ldf, feat2, nullptr};
+  k_point_mlp_vox<<<rank_ctas + div_up(NP, kMlpPts), 256, kMlpSmemFloats * 4, (cudaStream_t)stream_>>>(
+      a, rank_ctas, D, n2, chunks, prev_keys, prev_keys + NP, (bf16*)X, C, Ct);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
@@ -967,11 +1399,37 @@ static int occ_convs_tc(const TIn* gne, const float* w1, const float* b1, const 
   long long BV = (long long)B * D * D * D;
   k_occ_conv1_bf16<TIn><<<div_up(BV, 128), 128, 0, stream>>>(gne, w1, b1, B, D, (bf16*)h1_bf16);
   MF_LAUNCH_CHECK();
-  MF_ENSURE_DYN_SMEM(k_occ_conv2_mma, kOccTileBytes);
-  k_occ_conv2_mma<<<(unsigned)(B * D), 256, kOccTileBytes, stream>>>(
+  MF_ENSURE_DYN_SMEM(k_occ_conv2_mma, kOccConv2Bytes);
+  k_occ_conv2_mma<<<(unsigned)(B * D), 256, kOccConv2Bytes, stream>>>(
       (const bf16*)h1_bf16, w2, b2, B, (bf16*)X, Ct, c_off);
   MF_LAUNCH_CHECK();
   return MF_OK;
+}
+
+template <typename TIn>
+static int occ_fused(const TIn* gne, const float* w1, const float* b1, const float* w2,
+                     const float* b2, int B, int D, void* X, int Ct, int c_off,
+                     cudaStream_t stream) {
+  if (B <= 0 || !gne || !w1 || !b1 || !w2 || !b2 || !X) return MF_E_BADARG;
+  if (D != 32) return MF_E_UNSUPPORTED;
+  if ((Ct & 7) || (c_off & 7) || c_off + 16 > Ct) return MF_E_BADARG;
+  MF_ENSURE_DYN_SMEM(k_occ_fused<TIn>, occ_fused_bytes<TIn>());
+  k_occ_fused<TIn><<<(unsigned)(B * D), 256, occ_fused_bytes<TIn>(), stream>>>(gne, w1, b1, w2, b2, B,
+                                                                      (bf16*)X, Ct, c_off);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_cnn_occ_fused(const float* gne, const float* w1, const float* b1,
+                                const float* w2, const float* b2, int B, int D, void* X, int Ct,
+                                int c_off, void* stream_) {
+  return occ_fused<float>(gne, w1, b1, w2, b2, B, D, X, Ct, c_off, (cudaStream_t)stream_);
+}
+
+extern "C" int mf_cnn_occ_fused_u8(const uint8_t* gne, const float* w1, const float* b1,
+                                   const float* w2, const float* b2, int B, int D, void* X,
+                                   int Ct, int c_off, void* stream_) {
+  return occ_fused<uint8_t>(gne, w1, b1, w2, b2, B, D, X, Ct, c_off, (cudaStream_t)stream_);
 }
 
 extern "C" int mf_cnn_occ_convs_tc(const float* gne, const float* w1, const float* b1,
@@ -995,15 +1453,41 @@ static int voxelize_s2d(const float* feat2, const float* points, int B, int P, i
   if (!points || !prev_keys || !X || ((phases & 2) && !feat2)) return MF_E_BADARG;
   if ((long long)B * D * D * D >= (1LL << 31)) return MF_E_TOOLARGE;
   const int N = B * P;
+  // P <= 4096: rank-based path (prev_keys holds 2N ints: keys | sorted order); else search-based
+  int n2 = 32;
+  while (n2 < P) n2 <<= 1;
+  const bool sorted = P <= 4096 && ((long long)D * D * D + 1) * n2 < (1LL << 31);
+  int32_t* order = prev_keys + N;
   if (phases & 1) {
+    MF_PREFER_MAX_SMEM(k_s2d_clear);
     k_s2d_clear<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(prev_keys, N, C, D, Ct, (bf16*)X);
     MF_LAUNCH_CHECK();
-    k_s2d_keys<<<div_up(N, 256), 256, 0, stream>>>(points, B, P, D, prev_keys);
+    if (sorted) {
+      const int chunks = div_up(P, kRankPts);
+      MF_PREFER_MAX_SMEM(k_s2d_rank);
+      k_s2d_rank<<<B * chunks, 2 * kRankPts, (size_t)((P + 7) & ~7) * 4, stream>>>(
+          points, B, P, D, n2, chunks, prev_keys, order);
+    } else {
+      const size_t tab = (size_t)(((long long)D * D * D + 31) / 32) * 8;     // two bit tables
+      const int use_table = tab <= 200 * 1024;
+      MF_ENSURE_DYN_SMEM(k_s2d_keys, 200 * 1024);
+      k_s2d_keys<<<B, 1024, use_table ? tab : 0, stream>>>(points, B, P, D, prev_keys, use_table);
+    }
     MF_LAUNCH_CHECK();
   }
   if (phases & 2) {
-    k_s2d_scatter<<<div_up((long long)N * 32, 256), 256, 0, stream>>>(feat2, prev_keys, B, P, C, D, Ct,
-                                                                     (bf16*)X);
+    if (sorted) {
+      MF_PREFER_MAX_SMEM(k_s2d_scatter_sorted);
+      k_s2d_scatter_sorted<<<div_up(N, kScatWarps), 256, 0, stream>>>(feat2, prev_keys, order, B, P, C,
+                                                                     D, Ct, (bf16*)X);
+    } else {
+      // shared keys: the (at most 8 / P + 2) objects a CTA's 8 consecutive points belong to
+      const long long span = ((long long)(kScatWarps - 1) / P + 2) * P;
+      if (span * 4 > 160 * 1024) return MF_E_TOOLARGE;
+      MF_ENSURE_DYN_SMEM(k_s2d_scatter, 160 * 1024);
+      k_s2d_scatter<<<div_up(N, kScatWarps), 256, (size_t)span * 4, stream>>>(feat2, prev_keys, B, P, C,
+                                                                             D, Ct, (bf16*)X);
+    }
     MF_LAUNCH_CHECK();
   }
   return MF_OK;
@@ -1069,17 +1553,21 @@ extern "C" int mf_cnn_interp_cl(const void* grid, int s2d, const float* points, 
   if (!s2d && C % kInterpCH == 0 && slab_bytes <= 48 * 1024 && B <= 65535) {
     // small grid: stage a 16-channel slab per CTA, read the grid from L2 once
     dim3 g((unsigned)(C / kInterpCH), (unsigned)B);
+    MF_PREFER_MAX_SMEM(k_interp_cl_staged);
     k_interp_cl_staged<<<g, kInterpThreads, slab_bytes, (cudaStream_t)stream_>>>(
         (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
     MF_LAUNCH_CHECK();
     return MF_OK;
   }
-  if (s2d)
+  if (s2d) {
+    MF_PREFER_MAX_SMEM(k_interp_cl<true>);
     k_interp_cl<true><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
         (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
-  else
+  } else {
+    MF_PREFER_MAX_SMEM(k_interp_cl<false>);
     k_interp_cl<false><<<div_up(tot, 256), 256, 0, (cudaStream_t)stream_>>>(
         (const bf16*)grid, points, B, P, C, D, divisor, (bf16*)feat, ldf, col_off);
+  }
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
@@ -1092,6 +1580,7 @@ extern "C" int mf_cnn_pose(const float* out_rot, const float* out_trans, const f
   if (!out_rot || !out_trans || !out_conf || !points || !class_id || !pitch || !origin || !rot ||
       !trans || !conf)
     return MF_E_BADARG;
+  MF_PREFER_MAX_SMEM(k_pose);
   k_pose<<<div_up((long long)B * P, 128), 128, 0, (cudaStream_t)stream_>>>(
       out_rot, out_trans, out_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf);
   MF_LAUNCH_CHECK();
@@ -1136,6 +1625,7 @@ static int head4_pose(const void* hd3, int ld, const void* w_rot, const float* b
       !class_id || !pitch || !origin || !rot || !trans || !conf)
     return MF_E_BADARG;
   dim3 grid((unsigned)div_up(P, kH4Pts), (unsigned)B);
+  MF_PREFER_MAX_SMEM(k_head4_pose);
   k_head4_pose<<<grid, 256, 0, (cudaStream_t)stream_>>>(
       (const bf16*)hd3, ld, (const bf16*)w_rot, b_rot, (const bf16*)w_trans, b_trans,
       (const bf16*)w_conf, b_conf, points, class_id, pitch, origin, B, P, nfg, rot, trans, conf,

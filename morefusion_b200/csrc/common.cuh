@@ -20,6 +20,10 @@
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember
 // what has been set per device, not per process, so a process that drives several GPUs works.
 // Races between host threads are benign (the attribute call is idempotent).
+// Every kernel of a launch sequence asks for the SAME shared-memory carveout (all shared): an SM
+// has one L1/shared split at a time, and a kernel that prefers a different split than the one
+// the SM is configured for can only start once the SM has drained - which serialises kernels
+// that are meant to overlap on different streams / graph branches.
 #define MF_ENSURE_DYN_SMEM(func, bytes)                                                        \
   do {                                                                                         \
     static int _mf_smem_set[64];                                                               \
@@ -28,7 +32,22 @@
     if (_mf_dev < 0 || _mf_dev >= 64 || _mf_smem_set[_mf_dev] < (int)(bytes)) {                \
       MF_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                        (int)(bytes)));                                         \
+      MF_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout,   \
+                                       cudaSharedmemCarveoutMaxShared));                       \
       if (_mf_dev >= 0 && _mf_dev < 64) _mf_smem_set[_mf_dev] = (int)(bytes);                  \
+    }                                                                                          \
+  } while (0)
+
+// same carveout request for kernels without dynamic shared memory
+#define MF_PREFER_MAX_SMEM(func)                                                               \
+  do {                                                                                         \
+    static bool _mf_car_set[64];                                                               \
+    int _mf_dev = 0;                                                                           \
+    MF_CUDA_TRY(cudaGetDevice(&_mf_dev));                                                      \
+    if (_mf_dev < 0 || _mf_dev >= 64 || !_mf_car_set[_mf_dev]) {                               \
+      MF_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout,   \
+                                       cudaSharedmemCarveoutMaxShared));                       \
+      if (_mf_dev >= 0 && _mf_dev < 64) _mf_car_set[_mf_dev] = true;                           \
     }                                                                                          \
   } while (0)
 

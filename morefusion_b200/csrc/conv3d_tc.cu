@@ -739,6 +739,7 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   else rc = launch<128, 6>(args, grid, stream);
   if (rc) return rc;
   if (splitk > 1) {
+    MF_PREFER_MAX_SMEM(k_splitk_finish);
     k_splitk_finish<<<div_up((long long)p0.M * p0.N / 4, 256), 256, 0, stream>>>(args.e.ws, p0, splitk);
     MF_LAUNCH_CHECK();
   }

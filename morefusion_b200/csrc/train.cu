@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "cnn.cuh"
 
 namespace mf {
 
@@ -254,13 +255,15 @@ k_vox_bwd(const bf16* __restrict__ dx3, long long ldp, const int* __restrict__ k
           float* __restrict__ dfeat2) {
   const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (n >= B * P) return;
-  const int key = keys[n];
+  const int raw = keys[n];
+  const int key = raw < 0 ? -1 : (raw & MF_S2D_KEY_MASK);
   const int b = n / P, lo = b * P, hi = lo + P;
-  int count = 0;
-  if (key >= 0) {
+  int count = raw >= 0 ? 1 : 0;
+  if (raw >= 0 && (raw & MF_S2D_DUP_BIT)) {       // shared voxel: count its points
+    count = 0;
     for (int j0 = lo; j0 < hi; j0 += 32) {
       const int j = j0 + lane;
-      const bool m = j < hi && keys[j] == key;
+      const bool m = j < hi && keys[j] == raw;
       count += __popc(__ballot_sync(0xffffffffu, m));
     }
   }

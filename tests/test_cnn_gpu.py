@@ -117,6 +117,80 @@ def test_fused_voxelize_equals_operator_composition(cuda_device):
     assert torch.equal(x3_of(a, False), ref_a)    # and back
 
 
+@pytest.mark.parametrize("B,P,spread", [(2, 1000, 6.0), (3, 37, 2.0), (1, 5000, 9.0), (2, 4096, 30.0)])
+def test_voxelize_s2d_sorted_and_search_paths_bit_exact(cuda_device, B, P, spread):
+    """mf_cnn_voxelize_s2d (sort-based for P <= 4096, search-based above) against a sequential
+    restatement of average_voxelization_3d (average_voxelization_3d.py:43-118: fp32 sums in
+    ascending point order, IEEE divide) + bf16 rounding + the s2d layout; clustered points (most
+    voxels shared), NaN and out-of-grid points, two consecutive calls (sparse re-zeroing)."""
+    from morefusion_b200 import _lib
+    L = _lib.lib()
+    D, C, Ct = 32, 144, 160
+    J = D // 2 + 1
+    rs = np.random.RandomState(B * 1000 + P)
+    X = torch.zeros(B, J, J, J, 8 * Ct, dtype=torch.bfloat16, device=cuda_device)
+    prev = torch.full((2 * B * P,), -1, dtype=torch.int32, device=cuda_device)
+    for call in range(2):
+        pts = (15.5 + rs.randn(B, 3, P) * spread).astype(np.float32)
+        pts[0, :, 3] = np.nan
+        pts[-1, 0, 5] = 40.0
+        feat = rs.rand(B * P, C).astype(np.float32)
+        ft, pt = torch.as_tensor(feat, device=cuda_device), torch.as_tensor(pts, device=cuda_device)
+        _lib.check(L.mf_cnn_voxelize_s2d(_lib.ptr(ft), _lib.ptr(pt), B, P, C, D, Ct, _lib.ptr(prev),
+                                         _lib.ptr(X), _lib.stream()), "voxelize_s2d")
+        torch.cuda.synchronize()
+        want = np.zeros((B, J, J, J, 8, Ct), np.float32)
+        for b in range(B):
+            ijk = np.round(pts[b]).T                      # round-half-away == roundf for these values
+            sums, cnt = {}, {}
+            for p in range(P):
+                v = ijk[p]
+                if np.isnan(pts[b, :, p]).any() or (v < 0).any() or (v >= D).any():
+                    continue
+                k = tuple(int(t) for t in v)
+                sums[k] = feat[b * P + p].copy() if k not in sums else (sums[k] + feat[b * P + p]).astype(np.float32)
+                cnt[k] = cnt.get(k, 0) + 1
+            for (x, y, z), sm in sums.items():
+                px, py, pz = x + 1, y + 1, z + 1
+                r = ((px & 1) << 2) | ((py & 1) << 1) | (pz & 1)
+                want[b, px >> 1, py >> 1, pz >> 1, r, :C] = sm / np.float32(cnt[(x, y, z)])
+        got = X.reshape(B, J, J, J, 8, Ct).float().cpu().numpy()
+        ref = torch.as_tensor(want).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(got, ref), (call, np.abs(got - ref).max())
+        keys = prev[:B * P].cpu().numpy()
+        assert (keys[3] == -1) and (keys[(B - 1) * P + 5] == -1)
+
+
+@pytest.mark.parametrize("as_bytes", [False, True])
+def test_fused_occ_kernel_bit_identical_to_two_kernel_path(cuda_device, as_bytes):
+    """conv1_occ + conv2_occ in one kernel (conv1 evaluated per consumer slab in shared memory)
+    writes the same bits into the conv3 input as conv1 -> global bf16 -> conv2, for float and
+    byte occupancy grids (boundary slabs x = 0, 1, 30, 31 included: B x 32 CTAs cover them all)."""
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    B = 3
+    w = ocnn.init_weights(21, seed=3)
+    inp = make_inputs(B, seed=9)
+    m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)
+    gne = torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device)
+    if as_bytes:
+        gne = (gne > 0.5).to(torch.uint8)
+
+    def x3_of(fused):
+        m.fused_occ = fused
+        m.forward_features(
+            class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+            values=torch.as_tensor(inp["values"], device=cuda_device),
+            points=torch.as_tensor(inp["points"], device=cuda_device),
+            pitch=inp["pitch"], origin=inp["origin"], grid_nontarget_empty=gne)
+        torch.cuda.synchronize()
+        return m._wbufs[(B, 1000, cuda_device)]["x3"].clone()
+
+    ref = x3_of(False)
+    got = x3_of(True)
+    assert float(ref.reshape(B, -1, 160)[..., 144:].float().abs().max()) > 0
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+
+
 def test_fused_head4_and_concurrent_branches_equal_sequential(cuda_device):
     """Last head layer fused with class selection + pose epilogue, and the two-stream branch
     overlap, give the same poses as the sequential grouped-GEMM + k_pose composition (fp32
