@@ -285,10 +285,22 @@ int mf_gemm_bf16_tc_grouped(const GemmParams* p, int n_groups, void* workspace,
  * [M][N] partial sums when the launch splits K (few output tiles, long K). */
 size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N);
 int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes, void* stream);
-/* profiling hook: device buffer of 16*8 int64 receiving clock64 stamps of CTA 0's roles per work
- * unit (0/1 TMA producer begin/end, 2/3/4 MMA issuer buffer-free / first-operands / committed,
- * 5/6/7 epilogue accumulator-ready / accumulator-drained / stores issued); NULL switches it off */
-int mf_gemm_tc_set_stamps(void* dev_buf);
+/* Extended entry.
+ *  sync   : NULL, or MF_GEMM_TC_SYNC_INTS int32 words owned by the caller, zeroed ONCE before the
+ *           first call (the kernel leaves them zero).  With it, single-group bf16-output GEMMs
+ *           with >= 32 K blocks whose tile count would idle > 5 % of the SMs run "stream-K": the
+ *           tiles x K-blocks space is cut into one equal range per SM, a CTA that starts inside
+ *           a tile parks its fp32 accumulator in `workspace` (one 128 x 256 slot per SM) and the
+ *           tile's first CTA adds the slots in CTA order in its epilogue: every SM does the same
+ *           number of K blocks and there is no separate reduction launch.  Two launches that
+ *           may run concurrently must not share `sync` / `workspace`.
+ *  stamps : NULL, or a device buffer of 16*8 int64 receiving clock64 stamps of CTA 0's roles per
+ *           work unit (0/1 TMA producer begin/end, 2/3/4 MMA issuer buffer-free /
+ *           first-operands / committed, 5/6/7 epilogue accumulator-ready / drained / stored).
+ *  one_shot : non-zero selects the one-tile-per-CTA kernel (comparison baseline). */
+#define MF_GEMM_TC_SYNC_INTS 2048
+int mf_gemm_bf16_tc_ex(const GemmParams* p, int n_groups, void* workspace, size_t workspace_bytes,
+                       int32_t* sync, long long* stamps, int one_shot, void* stream);
 int mf_cnn_interp_cl(const void* grid_bf16, int s2d, const float* points /*[B,3,P]*/, int B,
                      int P, int C, int D, float divisor, void* feat_bf16, int ldf, int col_off,
                      void* stream);

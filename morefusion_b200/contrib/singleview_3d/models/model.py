@@ -124,6 +124,7 @@ class Model(torch.nn.Module):
         self.fused_head4 = True     # last head layer + class select + pose epilogue in one kernel
         self.concurrent_branches = True
         self.fused_occ = True       # conv1_occ + conv2_occ in one kernel (no global intermediate)
+        self.stream_k = True        # conv3 / conv4: equal K-block ranges per SM, reduction in the epilogue
         self._side_streams = {}
         self.launch_log = []
         self.n_launches = 0      # kernels of this library launched so far (bench's gpu_launches)
@@ -205,6 +206,10 @@ class Model(torch.nn.Module):
             out_conf=z(NP, self._n_fg_class, dt=f32),
             bi=torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(P),
             prev_keys=torch.full((2 * NP,), -1, dtype=torch.int32, device=dev),   # keys | sorted order
+            # stream-K GEMMs (conv3 / conv4): flag words (zeroed once, the kernels keep them
+            # zero) and the per-SM fp32 accumulator slots, owned by this buffer set
+            sk_sync=torch.zeros(2048, dtype=torch.int32, device=dev),
+            sk_ws=torch.empty(256 * 128 * 256, dtype=f32, device=dev),
         )
         if self._with_occupancy:
             b["occ1"] = z(B, D ** 3, 8, dt=f32)
@@ -215,15 +220,22 @@ class Model(torch.nn.Module):
 
     # ------------------------------------------------------------------ kernels
     def _gemm(self, L, A, W, bias, out, M, N, K, *, mode=GEMM_LINEAR, lda=0, Do=0, Ci8=0,
-              relu=1, out_mode=OUT_BF16, ldo=0, col_off=0):
+              relu=1, out_mode=OUT_BF16, ldo=0, col_off=0, streamk=None):
         gp = GemmParams(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(out), M, N, K, mode,
                         lda, W.shape[1], Do, Ci8, relu, out_mode, ldo, col_off)
         if self.use_tensor_cores:
-            ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(M, N), A.device)
-            rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.ptr(ws), ws.numel(), _lib.stream())
+            if streamk is not None and self.stream_k:
+                sync, ws = streamk
+                rc = L.mf_gemm_bf16_tc_ex(ctypes.byref(gp), 1, _lib.ptr(ws), ws.numel() * ws.element_size(),
+                                          _lib.ptr(sync), None, 0, _lib.stream())
+                launches = 1
+            else:
+                ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(M, N), A.device)
+                rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.ptr(ws), ws.numel(), _lib.stream())
+                launches = 1 + (1 if (M // 128) * max(N // 256, 1) <= 74 and K >= 4096 else 0)
             if rc == 0:
                 self.launch_log.append(("tc", M, N, K))
-                self.n_launches += 1 + (2 if (M // 128) * max(N // 256, 1) <= 74 and K >= 4096 else 0)
+                self.n_launches += launches
                 return
             if rc != -4:          # MF_E_UNSUPPORTED -> the SIMT kernel covers the shape
                 _lib.check(rc, "gemm_bf16_tc")
@@ -781,7 +793,8 @@ class Model(torch.nn.Module):
         with torch.cuda.device(dev):
             # conv3: 32^3 x Ct -> 16^3 x 256, written straight into conv4's s2d input
             self._gemm(L, buf["x3"], w["conv3/W"], w["conv3/b"], buf["x4"], B * 4096, 256,
-                       64 * Ct, mode=GEMM_CONV_S2D, Do=16, Ci8=8 * Ct, out_mode=OUT_S2D_BF16)
+                       64 * Ct, mode=GEMM_CONV_S2D, Do=16, Ci8=8 * Ct, out_mode=OUT_S2D_BF16,
+                       streamk=(buf["sk_sync"], buf["sk_ws"]))
 
     def _stage_post(self, st, out):
         L, dev, B, P, w, buf = self._ctx(st)
@@ -798,7 +811,7 @@ class Model(torch.nn.Module):
                 # conv4: 16^3 x 256 -> 8^3 x 512
                 self._gemm(L, buf["x4"], w["conv4/W"], w["conv4/b"], buf["h4"], B * 512, 512,
                            64 * 256, mode=GEMM_CONV_S2D, Do=8, Ci8=8 * 256, out_mode=OUT_BF16,
-                           ldo=512)
+                           ldo=512, streamk=(buf["sk_sync"], buf["sk_ws"]))
 
             forked = None
             if self.concurrent_branches:

@@ -241,7 +241,16 @@ k_gemm_tc(const __grid_constant__ TcArgs args) {
 // what the short-K head GEMMs (2-16 K blocks per tile) are dominated by in the one-shot kernel.
 struct TcSched {
   int m_tiles, n_tiles, groups, splitk, n_units;
-  long long* stamps;      // profiling hook (mf_gemm_tc_set_stamps): clock64 per role per unit, CTA 0
+  long long* stamps;      // profiling hook (mf_gemm_bf16_tc_ex): clock64 per role per unit, CTA 0
+  // stream-K (one group, splitk == 1): the tiles x K-blocks iteration space is cut into gridDim.x
+  // equal contiguous ranges, so every SM does the same number of K blocks whatever the tile
+  // count (256 tiles on 148 SMs would otherwise leave 13.5 % of the machine idle in the second
+  // wave).  A CTA whose range starts inside a tile stores that segment's raw fp32 accumulator in
+  // its workspace slot and raises its flags; the CTA that holds the tile's first K block owns
+  // the tile and adds the slots of the CTAs after it, in CTA order, in its epilogue.
+  int streamk;
+  int* sk_flags;          // [gridDim.x][8] (one word per epilogue warp), zero between launches
+  float* sk_ws;           // [gridDim.x][128 x BLOCK_N] fp32
 };
 #define TC_STAMP(slot)                                                        \
   do {                                                                        \
@@ -257,6 +266,55 @@ __device__ __forceinline__ void unit_decode(const TcSched& sc, int u, int& g, in
   mt = r % sc.m_tiles;
   g = r / sc.m_tiles;
 }
+
+// One piece of work of a persistent CTA: K blocks [kb0, kb1) of unit u.
+struct TcSeg {
+  int u, kb0, kb1;
+  int partial;            // stream-K: store the raw accumulator to this CTA's slot (not the output)
+  int peer0, n_peers;     // stream-K owner: add the slots of CTAs peer0 .. peer0 + n_peers - 1
+};
+
+struct TcSegIter {
+  long long pos, hi, W;   // stream-K: position in the tiles x K-blocks space
+  int u;                  // otherwise: next unit
+  __device__ __forceinline__ static long long lo_of(long long W, int c) {
+    return W * c / (int)gridDim.x;
+  }
+  __device__ __forceinline__ TcSegIter(const TcSched& sc, int kb_total) {
+    W = (long long)sc.n_units * kb_total;
+    pos = sc.streamk ? lo_of(W, blockIdx.x) : 0;
+    hi = sc.streamk ? lo_of(W, blockIdx.x + 1) : 0;
+    u = blockIdx.x;
+  }
+  __device__ __forceinline__ bool next(const TcSched& sc, const TcExtra& e, TcSeg& s) {
+    s.partial = 0; s.peer0 = 0; s.n_peers = 0;
+    if (sc.streamk) {
+      if (pos >= hi) return false;
+      const int t = (int)(pos / e.kb_total);
+      const int k0 = (int)(pos - (long long)t * e.kb_total);
+      const long long room = hi - pos;
+      const int k1 = room < (long long)(e.kb_total - k0) ? k0 + (int)room : e.kb_total;
+      s.u = t; s.kb0 = k0; s.kb1 = k1;
+      s.partial = k0 != 0;
+      if (k0 == 0 && k1 < e.kb_total) {
+        const long long tile_end = (long long)(t + 1) * e.kb_total;
+        s.peer0 = blockIdx.x + 1;
+        int c = s.peer0;
+        while (c < (int)gridDim.x && lo_of(W, c) < tile_end) ++c;
+        s.n_peers = c - s.peer0;
+      }
+      pos += k1 - k0;
+      return true;
+    }
+    if (u >= sc.n_units) return false;
+    const int split = u % sc.splitk;
+    s.u = u;
+    s.kb0 = split * e.kb_per_split;
+    s.kb1 = min(s.kb0 + e.kb_per_split, e.kb_total);
+    u += gridDim.x;
+    return true;
+  }
+};
 
 constexpr int TC_P_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / idle, 4-11: epilogue
 constexpr int TC_STG_BYTES = 32 * 128;   // per-epilogue-warp staging tile
@@ -311,13 +369,15 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
     // ===== TMA producer
     int kc = 0;                                        // K blocks issued so far (ring position)
     int it = 0;
-    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
+    TcSegIter iter(sc, e.kb_total);
+    TcSeg seg;
+    for (; iter.next(sc, e, seg); ++it) {
       int g, mt, nt, split;
-      unit_decode(sc, u, g, mt, nt, split);
+      unit_decode(sc, seg.u, g, mt, nt, split);
       const GemmParams& p = args.p[g];
       TC_STAMP(0);
       const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N;
-      const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
+      const int kb0 = seg.kb0, kb1 = seg.kb1;
       int cb = 0, cw = 0, ch = 0, cd = 0;
       if (p.mode == GEMM_CONV_S2D) {
         int Do = p.Do;
@@ -349,10 +409,10 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                                ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
     int kc = 0, it = 0;
-    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
-      int g, mt, nt, split;
-      unit_decode(sc, u, g, mt, nt, split);
-      const int kb0 = split * e.kb_per_split, kb1 = min(kb0 + e.kb_per_split, e.kb_total);
+    TcSegIter iter(sc, e.kb_total);
+    TcSeg seg;
+    for (; iter.next(sc, e, seg); ++it) {
+      const int kb0 = seg.kb0, kb1 = seg.kb1;
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4, 32);    // epilogue has drained this buffer
@@ -384,9 +444,15 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
     constexpr int EPI_COLS = BLOCK_N / 2, NCH = EPI_COLS / 32;
     const uint32_t stg_s = smem_u32(out_stage + (size_t)(warp - 4) * TC_STG_BYTES);  // 32 rows x 128 B
     int it = 0;
-    for (int u = blockIdx.x; u < sc.n_units; u += gridDim.x, ++it) {
+    TcSegIter iter(sc, e.kb_total);
+    TcSeg seg;
+    // stream-K slots: this warp's 32 rows x EPI_COLS columns, stored chunk-major / lane-minor so
+    // that a warp-wide float4 access is 512 contiguous bytes
+    const int wslot = warp - 4;
+    constexpr long long SLOT_FLOATS = (long long)TC_BLOCK_M * BLOCK_N;
+    for (; iter.next(sc, e, seg); ++it) {
       int g, mt, nt, split;
-      unit_decode(sc, u, g, mt, nt, split);
+      unit_decode(sc, seg.u, g, mt, nt, split);
       const GemmParams& p = args.p[g];
       const int m0 = mt * TC_BLOCK_M, n0 = nt * BLOCK_N + hsel * EPI_COLS;
       const int acc = it & 1;
@@ -400,7 +466,43 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
       const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N + hsel * EPI_COLS) +
                             ((uint32_t)(q * 32) << 16);
       const bool coalesced_bf16 = !(p.N & 31) && e.splitk == 1 && p.out_mode != OUT_F32;
-      if (coalesced_bf16) {
+      if (seg.partial) {
+        // stream-K: this CTA holds a later K range of a tile another CTA owns
+        float4* slot = reinterpret_cast<float4*>(sc.sk_ws + (long long)blockIdx.x * SLOT_FLOATS +
+                                                 (long long)wslot * 32 * EPI_COLS);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            slot[(c * 8 + j) * 32 + lane] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(sc.sk_flags + blockIdx.x * 8 + wslot),
+                       "r"(1) : "memory");
+      } else if (coalesced_bf16) {
+        if (seg.n_peers > 0) {
+          // wait for the same-numbered epilogue warp of every peer (they ran these K blocks at the
+          // START of their range, this CTA reaches the tile at the END of its own: normally no wait)
+          if (lane == 0) {
+            for (int pi = 0; pi < seg.n_peers; ++pi) {
+              const int* f = sc.sk_flags + (seg.peer0 + pi) * 8 + wslot;
+              int v = 0;
+              for (long long spin = 0; spin < (1LL << 24); ++spin) {
+                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v) break;
+                __nanosleep(64);
+              }
+              if (!v && e.err) atomicExch(e.err, 7);
+            }
+          }
+          __syncwarp();
+        }
         // bf16 outputs.  Chunks of 32 columns: the tcgen05.ld of chunk c+1 is in flight while
         // chunk c gets bias/ReLU/convert.  Two chunks (64 columns = 128 B per row) are staged in
         // this warp's XOR-swizzled shared-memory tile and written out with row-contiguous
@@ -422,6 +524,18 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
         auto process = [&](uint32_t (&r)[32], int c) {
           const int n = n0 + c * 32;
           if (n < Nn) {
+            for (int pi = 0; pi < seg.n_peers; ++pi) {      // stream-K: later K ranges of this tile
+              const float4* ps = reinterpret_cast<const float4*>(
+                  sc.sk_ws + (long long)(seg.peer0 + pi) * SLOT_FLOATS + (long long)wslot * 32 * EPI_COLS);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 a = __ldcg(ps + (c * 8 + j) * 32 + lane);
+                r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + a.x);
+                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a.y);
+                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a.z);
+                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a.w);
+              }
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -474,6 +588,11 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
           if (c + 2 < NCH) tmem_ld_32x32_issue(tacc + (uint32_t)((c + 2) * 32), ra);
           process(rb, c + 1);
           if (c + 2 < NCH) tmem_ld_wait(ra);
+        }
+        if (seg.n_peers > 0) {                  // slots consumed: re-arm the flags for the next launch
+          __syncwarp();
+          if (lane == 0)
+            for (int pi = 0; pi < seg.n_peers; ++pi) sc.sk_flags[(seg.peer0 + pi) * 8 + wslot] = 0;
         }
       } else {
         int pN = p.N, pM = p.M, prelu = p.relu, pmode = p.out_mode;
@@ -597,12 +716,6 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
   return r == CUDA_SUCCESS ? MF_OK : MF_E_BADARG;
 }
 
-static long long* g_tc_stamps = nullptr;
-extern "C" int mf_gemm_tc_set_stamps(void* dev_buf) {
-  g_tc_stamps = reinterpret_cast<long long*>(dev_buf);
-  return MF_OK;
-}
-
 template <int BLOCK_N, int STAGES>
 static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t stream) {
   constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
@@ -610,19 +723,10 @@ static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t
   int n_sm = 148, dev = 0;
   MF_CUDA_TRY(cudaGetDevice(&dev));
   MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  int grid = sc.n_units < n_sm ? sc.n_units : n_sm;
+  int grid = (sc.n_units < n_sm && !sc.streamk) ? sc.n_units : n_sm;
   k_gemm_tc_persistent<BLOCK_N, STAGES><<<grid, TC_P_THREADS, smem, stream>>>(args, sc);
   MF_LAUNCH_CHECK();
   return MF_OK;
-}
-
-static bool persistent_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MF_GEMM_PERSISTENT");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
 }
 
 template <int BLOCK_N, int STAGES>
@@ -684,11 +788,14 @@ static int make_maps(const GemmParams& p, int BN, CUtensorMap* tmA, CUtensorMap*
 using namespace mf;
 
 extern "C" size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N) {
-  return (size_t)M * N * 4 * 4 + 256;      // up to 4 split-K slices
+  size_t splitk = (size_t)M * N * 4 * 4 + 256;              // up to 4 split-K slices
+  size_t streamk = (size_t)256 * TC_BLOCK_M * 256 * 4;      // one 128 x 256 fp32 slot per SM (<= 256)
+  return splitk > streamk ? splitk : streamk;
 }
 
-extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void* workspace,
-                                       size_t workspace_bytes, void* stream_) {
+extern "C" int mf_gemm_bf16_tc_ex(const GemmParams* hp, int n_groups, void* workspace,
+                                  size_t workspace_bytes, int32_t* sync, long long* stamps,
+                                  int one_shot, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!hp || n_groups < 1 || n_groups > TC_MAX_GROUPS) return MF_E_BADARG;
   TcArgs args;
@@ -715,7 +822,20 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   const int m_tiles = (p0.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (maxN + BN - 1) / BN;
   int splitk = 1;
   const int tiles = m_tiles * n_tiles * n_groups;
-  if (n_groups == 1 && tiles <= 74 && args.e.kb_total >= 64 && p0.N % 32 == 0) {
+  int n_sm = 148, dev = 0;
+  MF_CUDA_TRY(cudaGetDevice(&dev));
+  MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  // stream-K when the caller provides the flag words and whole-tile scheduling would idle > 5 %
+  // of the SMs (or there are fewer tiles than SMs) on a long-K problem with bf16 output
+  bool streamk = false;
+  if (sync && !one_shot && n_groups == 1 && p0.N % 32 == 0 && p0.out_mode != OUT_F32 &&
+      args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8) {
+    const int waves = (tiles + n_sm - 1) / n_sm;
+    const double busy = (double)tiles / ((double)waves * n_sm);
+    const size_t need = (size_t)n_sm * TC_BLOCK_M * BN * 4;
+    if (busy < 0.95 && workspace && workspace_bytes >= need) streamk = true;
+  }
+  if (!streamk && n_groups == 1 && tiles <= 74 && args.e.kb_total >= 64 && p0.N % 32 == 0) {
     splitk = 148 / tiles;
     if (splitk > 4) splitk = 4;
     if (splitk < 1) splitk = 1;
@@ -730,9 +850,9 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
   }
   dim3 grid(n_tiles, m_tiles, splitk * n_groups);
   int rc;
-  if (persistent_enabled()) {
+  if (!one_shot) {
     TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk,
-               g_tc_stamps};
+               stamps, streamk ? 1 : 0, sync, (float*)workspace};
     if (BN == 256) rc = launch_persistent<256, 4>(args, sc, stream);
     else rc = launch_persistent<128, 6>(args, sc, stream);
   } else if (BN == 256) rc = launch<256, 4>(args, grid, stream);
@@ -744,6 +864,11 @@ extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void*
     MF_LAUNCH_CHECK();
   }
   return MF_OK;
+}
+
+extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  return mf_gemm_bf16_tc_ex(hp, n_groups, workspace, workspace_bytes, nullptr, nullptr, 0, stream_);
 }
 
 extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t workspace_bytes,

@@ -57,10 +57,10 @@ for name, M, N, K in SHAPES:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 20
     tf = 2.0 * M * N * K / us / 1e6
-    L.mf_gemm_tc_set_stamps(_lib.ptr(stamps))
-    call()
+    rc = L.mf_gemm_bf16_tc_ex(ctypes.byref(gp), 1, _lib.ptr(ws), ws.numel(), None, _lib.ptr(stamps), 0,
+                              _lib.stream())
+    assert rc == 0, rc
     torch.cuda.synchronize()
-    L.mf_gemm_tc_set_stamps(None)
     st = stamps.cpu().view(16, 8)
     t0 = int(st[0, 0])
     rows = []

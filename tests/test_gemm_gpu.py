@@ -22,6 +22,13 @@ def _call(kind, A, W, bias, out, M, N, K, **kw):
     if kind == "tc":
         ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(M, N), A.device)
         rc = L.mf_gemm_bf16_tc(ctypes.byref(gp), _lib.ptr(ws), ws.numel(), _lib.stream())
+    elif kind in ("sk", "one_shot"):
+        # stream-K: caller-owned flag words (zeroed once, reused across calls) + slots
+        sync = kw["sync"] if "sync" in kw else None
+        ws = torch.empty(L.mf_gemm_bf16_tc_workspace_bytes(M, N), dtype=torch.uint8, device=A.device)
+        ws.fill_(0x7F)                       # garbage in the slots must not matter
+        rc = L.mf_gemm_bf16_tc_ex(ctypes.byref(gp), 1, _lib.ptr(ws), ws.numel(), _lib.ptr(sync), None,
+                                  1 if kind == "one_shot" else 0, _lib.stream())
     else:
         rc = L.mf_gemm_bf16_simt(ctypes.byref(gp), _lib.stream())
     torch.cuda.synchronize()
@@ -79,6 +86,63 @@ def test_tc_conv_s2d(cuda_device, Do, Ci, Co, B):
         out2 = torch.zeros(B, J2, J2, J2, 8 * N, device=cuda_device, dtype=torch.bfloat16)
         rc = _call("tc", X, Wg, bias, out2, M, N, K, mode=1, Do=Do, Ci8=8 * Ci, out_mode=2)
         assert rc == 0
+        h = out.reshape(B, Do, Do, Do, N).permute(0, 4, 1, 2, 3)
+        hp = torch.nn.functional.pad(h, (1, 1, 1, 1, 1, 1))
+        want = hp.reshape(B, N, J2, 2, J2, 2, J2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J2, J2, J2, 8 * N)
+        assert torch.equal(out2, want.contiguous())
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 8192), (8000, 512, 2048), (32768, 256, 2048),
+                                   (2304, 256, 4096), (640, 256, 16384)])
+def test_tc_stream_k_linear(cuda_device, M, N, K):
+    """Stream-K scheduling (equal K-block ranges per SM, partial accumulators parked in the
+    workspace, reduction in the owning CTA's epilogue) against the fp32 reference, three calls
+    on the same flag words (the kernel must leave them zero)."""
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=cuda_device).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=cuda_device) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda_device)
+    sync = torch.zeros(2048, dtype=torch.int32, device=cuda_device)
+    ref = torch.relu(A.float() @ W.float().T + bias)
+    for _ in range(3):
+        out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+        rc = _call("sk", A, W, bias, out, M, N, K, lda=K, sync=sync)
+        assert rc == 0
+        err = (out.float() - ref).abs().max().item()
+        assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+        assert int(sync.abs().sum()) == 0
+    one = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    assert _call("one_shot", A, W, bias, one, M, N, K, lda=K, sync=None) == 0
+    # same products, different fp32 summation split: within one bf16 ulp of the one-shot kernel
+    torch.testing.assert_close(out.float(), one.float(), rtol=2 ** -7, atol=2e-2)
+
+
+@pytest.mark.parametrize("Do,Ci,Co,B", [(16, 160, 256, 8), (8, 256, 512, 8), (16, 160, 256, 3)])
+def test_tc_stream_k_conv_s2d(cuda_device, Do, Ci, Co, B):
+    """conv3 / conv4 shapes of the model (256 and 64 tiles on 148 SMs) under stream-K, in both
+    output layouts, against the whole-tile schedule of the same kernel."""
+    from morefusion_b200.contrib.singleview_3d.models.model import pack_conv_k4s2_weight
+    torch.manual_seed(1)
+    D, J = 2 * Do, Do + 1
+    x = torch.randn(B, Ci, D, D, D, device=cuda_device).to(torch.bfloat16)
+    Wc = (torch.randn(Co, Ci, 4, 4, 4, device=cuda_device) / (Ci * 64) ** 0.5)
+    bias = torch.randn(Co, device=cuda_device)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1, 1, 1))
+    X = xp.reshape(B, Ci, J, 2, J, 2, J, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J, J, J, 8 * Ci).contiguous()
+    Wg = pack_conv_k4s2_weight(Wc)
+    M, N, K = B * Do ** 3, Co, 64 * Ci
+    sync = torch.zeros(2048, dtype=torch.int32, device=cuda_device)
+    ref = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+    assert _call("tc", X, Wg, bias, ref, M, N, K, mode=1, Do=Do, Ci8=8 * Ci) == 0
+    for _ in range(2):
+        out = torch.zeros(M, N, device=cuda_device, dtype=torch.bfloat16)
+        assert _call("sk", X, Wg, bias, out, M, N, K, mode=1, Do=Do, Ci8=8 * Ci, sync=sync) == 0
+        torch.testing.assert_close(out.float(), ref.float(), rtol=2 ** -7, atol=2e-2)
+        assert int(sync.abs().sum()) == 0
+    if Do == 16:
+        J2 = Do // 2 + 1
+        out2 = torch.zeros(B, J2, J2, J2, 8 * N, device=cuda_device, dtype=torch.bfloat16)
+        assert _call("sk", X, Wg, bias, out2, M, N, K, mode=1, Do=Do, Ci8=8 * Ci, out_mode=2, sync=sync) == 0
         h = out.reshape(B, Do, Do, Do, N).permute(0, 4, 1, 2, 3)
         hp = torch.nn.functional.pad(h, (1, 1, 1, 1, 1, 1))
         want = hp.reshape(B, N, J2, 2, J2, 2, J2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J2, J2, J2, 8 * N)
