@@ -287,8 +287,8 @@ size_t mf_gemm_bf16_tc_workspace_bytes(int M, int N);
 int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes, void* stream);
 /* Extended entry.
  *  sync   : NULL, or MF_GEMM_TC_SYNC_INTS int32 words owned by the caller, zeroed ONCE before the
- *           first call (the kernel leaves them zero).  With it, single-group bf16-output GEMMs
- *           with >= 32 K blocks whose tile count would idle > 5 % of the SMs run "stream-K": the
+ *           first call (the kernel leaves them zero).  With it, bf16-output GEMMs (grouped or
+ *           not) whose tile count would idle > 5 % of the SMs run "stream-K": the
  *           tiles x K-blocks space is cut into one equal range per SM, a CTA that starts inside
  *           a tile parks its fp32 accumulator in `workspace` (one 128 x 256 slot per SM) and the
  *           tile's first CTA adds the slots in CTA order in its epilogue: every SM does the same
@@ -301,6 +301,15 @@ int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes
 #define MF_GEMM_TC_SYNC_INTS 2048
 int mf_gemm_bf16_tc_ex(const GemmParams* p, int n_groups, void* workspace, size_t workspace_bytes,
                        int32_t* sync, long long* stamps, int one_shot, void* stream);
+/* Layers 1-3 of the three pose heads (model.py:239-254) as ONE persistent launch.  layers[0] =
+ * the three first layers side by side (N = 3 x 640), layers[1..3] = conv2_{rot,trans,conf}
+ * reading their column block of layer 0's output, layers[4..6] = conv3_* reading layers[1..3]'s
+ * outputs; all GEMM_LINEAR, OUT_BF16, same M.  Tiles of later layers start as soon as the
+ * 128-row tiles they read are stored (global arrival counters), so the three layers share one
+ * wave structure and there are no launch gaps.  sync: MF_HEADS_SYNC_INTS int32 words owned by the
+ * caller, zeroed ONCE (never reset afterwards: an epoch word makes the counters monotonic). */
+#define MF_HEADS_SYNC_INTS 4096
+int mf_cnn_heads_tc(const GemmParams* layers, int n_layers /* 7 */, int32_t* sync, void* stream);
 int mf_cnn_interp_cl(const void* grid_bf16, int s2d, const float* points /*[B,3,P]*/, int B,
                      int P, int C, int D, float divisor, void* feat_bf16, int ldf, int col_off,
                      void* stream);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mf_gemm_bf16_tc_workspace_bytes": (c_sz, [c_i, c_i]),
     "mf_gemm_bf16_tc": (c_i, [c_p, c_p, c_sz, c_p]),
     "mf_gemm_bf16_tc_ex": (c_i, [c_p, c_i, c_p, c_sz, c_p, c_p, c_i, c_p]),
+    "mf_cnn_heads_tc": (c_i, [c_p, c_i, c_p, c_p]),
     "mf_gemm_bf16_simt_grouped": (c_i, [c_p, c_i, c_p]),
     "mf_gemm_bf16_tc_grouped": (c_i, [c_p, c_i, c_p, c_sz, c_p]),
     "mf_cnn_interp_cl": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_i, c_p]),

@@ -125,6 +125,7 @@ class Model(torch.nn.Module):
         self.concurrent_branches = True
         self.fused_occ = True       # conv1_occ + conv2_occ in one kernel (no global intermediate)
         self.stream_k = True        # conv3 / conv4: equal K-block ranges per SM, reduction in the epilogue
+        self.fused_heads = True     # head layers 1-3 (7 GEMMs) as one persistent launch with tile-level dependencies
         self._side_streams = {}
         self.launch_log = []
         self.n_launches = 0      # kernels of this library launched so far (bench's gpu_launches)
@@ -209,6 +210,7 @@ class Model(torch.nn.Module):
             # stream-K GEMMs (conv3 / conv4): flag words (zeroed once, the kernels keep them
             # zero) and the per-SM fp32 accumulator slots, owned by this buffer set
             sk_sync=torch.zeros(2048, dtype=torch.int32, device=dev),
+            hd_sync=torch.zeros(4096, dtype=torch.int32, device=dev),      # fused heads: epoch + counters
             sk_ws=torch.empty(256 * 128 * 256, dtype=f32, device=dev),
         )
         if self._with_occupancy:
@@ -243,7 +245,7 @@ class Model(torch.nn.Module):
         self.n_launches += 1
         _lib.check(L.mf_gemm_bf16_simt(ctypes.byref(gp), _lib.stream()), "gemm_bf16_simt")
 
-    def _gemm_grouped(self, L, specs):
+    def _gemm_grouped(self, L, specs, streamk=None):
         """Up to 3 GEMMs in one launch; tcgen05 when the shapes match and qualify, else SIMT."""
         n = len(specs)
         arr = (GemmParams * n)()
@@ -257,8 +259,13 @@ class Model(torch.nn.Module):
                 sp.get("out_mode", OUT_BF16), sp.get("ldo", 0), sp.get("col_off", 0))
         if self.use_tensor_cores:
             dev = specs[0]["A"].device
-            ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(specs[0]["M"], specs[0]["N"]), dev)
-            rc = L.mf_gemm_bf16_tc_grouped(arr, n, _lib.ptr(ws), ws.numel(), _lib.stream())
+            if streamk is not None and self.stream_k:
+                sync, ws = streamk
+                rc = L.mf_gemm_bf16_tc_ex(arr, n, _lib.ptr(ws), ws.numel() * ws.element_size(),
+                                          _lib.ptr(sync), None, 0, _lib.stream())
+            else:
+                ws = _util.workspace(L.mf_gemm_bf16_tc_workspace_bytes(specs[0]["M"], specs[0]["N"]), dev)
+                rc = L.mf_gemm_bf16_tc_grouped(arr, n, _lib.ptr(ws), ws.numel(), _lib.stream())
             if rc == 0:
                 self.n_launches += 1
                 return
@@ -266,6 +273,31 @@ class Model(torch.nn.Module):
                 _lib.check(rc, "gemm_bf16_tc_grouped")
         _lib.check(L.mf_gemm_bf16_simt_grouped(arr, n, _lib.stream()), "gemm_bf16_simt_grouped")
         self.n_launches += 1
+
+    def _heads_fused(self, L, buf, w, NP):
+        """Layers 1-3 of the three heads as one persistent launch (mf_cnn_heads_tc).  Returns
+        False when the library declines the shapes (the caller then runs the three launches)."""
+        heads = ("rot", "trans", "conf")
+        arr = (GemmParams * 7)()
+        keep = [buf["hd1"][:, i * 640:] for i in range(3)] + [buf["hd2"][:, i * 256:] for i in range(3)]
+        arr[0] = GemmParams(_lib.ptr(buf["feat"]), _lib.ptr(w["head1/W"]), _lib.ptr(w["head1/b"]),
+                            _lib.ptr(buf["hd1"]), NP, 1920, 984, GEMM_LINEAR, FEAT_LD,
+                            w["head1/W"].shape[1], 0, 0, 1, OUT_BF16, 1920, 0)
+        for i, h in enumerate(heads):
+            W2, W3 = w[f"conv2_{h}/W"], w[f"conv3_{h}/W"]
+            arr[1 + i] = GemmParams(_lib.ptr(keep[i]), _lib.ptr(W2), _lib.ptr(w[f"conv2_{h}/b"]),
+                                    _lib.ptr(buf["hd2"]), NP, 256, 640, GEMM_LINEAR, 1920, W2.shape[1],
+                                    0, 0, 1, OUT_BF16, 768, i * 256)
+            arr[4 + i] = GemmParams(_lib.ptr(keep[3 + i]), _lib.ptr(W3), _lib.ptr(w[f"conv3_{h}/b"]),
+                                    _lib.ptr(buf["hd3"]), NP, 128, 256, GEMM_LINEAR, 768, W3.shape[1],
+                                    0, 0, 1, OUT_BF16, 384, i * 128)
+        rc = L.mf_cnn_heads_tc(arr, 7, _lib.ptr(buf["hd_sync"]), _lib.stream())
+        if rc == -4:
+            return False
+        _lib.check(rc, "heads_tc")
+        self.launch_log.append(("tc", NP, 1920, 984))
+        self.n_launches += 1
+        return True
 
     # ------------------------------------------------------------------ reference API
     def _keep_indices(self, n_point):
@@ -836,18 +868,19 @@ class Model(torch.nn.Module):
             if forked:
                 forked[0].wait_stream(forked[1])
             # heads (model.py:239-254)
-            self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
-                       lda=FEAT_LD, ldo=1920)
             heads = ("rot", "trans", "conf")
-            # layers 2-4 of the three heads: one grouped launch per layer (grid.z = head)
-            self._gemm_grouped(L, [dict(
-                A=buf["hd1"][:, i * 640:], W=w[f"conv2_{h}/W"], bias=w[f"conv2_{h}/b"],
-                out=buf["hd2"], M=NP, N=256, K=640, lda=1920, ldo=768, col_off=i * 256)
-                for i, h in enumerate(heads)])
-            self._gemm_grouped(L, [dict(
-                A=buf["hd2"][:, i * 256:], W=w[f"conv3_{h}/W"], bias=w[f"conv3_{h}/b"],
-                out=buf["hd3"], M=NP, N=128, K=256, lda=768, ldo=384, col_off=i * 128)
-                for i, h in enumerate(heads)])
+            if not (self.fused_heads and self.use_tensor_cores and self._heads_fused(L, buf, w, NP)):
+                self._gemm(L, buf["feat"], w["head1/W"], w["head1/b"], buf["hd1"], NP, 1920, 984,
+                           lda=FEAT_LD, ldo=1920)
+                # layers 2-4 of the three heads: one grouped launch per layer (grid.z = head)
+                self._gemm_grouped(L, [dict(
+                    A=buf["hd1"][:, i * 640:], W=w[f"conv2_{h}/W"], bias=w[f"conv2_{h}/b"],
+                    out=buf["hd2"], M=NP, N=256, K=640, lda=1920, ldo=768, col_off=i * 256)
+                    for i, h in enumerate(heads)])
+                self._gemm_grouped(L, [dict(
+                    A=buf["hd2"][:, i * 256:], W=w[f"conv3_{h}/W"], bias=w[f"conv3_{h}/b"],
+                    out=buf["hd3"], M=NP, N=128, K=256, lda=768, ldo=384, col_off=i * 128)
+                    for i, h in enumerate(heads)])
             if self.fused_head4 and getattr(self, "_raw8", None) is not None:
                 # training forward: also keep the 8 selected pre-activation outputs
                 _lib.check(L.mf_cnn_head4_pose_train(

@@ -662,6 +662,279 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
   }
 }
 
+// ------------------------------------------------------------------ the pose heads as ONE launch
+// Layers 1-3 of the three heads (model.py:239-254: head1 = the three first layers side by side,
+// 3 x conv2_*, 3 x conv3_*) are 7 GEMMs whose only coupling is per 128-row tile: a layer-2 tile
+// needs the layer-1 tiles of its rows, a layer-3 tile the layer-2 tile of its head and rows.  As
+// separate launches each layer ends in a partially filled wave plus a launch gap (36.5 + 16.1 +
+// 10.0 us for 33 us of tensor work).  Here the 504 + 189 + 189 tiles are ONE unit list of a
+// persistent kernel: units are dealt round-robin in list order, a unit's TMA producer waits for
+// a global arrival counter of its input tile(s) before the first load, the epilogue warps bump
+// the counter of their output tile after their stores.  A unit only ever waits for units earlier
+// in the list and every CTA walks the list in order, so there is no cycle.
+// Counters are never reset: every launch reads an epoch word at start (thresholds = (epoch + 1) x
+// arrivals per launch) and the last CTA to finish bumps it, so CUDA-graph replays need no memset.
+constexpr int HD_LAYERS = 7;
+struct HeadsArgs {
+  CUtensorMap tmA[HD_LAYERS];
+  CUtensorMap tmW[HD_LAYERS];
+  GemmParams p[HD_LAYERS];
+  int bn[HD_LAYERS];            // N tile: 256 or 128
+  int kb[HD_LAYERS];            // K blocks
+  int n_tiles[HD_LAYERS];
+  int unit_begin[HD_LAYERS + 1];
+  int dep_base[HD_LAYERS];      // counter (per m tile) to wait on, -1 = none
+  int dep_target[HD_LAYERS];    // its arrivals per launch
+  int sig_base[HD_LAYERS];      // counter (per m tile) to bump, -1 = none
+  int m_tiles, n_units;
+  int* sync;                    // [0] epoch, [1] finished CTAs, [16 ..] counters
+  int* err;
+};
+
+__device__ __forceinline__ void hd_decode(const HeadsArgs& a, int u, int& q, int& mt, int& nt) {
+  q = 0;
+#pragma unroll
+  for (int i = 1; i < HD_LAYERS; ++i) q += (u >= a.unit_begin[i]) ? 1 : 0;
+  const int r = u - a.unit_begin[q];
+  nt = r % a.n_tiles[q];
+  mt = r / a.n_tiles[q];
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(TC_P_THREADS, 1)
+k_heads_tc(const __grid_constant__ HeadsArgs args) {
+  constexpr int MAX_N = 256;
+  constexpr int STAGE_BYTES = TC_A_BYTES + MAX_N * TC_BLOCK_K * 2;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* out_stage = smem + (size_t)STAGES * STAGE_BYTES;   // 8 x TC_STG_BYTES
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ int epoch_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    int ep;
+    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(ep) : "l"(args.sync) : "memory");
+    epoch_slot = ep;
+#pragma unroll
+    for (int q = 0; q < HD_LAYERS; ++q) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmA[q])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmW[q])) : "memory");
+    }
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 8);
+    mbar_init(&tmem_empty_bar[1], 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)(2 * MAX_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const unsigned epoch1 = (unsigned)epoch_slot + 1u;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer
+    int kc = 0;
+    for (int u = blockIdx.x; u < args.n_units; u += gridDim.x) {
+      int q, mt, nt;
+      hd_decode(args, u, q, mt, nt);
+      if (args.dep_base[q] >= 0) {
+        // input rows of this tile are written by earlier units (other SMs, generic-proxy stores)
+        const int* c = args.sync + 16 + args.dep_base[q] + mt;
+        const unsigned target = epoch1 * (unsigned)args.dep_target[q];
+        long long t0 = clock64();
+        for (;;) {
+          int v;
+          asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+          if ((int)((unsigned)v - target) >= 0) break;
+          __nanosleep(100);
+          if (clock64() - t0 > 4000000000LL) {
+            if (args.err) atomicExch(args.err, 9);
+            __threadfence_system();
+            __trap();
+          }
+        }
+        // order the acquired (generic-proxy) view before this thread's async-proxy (TMA) reads
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      const int m0 = mt * TC_BLOCK_M, n0 = nt * args.bn[q];
+      const uint32_t bytes = (uint32_t)(TC_A_BYTES + args.bn[q] * TC_BLOCK_K * 2);
+      const int kbn = args.kb[q];
+      for (int kb = 0; kb < kbn; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, args.err, 1, 64);
+        mbar_expect_tx(&full_bar[s], bytes);
+        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        tma_load_2d(sa, &args.tmA[q], &full_bar[s], kb * TC_BLOCK_K, m0);
+        tma_load_2d(sa + TC_A_BYTES, &args.tmW[q], &full_bar[s], kb * TC_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer
+    int kc = 0, it = 0;
+    for (int u = blockIdx.x; u < args.n_units; u += gridDim.x, ++it) {
+      int q, mt, nt;
+      hd_decode(args, u, q, mt, nt);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(args.bn[q] >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1, args.err, 4, 32);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MAX_N);
+      const int kbn = args.kb[q];
+      for (int kb = 0; kb < kbn; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, args.err, 2, 20);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = make_sw128_desc(sa);
+        const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+          umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 8 warps; warp w reads TMEM lane quarter w%4 and column half (w-4)/4
+    const int q4 = warp & 3, hsel = (warp - 4) >> 2;
+    const uint32_t stg_s = smem_u32(out_stage + (size_t)(warp - 4) * TC_STG_BYTES);
+    int it = 0;
+    for (int u = blockIdx.x; u < args.n_units; u += gridDim.x, ++it) {
+      int q, mt, nt;
+      hd_decode(args, u, q, mt, nt);
+      const GemmParams& p = args.p[q];
+      const int epi_cols = args.bn[q] >> 1, nch = epi_cols >> 5;
+      const int m0 = mt * TC_BLOCK_M, n0 = nt * args.bn[q] + hsel * epi_cols;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], aph, args.err, 3, 128);
+      tcgen05_fence_after();
+      const int m = m0 + q4 * 32 + lane;
+      const bool row_ok = m < p.M;
+      const long long roff = row_ok ? (long long)m * p.ldo + p.col_off : 0;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * MAX_N + hsel * epi_cols) +
+                            ((uint32_t)(q4 * 32) << 16);
+      const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+      int relu_i = p.relu, Nn = p.N;
+      const float* bias = p.bias;
+      bf16* outp = reinterpret_cast<bf16*>(p.out);
+      asm volatile("" : "+r"(relu_i), "+r"(Nn), "+l"(bias), "+l"(outp));
+      const bool relu = relu_i != 0;
+      long long rofs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rofs[i] = __shfl_sync(0xffffffffu, roff, i * 4 + (lane >> 3));
+      uint32_t ra[32], rb[32];
+      auto process = [&](uint32_t (&r)[32], int c) {
+        const int n = n0 + c * 32;
+        if (n < Nn) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bq = bias ? __ldg(reinterpret_cast<const float4*>(bias + n) + j)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 uu;
+            if (relu) {
+              uu.x = pack_bf16x2_relu(v[8 * j + 0], v[8 * j + 1]);
+              uu.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
+              uu.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]);
+              uu.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
+            } else {
+              uu.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              uu.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              uu.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              uu.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            }
+            const int piece = ((c & 1) * 4 + j) ^ (lane & 7);
+            sts_v4(stg_s + lane * 128 + piece * 16, uu);
+          }
+        }
+        if (c & 1) {
+          __syncwarp();
+          const int ncol = n0 + (c - 1) * 32 + (lane & 7) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            const uint4 uu = lds_v4(stg_s + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+            if (((okmask >> row) & 1u) && ncol < Nn)
+              *reinterpret_cast<uint4*>(outp + rofs[i] + ncol) = uu;
+          }
+          __syncwarp();
+        }
+      };
+      tmem_ld_32x32_issue(tacc, ra);
+      tmem_ld_wait(ra);
+#pragma unroll 1
+      for (int c = 0; c < nch; c += 2) {
+        tmem_ld_32x32_issue(tacc + (uint32_t)((c + 1) * 32), rb);
+        process(ra, c);
+        tmem_ld_wait(rb);
+        if (c + 2 < nch) tmem_ld_32x32_issue(tacc + (uint32_t)((c + 2) * 32), ra);
+        process(rb, c + 1);
+        if (c + 2 < nch) tmem_ld_wait(ra);
+      }
+      // accumulator drained: hand the buffer back to the MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc]))
+                     : "memory");
+      // this warp's part of the output tile is stored: publish it to the consumers of the tile
+      if (args.sig_base[q] >= 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(args.sync + 16 + args.sig_base[q] + mt, 1);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(2 * MAX_N))
+                 : "memory");
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int d = atomicAdd(args.sync + 1, 1);
+    if (d == (int)gridDim.x - 1) {          // last CTA: next launch gets the next epoch
+      args.sync[1] = 0;
+      __threadfence();
+      atomicAdd(args.sync, 1);
+    }
+  }
+}
+
 // split-K epilogue: sum the slices, bias + activation + layout; 4 columns per thread
 __global__ void k_splitk_finish(const float* __restrict__ ws, GemmParams p, int splitk) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,8 +1101,12 @@ extern "C" int mf_gemm_bf16_tc_ex(const GemmParams* hp, int n_groups, void* work
   // stream-K when the caller provides the flag words and whole-tile scheduling would idle > 5 %
   // of the SMs (or there are fewer tiles than SMs) on a long-K problem with bf16 output
   bool streamk = false;
-  if (sync && !one_shot && n_groups == 1 && p0.N % 32 == 0 && p0.out_mode != OUT_F32 &&
-      args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8) {
+  // (short-K problems are epilogue-bound: the extra accumulator round trip costs more than the
+  // idle tail it removes - measured on the head GEMMs: 36.5 -> 40.4, 16.1 -> 21.1, 10.0 -> 13.5 us)
+  bool sk_ok = sync && !one_shot && args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8;
+  for (int g = 0; g < n_groups; ++g)
+    sk_ok = sk_ok && hp[g].N % 32 == 0 && hp[g].out_mode != OUT_F32;
+  if (sk_ok) {
     const int waves = (tiles + n_sm - 1) / n_sm;
     const double busy = (double)tiles / ((double)waves * n_sm);
     const size_t need = (size_t)n_sm * TC_BLOCK_M * BN * 4;
@@ -869,6 +1146,62 @@ extern "C" int mf_gemm_bf16_tc_ex(const GemmParams* hp, int n_groups, void* work
 extern "C" int mf_gemm_bf16_tc_grouped(const GemmParams* hp, int n_groups, void* workspace,
                                        size_t workspace_bytes, void* stream_) {
   return mf_gemm_bf16_tc_ex(hp, n_groups, workspace, workspace_bytes, nullptr, nullptr, 0, stream_);
+}
+
+extern "C" int mf_cnn_heads_tc(const GemmParams* layers, int n_layers, int32_t* sync, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!layers || n_layers != HD_LAYERS || !sync) return MF_E_BADARG;
+  HeadsArgs a;
+  memset(&a, 0, sizeof(a));
+  const int M = layers[0].M;
+  const int m_tiles = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  if (16 + 4 * m_tiles > MF_HEADS_SYNC_INTS) return MF_E_TOOLARGE;
+  int units = 0;
+  for (int q = 0; q < HD_LAYERS; ++q) {
+    const GemmParams& p = layers[q];
+    int rc = check_shape(p);
+    if (rc) return rc;
+    if (p.M != M || p.mode != GEMM_LINEAR || p.out_mode != OUT_BF16 || p.N % 32 != 0 || p.N < 128)
+      return MF_E_UNSUPPORTED;
+    if (q >= 2 && q <= 3 && (p.N != layers[1].N || p.K != layers[1].K)) return MF_E_UNSUPPORTED;
+    if (q >= 5 && (p.N != layers[4].N || p.K != layers[4].K)) return MF_E_UNSUPPORTED;
+    a.p[q] = p;
+    a.bn[q] = p.N >= 256 ? 256 : 128;
+    a.kb[q] = (p.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    a.n_tiles[q] = (p.N + a.bn[q] - 1) / a.bn[q];
+    a.unit_begin[q] = units;
+    units += m_tiles * a.n_tiles[q];
+    int dummy = 0;
+    rc = make_maps(p, a.bn[q], &a.tmA[q], &a.tmW[q], &dummy);
+    if (rc) return rc;
+  }
+  a.unit_begin[HD_LAYERS] = units;
+  // counters: [0, m_tiles) layer-1 rows; [m_tiles * (1 + h), ...) layer-2 rows of head h
+  a.dep_base[0] = -1;
+  a.sig_base[0] = 0;
+  for (int h = 0; h < 3; ++h) {
+    a.dep_base[1 + h] = 0;
+    a.dep_target[1 + h] = a.n_tiles[0] * 8;            // 8 epilogue warps per tile
+    a.sig_base[1 + h] = m_tiles * (1 + h);
+    a.dep_base[4 + h] = m_tiles * (1 + h);
+    a.dep_target[4 + h] = a.n_tiles[1 + h] * 8;
+    a.sig_base[4 + h] = -1;
+  }
+  a.m_tiles = m_tiles;
+  a.n_units = units;
+  a.sync = sync;
+  a.err = nullptr;
+  constexpr int STAGES = 4;
+  constexpr int smem = STAGES * (TC_A_BYTES + 256 * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
+  MF_ENSURE_DYN_SMEM((k_heads_tc<STAGES>), smem);
+  int n_sm = 148, dev = 0;
+  MF_CUDA_TRY(cudaGetDevice(&dev));
+  MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  // every CTA must be resident (units wait on units of other CTAs): one CTA per SM at most
+  const int grid = units < n_sm ? units : n_sm;
+  k_heads_tc<STAGES><<<grid, TC_P_THREADS, smem, stream>>>(a);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
 }
 
 extern "C" int mf_gemm_bf16_tc(const GemmParams* hp, void* workspace, size_t workspace_bytes,

@@ -191,6 +191,38 @@ def test_fused_occ_kernel_bit_identical_to_two_kernel_path(cuda_device, as_bytes
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
 
 
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_fused_heads_launch_bit_identical_to_three_launches(cuda_device, B):
+    """Head layers 1-3 as one persistent launch with tile-level dependencies (mf_cnn_heads_tc):
+    same tiles, same K order, same epilogue as the three grouped launches -> identical bits in
+    hd1 / hd2 / hd3 and in the poses; repeated calls exercise the epoch counters."""
+    from morefusion_b200.contrib.singleview_3d.models import Model
+    w = ocnn.init_weights(21, seed=5)
+    m = Model(n_fg_class=21, with_occupancy=True).to(cuda_device).load_reference_weights(w)
+
+    def run(inp, fused):
+        m.fused_heads = fused
+        out = m.forward_features(
+            class_id=torch.as_tensor(inp["class_id"], device=cuda_device),
+            values=torch.as_tensor(inp["values"], device=cuda_device),
+            points=torch.as_tensor(inp["points"], device=cuda_device),
+            pitch=inp["pitch"], origin=inp["origin"],
+            grid_nontarget_empty=torch.as_tensor(inp["grid_nontarget_empty"], device=cuda_device))
+        torch.cuda.synchronize()
+        buf = m._wbufs[(B, 1000, cuda_device)]
+        return [o.clone() for o in out] + [buf[k].clone() for k in ("hd1", "hd2", "hd3")]
+
+    for seed in (21, 22, 23):
+        inp = make_inputs(B, seed=seed)
+        ref = run(inp, False)
+        got = run(inp, True)
+        assert any(k[0] == "tc" for k in m.launch_log)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    ep = int(m._wbufs[(B, 1000, cuda_device)]["hd_sync"][0])
+    assert ep == 3, ep            # one epoch per fused launch
+
+
 def test_fused_head4_and_concurrent_branches_equal_sequential(cuda_device):
     """Last head layer fused with class selection + pose epilogue, and the two-stream branch
     overlap, give the same poses as the sequential grouped-GEMM + k_pose composition (fp32

@@ -147,3 +147,33 @@ def test_tc_stream_k_conv_s2d(cuda_device, Do, Ci, Co, B):
         hp = torch.nn.functional.pad(h, (1, 1, 1, 1, 1, 1))
         want = hp.reshape(B, N, J2, 2, J2, 2, J2, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, J2, J2, J2, 8 * N)
         assert torch.equal(out2, want.contiguous())
+
+
+@pytest.mark.parametrize("M,N,K", [(8000, 256, 640), (8000, 128, 256), (1000, 256, 640)])
+def test_tc_stream_k_grouped_heads(cuda_device, M, N, K):
+    """The three pose heads as one grouped stream-K launch (short K: 4-10 K blocks per tile):
+    column-offset outputs into one buffer, compared with per-head fp32 references."""
+    from morefusion_b200 import _lib
+    from morefusion_b200.contrib.singleview_3d.models.model import GemmParams
+    L = _lib.lib()
+    torch.manual_seed(2)
+    A = torch.randn(M, 3 * K, device=cuda_device).to(torch.bfloat16)
+    Ws = [(torch.randn(N, K, device=cuda_device) / K ** 0.5).to(torch.bfloat16) for _ in range(3)]
+    bs = [torch.randn(N, device=cuda_device) for _ in range(3)]
+    sync = torch.zeros(2048, dtype=torch.int32, device=cuda_device)
+    ws = torch.empty(L.mf_gemm_bf16_tc_workspace_bytes(M, N), dtype=torch.uint8, device=cuda_device)
+    for rep in range(2):
+        out = torch.zeros(M, 3 * N, device=cuda_device, dtype=torch.bfloat16)
+        arr = (GemmParams * 3)()
+        views = [A[:, i * K:] for i in range(3)]
+        for i in range(3):
+            arr[i] = GemmParams(_lib.ptr(views[i]), _lib.ptr(Ws[i]), _lib.ptr(bs[i]), _lib.ptr(out), M, N, K,
+                                0, 3 * K, K, 0, 0, 1, 0, 3 * N, i * N)
+        rc = L.mf_gemm_bf16_tc_ex(arr, 3, _lib.ptr(ws), ws.numel(), _lib.ptr(sync), None, 0, _lib.stream())
+        torch.cuda.synchronize()
+        assert rc == 0
+        for i in range(3):
+            ref = torch.relu(A[:, i * K:(i + 1) * K].float() @ Ws[i].float().T + bs[i])
+            got = out[:, i * N:(i + 1) * N].float()
+            assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+        assert int(sync.abs().sum()) == 0
