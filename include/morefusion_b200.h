@@ -297,7 +297,9 @@ int mf_gemm_bf16_tc(const GemmParams* p, void* workspace, size_t workspace_bytes
  *  stamps : NULL, or a device buffer of 16*8 int64 receiving clock64 stamps of CTA 0's roles per
  *           work unit (0/1 TMA producer begin/end, 2/3/4 MMA issuer buffer-free /
  *           first-operands / committed, 5/6/7 epilogue accumulator-ready / drained / stored).
- *  one_shot : non-zero selects the one-tile-per-CTA kernel (comparison baseline). */
+ *  one_shot : 0 = best kernel for the shape (the CTA-pair cta_group::2 kernel for single-group
+ *           bf16-output problems with N >= 256, else the single-CTA persistent kernel);
+ *           1 = the one-tile-per-CTA kernel, 2 = the single-CTA persistent kernel (baselines). */
 #define MF_GEMM_TC_SYNC_INTS 2048
 int mf_gemm_bf16_tc_ex(const GemmParams* p, int n_groups, void* workspace, size_t workspace_bytes,
                        int32_t* sync, long long* stamps, int one_shot, void* stream);

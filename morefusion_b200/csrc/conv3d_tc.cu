@@ -662,6 +662,332 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile: each CTA stages its
+// own 128 rows of A and HALF of the B tile (128 of the 256 weight rows) per K block - 32 KB per
+// CTA per K block instead of 48 KB - and the leader CTA's single thread issues one
+// tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory and writes each CTA's
+// 128 accumulator rows into that CTA's own TMEM.  The single-CTA kernel is bound by operand
+// delivery (4 stages x 48 KB in flight against ~1.7 us of TMA latency, measured 0.46-0.58 us per
+// K block against 0.37 us of tensor work); here the same shared memory holds 6 stages and every
+// stage carries 1.5x the tensor work.
+//   full_bar   : leader only; its producer arms 2 x 32 KB, BOTH CTAs' TMA loads credit it
+//   empty_bar  : per CTA; released by the leader's multicast commit (both CTAs' producers wake)
+//   tmem_full  : per CTA; multicast commit
+//   tmem_empty : leader only; 16 arrivals = 8 epilogue warps of each CTA (the peer arrives remotely)
+// Scheduling: units are 256-row tiles dealt to CLUSTERS; stream-K as in the single-CTA kernel with
+// cluster ranges, slots and flags per CTA (each CTA parks / adds its own 128-row half).
+struct TcPairIter {
+  long long pos, hi, W;
+  int u, ncl, cl;
+  __device__ __forceinline__ long long lo_of(int c) const { return W * c / ncl; }
+  __device__ __forceinline__ TcPairIter(const TcSched& sc, int kb_total) {
+    ncl = (int)gridDim.x >> 1;
+    cl = (int)blockIdx.x >> 1;
+    W = (long long)sc.n_units * kb_total;
+    pos = sc.streamk ? lo_of(cl) : 0;
+    hi = sc.streamk ? lo_of(cl + 1) : 0;
+    u = cl;
+  }
+  __device__ __forceinline__ bool next(const TcSched& sc, const TcExtra& e, TcSeg& s) {
+    s.partial = 0; s.peer0 = 0; s.n_peers = 0;
+    if (sc.streamk) {
+      if (pos >= hi) return false;
+      const int t = (int)(pos / e.kb_total);
+      const int k0 = (int)(pos - (long long)t * e.kb_total);
+      const long long room = hi - pos;
+      const int k1 = room < (long long)(e.kb_total - k0) ? k0 + (int)room : e.kb_total;
+      s.u = t; s.kb0 = k0; s.kb1 = k1;
+      s.partial = k0 != 0;
+      if (k0 == 0 && k1 < e.kb_total) {
+        const long long tile_end = (long long)(t + 1) * e.kb_total;
+        s.peer0 = cl + 1;
+        int c = s.peer0;
+        while (c < ncl && lo_of(c) < tile_end) ++c;
+        s.n_peers = c - s.peer0;
+      }
+      pos += k1 - k0;
+      return true;
+    }
+    if (u >= sc.n_units) return false;
+    s.u = u; s.kb0 = 0; s.kb1 = e.kb_total;
+    u += ncl;
+    return true;
+  }
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_P_THREADS, 1)
+k_gemm_tc_pair(const __grid_constant__ TcArgs args, const TcSched sc) {
+  constexpr int BLOCK_N = 256;                        // N of the pair tile; each CTA stages 128 rows
+  constexpr int B_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;   // 32 KB
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* out_stage = smem + (size_t)STAGES * STAGE_BYTES;   // 8 x TC_STG_BYTES
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcExtra& e = args.e;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmA[0])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.tmW[0])) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 16);      // 8 epilogue warps of each CTA of the pair
+    mbar_init(&tmem_empty_bar[1], 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer's barriers exist before anything signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const GemmParams& p = args.p[0];
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs: own A rows, own half of the B tile)
+    int kc = 0;
+    TcPairIter iter(sc, e.kb_total);
+    TcSeg seg;
+    while (iter.next(sc, e, seg)) {
+      int g, mt, nt, split;
+      unit_decode(sc, seg.u, g, mt, nt, split);
+      const int m0 = mt * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
+      const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+      int cb = 0, cw = 0, ch = 0, cd = 0;
+      if (p.mode == GEMM_CONV_S2D) {
+        int Do = p.Do;
+        cw = m0 % Do;
+        ch = (m0 / Do) % Do;
+        cd = (m0 / (Do * Do)) % Do;
+        cb = m0 / (Do * Do * Do);
+      }
+      for (int kb = seg.kb0; kb < seg.kb1; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, e.err, 1, 64);
+        if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        if (p.mode == GEMM_CONV_S2D) {
+          int a = kb / e.kb_per_a, c = (kb - a * e.kb_per_a) * TC_BLOCK_K;
+          tma_load_5d_pair(sa, &args.tmA[0], &full_bar[s], c, cw + (a & 1), ch + ((a >> 1) & 1),
+                           cd + ((a >> 2) & 1), cb);
+        } else {
+          tma_load_2d_pair(sa, &args.tmA[0], &full_bar[s], kb * TC_BLOCK_K, m0);
+        }
+        tma_load_2d_pair(sa + TC_A_BYTES, &args.tmW[0], &full_bar[s], kb * TC_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===== MMA issuer (leader CTA only): M = 256 over the pair, N = 256
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                               ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * TC_BLOCK_M) >> 4) << 24);
+    int kc = 0, it = 0;
+    TcPairIter iter(sc, e.kb_total);
+    TcSeg seg;
+    for (; iter.next(sc, e, seg); ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1, e.err, 4, 32);    // both CTAs drained this buffer
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = seg.kb0; kb < seg.kb1; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, e.err, 2, 20);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = make_sw128_desc(sa);
+        const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BLOCK_K / 16; ++k)
+          umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                         (kb > seg.kb0 || k > 0) ? 1u : 0u);
+        umma_commit_pair(&empty_bar[s]);
+      }
+      umma_commit_pair(&tmem_full_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, own 128 accumulator rows): as in k_gemm_tc_persistent
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    constexpr int EPI_COLS = BLOCK_N / 2, NCH = EPI_COLS / 32;
+    const uint32_t stg_s = smem_u32(out_stage + (size_t)(warp - 4) * TC_STG_BYTES);
+    const int wslot = warp - 4;
+    constexpr long long SLOT_FLOATS = (long long)TC_BLOCK_M * BLOCK_N;
+    int it = 0;
+    TcPairIter iter(sc, e.kb_total);
+    TcSeg seg;
+    for (; iter.next(sc, e, seg); ++it) {
+      int g, mt, nt, split;
+      unit_decode(sc, seg.u, g, mt, nt, split);
+      const int m0 = mt * (2 * TC_BLOCK_M) + (int)rank * TC_BLOCK_M;
+      const int n0 = nt * BLOCK_N + hsel * EPI_COLS;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], aph, e.err, 3, 128);
+      tcgen05_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const long long roff = row_ok ? out_row_offset(p, m) : 0;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * BLOCK_N + hsel * EPI_COLS) +
+                            ((uint32_t)(q * 32) << 16);
+      if (seg.partial) {
+        float4* slot = reinterpret_cast<float4*>(sc.sk_ws + (long long)blockIdx.x * SLOT_FLOATS +
+                                                 (long long)wslot * 32 * EPI_COLS);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            slot[(c * 8 + j) * 32 + lane] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(sc.sk_flags + blockIdx.x * 8 + wslot),
+                       "r"(1) : "memory");
+      } else {
+        // peers of this CTA: the same-rank CTA of the following clusters
+        if (seg.n_peers > 0) {
+          if (lane == 0) {
+            for (int pi = 0; pi < seg.n_peers; ++pi) {
+              const int* f = sc.sk_flags + (2 * (seg.peer0 + pi) + (int)rank) * 8 + wslot;
+              int v = 0;
+              for (long long spin = 0; spin < (1LL << 24); ++spin) {
+                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v) break;
+                __nanosleep(64);
+              }
+              if (!v && e.err) atomicExch(e.err, 7);
+            }
+          }
+          __syncwarp();
+        }
+        const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+        int relu_i = p.relu, Nn = p.N;
+        const float* bias = p.bias;
+        bf16* outp = reinterpret_cast<bf16*>(p.out);
+        asm volatile("" : "+r"(relu_i), "+r"(Nn), "+l"(bias), "+l"(outp));
+        const bool relu = relu_i != 0;
+        long long rofs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rofs[i] = __shfl_sync(0xffffffffu, roff, i * 4 + (lane >> 3));
+        uint32_t ra[32], rb[32];
+        auto process = [&](uint32_t (&r)[32], int c) {
+          const int n = n0 + c * 32;
+          if (n < Nn) {
+            for (int pi = 0; pi < seg.n_peers; ++pi) {
+              const float4* ps = reinterpret_cast<const float4*>(
+                  sc.sk_ws + (long long)(2 * (seg.peer0 + pi) + (int)rank) * SLOT_FLOATS +
+                  (long long)wslot * 32 * EPI_COLS);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 a = __ldcg(ps + (c * 8 + j) * 32 + lane);
+                r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + a.x);
+                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a.y);
+                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a.z);
+                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a.w);
+              }
+            }
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bq = bias ? __ldg(reinterpret_cast<const float4*>(bias + n) + j)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 uu;
+              if (relu) {
+                uu.x = pack_bf16x2_relu(v[8 * j + 0], v[8 * j + 1]);
+                uu.y = pack_bf16x2_relu(v[8 * j + 2], v[8 * j + 3]);
+                uu.z = pack_bf16x2_relu(v[8 * j + 4], v[8 * j + 5]);
+                uu.w = pack_bf16x2_relu(v[8 * j + 6], v[8 * j + 7]);
+              } else {
+                uu.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                uu.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                uu.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                uu.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              }
+              const int piece = ((c & 1) * 4 + j) ^ (lane & 7);
+              sts_v4(stg_s + lane * 128 + piece * 16, uu);
+            }
+          }
+          if (c & 1) {
+            __syncwarp();
+            const int ncol = n0 + (c - 1) * 32 + (lane & 7) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);
+              const uint4 uu = lds_v4(stg_s + row * 128 + (((lane & 7) ^ (row & 7)) * 16));
+              if (((okmask >> row) & 1u) && ncol < Nn)
+                *reinterpret_cast<uint4*>(outp + rofs[i] + ncol) = uu;
+            }
+            __syncwarp();
+          }
+        };
+        tmem_ld_32x32_issue(tacc, ra);
+        tmem_ld_wait(ra);
+#pragma unroll
+        for (int c = 0; c < NCH; c += 2) {
+          tmem_ld_32x32_issue(tacc + (uint32_t)((c + 1) * 32), rb);
+          process(ra, c);
+          tmem_ld_wait(rb);
+          if (c + 2 < NCH) tmem_ld_32x32_issue(tacc + (uint32_t)((c + 2) * 32), ra);
+          process(rb, c + 1);
+          if (c + 2 < NCH) tmem_ld_wait(ra);
+        }
+        if (seg.n_peers > 0) {
+          __syncwarp();
+          if (lane == 0)
+            for (int pi = 0; pi < seg.n_peers; ++pi)
+              sc.sk_flags[(2 * (seg.peer0 + pi) + (int)rank) * 8 + wslot] = 0;
+        }
+      }
+      // this warp is done reading the accumulator buffer: tell the leader's MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // both CTAs are done with the pair's TMEM / barriers
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(2 * BLOCK_N))
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ the pose heads as ONE launch
 // Layers 1-3 of the three heads (model.py:239-254: head1 = the three first layers side by side,
 // 3 x conv2_*, 3 x conv3_*) are 7 GEMMs whose only coupling is per 128-row tile: a layer-2 tile
@@ -1002,6 +1328,41 @@ static int launch_persistent(const TcArgs& args, const TcSched& sc, cudaStream_t
   return MF_OK;
 }
 
+template <int STAGES>
+static int launch_pair(const TcArgs& args, const TcSched& sc, int n_sm, cudaStream_t stream) {
+  constexpr int smem = STAGES * (TC_A_BYTES + 128 * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
+  MF_ENSURE_DYN_SMEM((k_gemm_tc_pair<STAGES>), smem);
+  int grid = n_sm & ~1;
+  if (!sc.streamk && 2 * sc.n_units < grid) grid = 2 * sc.n_units;
+  k_gemm_tc_pair<STAGES><<<grid, TC_P_THREADS, smem, stream>>>(args, sc);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+// how many CTA pairs of k_gemm_tc_pair the device can hold at once (cached per device)
+static int pair_clusters(int dev) {
+  static int cached[64];
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+  constexpr int smem = 6 * (TC_A_BYTES + 128 * TC_BLOCK_K * 2) + 1024 + 8 * TC_STG_BYTES;
+  if (cudaFuncSetAttribute(k_gemm_tc_pair<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2, 1, 1);
+  cfg.blockDim = dim3(TC_P_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tc_pair<6>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  if (dev >= 0 && dev < 64) cached[dev] = n > 0 ? n : -1;
+  return n;
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch(const TcArgs& args, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (TC_A_BYTES + BLOCK_N * TC_BLOCK_K * 2) + 1024;
@@ -1098,12 +1459,34 @@ extern "C" int mf_gemm_bf16_tc_ex(const GemmParams* hp, int n_groups, void* work
   int n_sm = 148, dev = 0;
   MF_CUDA_TRY(cudaGetDevice(&dev));
   MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  // ---- CTA-pair kernel (cta_group::2): one group, 256-wide N tiles, bf16 output
+  if (one_shot == 0 && n_groups == 1 && BN == 256 && p0.N % 32 == 0 && p0.out_mode != OUT_F32) {
+    const int ncl = pair_clusters(dev);
+    if (ncl > 0 && 2 * ncl >= (n_sm & ~1)) {
+      int rc = make_maps(p0, 128, &args.tmA[0], &args.tmW[0], &args.e.kb_per_a);   // B box: 128 rows
+      if (rc) return rc;
+      const int m_tiles2 = (p0.M + 2 * TC_BLOCK_M - 1) / (2 * TC_BLOCK_M);
+      const int tiles2 = m_tiles2 * n_tiles, clusters = (n_sm & ~1) / 2;
+      bool sk = false;
+      if (sync && args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8) {
+        const int waves = (tiles2 + clusters - 1) / clusters;
+        const double busy = (double)tiles2 / ((double)waves * clusters);
+        const size_t need = (size_t)n_sm * TC_BLOCK_M * 256 * 4;
+        if (busy < 0.95 && workspace && workspace_bytes >= need) sk = true;
+      }
+      args.e.kb_per_split = args.e.kb_total;
+      args.e.splitk = 1;
+      args.e.err = nullptr;
+      TcSched sc{m_tiles2, n_tiles, 1, 1, tiles2, stamps, sk ? 1 : 0, sync, (float*)workspace};
+      return launch_pair<6>(args, sc, n_sm, stream);
+    }
+  }
   // stream-K when the caller provides the flag words and whole-tile scheduling would idle > 5 %
   // of the SMs (or there are fewer tiles than SMs) on a long-K problem with bf16 output
   bool streamk = false;
   // (short-K problems are epilogue-bound: the extra accumulator round trip costs more than the
   // idle tail it removes - measured on the head GEMMs: 36.5 -> 40.4, 16.1 -> 21.1, 10.0 -> 13.5 us)
-  bool sk_ok = sync && !one_shot && args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8;
+  bool sk_ok = sync && one_shot != 1 && args.e.kb_total >= 32 && n_sm <= MF_GEMM_TC_SYNC_INTS / 8;
   for (int g = 0; g < n_groups; ++g)
     sk_ok = sk_ok && hp[g].N % 32 == 0 && hp[g].out_mode != OUT_F32;
   if (sk_ok) {
@@ -1127,7 +1510,7 @@ extern "C" int mf_gemm_bf16_tc_ex(const GemmParams* hp, int n_groups, void* work
   }
   dim3 grid(n_tiles, m_tiles, splitk * n_groups);
   int rc;
-  if (!one_shot) {
+  if (one_shot != 1) {
     TcSched sc{m_tiles, n_tiles, n_groups, splitk, m_tiles * n_tiles * n_groups * splitk,
                stamps, streamk ? 1 : 0, sync, (float*)workspace};
     if (BN == 256) rc = launch_persistent<256, 4>(args, sc, stream);
