@@ -456,13 +456,13 @@ def run_ours(args, rank, world, local):
     flops = CONV3_FLOPS_PER_OBJECT * B_PER_RANK
     achieved = flops / (conv3_avg_ms * 1e-3) / 1e12
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_conv3_ncu_summary.json")
+    prof = os.path.join(ROOT, "profiles", "r02_conv3_pair_ncu_summary.json")
     if os.path.exists(prof):
         try:
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = dict(bound="tensor", kernel="k_gemm_tc_persistent<256,4> (conv3 160->256 k4 s2, implicit GEMM M=32768 N=256 K=10240)",
+    roof = dict(bound="tensor", kernel="k_gemm_tc_pair<6> (conv3 160->256 k4 s2, implicit GEMM M=32768 N=256 K=10240, cta_group::2, stream-K)",
                 achieved=achieved, peak=pk["bf16"], unit="TFLOP/s",
                 frac=achieved / pk["bf16"], frac_of_sustained_peak=achieved / pk["bf16_sustained"],
                 peak_source=pk["source"] + ", burst figure (0.14 ms kernel between L2 flushes); "
@@ -472,7 +472,7 @@ def run_ours(args, rank, world, local):
                       "(step split into 3 graphs); `value` times the one-graph step",
                 traffic=traffic,
                 traffic_source="profile constant: dram__bytes_read+write per launch from the committed "
-                               "ncu --set full capture (profiles/r01_conv3_ncu_summary.json), not measured in this run")
+                               "ncu --set full capture (profiles/r02_conv3_pair_ncu_summary.json), not measured in this run")
     # ---- the two HBM-bound targets north_star names + the per-frame chain (BASELINE configs 1/4/5)
     for name, fn in (("avg_vox", lambda: bench_avg_vox(dev, pk, flush)),
                      ("icc", lambda: bench_icc(dev, pk, args.quick))):

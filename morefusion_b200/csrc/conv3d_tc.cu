@@ -678,40 +678,43 @@ k_gemm_tc_persistent(const __grid_constant__ TcArgs args, const TcSched sc) {
 // Scheduling: units are 256-row tiles dealt to CLUSTERS; stream-K as in the single-CTA kernel with
 // cluster ranges, slots and flags per CTA (each CTA parks / adds its own 128-row half).
 struct TcPairIter {
+  // stream-K hybrid: the first dp_tiles = floor(tiles / clusters) x clusters tiles are dealt whole
+  // (one per cluster and wave: no partial sums, and the two K halves of a tile are not fetched
+  // 100 us apart), only the remaining tiles x K-blocks space is cut into equal ranges
   long long pos, hi, W;
-  int u, ncl, cl;
+  int u, ncl, cl, dp_tiles;
   __device__ __forceinline__ long long lo_of(int c) const { return W * c / ncl; }
   __device__ __forceinline__ TcPairIter(const TcSched& sc, int kb_total) {
     ncl = (int)gridDim.x >> 1;
     cl = (int)blockIdx.x >> 1;
-    W = (long long)sc.n_units * kb_total;
-    pos = sc.streamk ? lo_of(cl) : 0;
-    hi = sc.streamk ? lo_of(cl + 1) : 0;
+    dp_tiles = sc.streamk ? (sc.n_units / ncl) * ncl : sc.n_units;
+    W = (long long)(sc.n_units - dp_tiles) * kb_total;
+    pos = lo_of(cl);
+    hi = lo_of(cl + 1);
     u = cl;
   }
   __device__ __forceinline__ bool next(const TcSched& sc, const TcExtra& e, TcSeg& s) {
     s.partial = 0; s.peer0 = 0; s.n_peers = 0;
-    if (sc.streamk) {
-      if (pos >= hi) return false;
-      const int t = (int)(pos / e.kb_total);
-      const int k0 = (int)(pos - (long long)t * e.kb_total);
-      const long long room = hi - pos;
-      const int k1 = room < (long long)(e.kb_total - k0) ? k0 + (int)room : e.kb_total;
-      s.u = t; s.kb0 = k0; s.kb1 = k1;
-      s.partial = k0 != 0;
-      if (k0 == 0 && k1 < e.kb_total) {
-        const long long tile_end = (long long)(t + 1) * e.kb_total;
-        s.peer0 = cl + 1;
-        int c = s.peer0;
-        while (c < ncl && lo_of(c) < tile_end) ++c;
-        s.n_peers = c - s.peer0;
-      }
-      pos += k1 - k0;
+    if (u < dp_tiles) {
+      s.u = u; s.kb0 = 0; s.kb1 = e.kb_total;
+      u += ncl;
       return true;
     }
-    if (u >= sc.n_units) return false;
-    s.u = u; s.kb0 = 0; s.kb1 = e.kb_total;
-    u += ncl;
+    if (pos >= hi) return false;
+    const int t = (int)(pos / e.kb_total);
+    const int k0 = (int)(pos - (long long)t * e.kb_total);
+    const long long room = hi - pos;
+    const int k1 = room < (long long)(e.kb_total - k0) ? k0 + (int)room : e.kb_total;
+    s.u = dp_tiles + t; s.kb0 = k0; s.kb1 = k1;
+    s.partial = k0 != 0;
+    if (k0 == 0 && k1 < e.kb_total) {
+      const long long tile_end = (long long)(t + 1) * e.kb_total;
+      s.peer0 = cl + 1;
+      int c = s.peer0;
+      while (c < ncl && lo_of(c) < tile_end) ++c;
+      s.n_peers = c - s.peer0;
+    }
+    pos += k1 - k0;
     return true;
   }
 };
@@ -770,6 +773,9 @@ k_gemm_tc_pair(const __grid_constant__ TcArgs args, const TcSched sc) {
     int kc = 0;
     TcPairIter iter(sc, e.kb_total);
     TcSeg seg;
+    // linear A is streamed (each byte feeds the n_tiles of one row tile): let it leave L2 first;
+    // the weights every cluster re-reads and the stream-K slots must survive the pass
+    const uint64_t pol_a = l2_policy_evict_first(), pol_w = l2_policy_evict_last();
     while (iter.next(sc, e, seg)) {
       int g, mt, nt, split;
       unit_decode(sc, seg.u, g, mt, nt, split);
@@ -791,12 +797,13 @@ k_gemm_tc_pair(const __grid_constant__ TcArgs args, const TcSched sc) {
         unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
         if (p.mode == GEMM_CONV_S2D) {
           int a = kb / e.kb_per_a, c = (kb - a * e.kb_per_a) * TC_BLOCK_K;
+          // conv: every s2d input voxel is read by 8 kernel offsets (of different tiles): default policy
           tma_load_5d_pair(sa, &args.tmA[0], &full_bar[s], c, cw + (a & 1), ch + ((a >> 1) & 1),
                            cd + ((a >> 2) & 1), cb);
         } else {
-          tma_load_2d_pair(sa, &args.tmA[0], &full_bar[s], kb * TC_BLOCK_K, m0);
+          tma_load_2d_pair_hint(sa, &args.tmA[0], &full_bar[s], kb * TC_BLOCK_K, m0, pol_a);
         }
-        tma_load_2d_pair(sa + TC_A_BYTES, &args.tmW[0], &full_bar[s], kb * TC_BLOCK_K, n0);
+        tma_load_2d_pair_hint(sa + TC_A_BYTES, &args.tmW[0], &full_bar[s], kb * TC_BLOCK_K, n0, pol_w);
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
@@ -855,15 +862,17 @@ k_gemm_tc_pair(const __grid_constant__ TcArgs args, const TcSched sc) {
       if (seg.partial) {
         float4* slot = reinterpret_cast<float4*>(sc.sk_ws + (long long)blockIdx.x * SLOT_FLOATS +
                                                  (long long)wslot * 32 * EPI_COLS);
+        const uint64_t pol_keep = l2_policy_evict_last();     // read back at the end of the kernel
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            slot[(c * 8 + j) * 32 + lane] =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            st_global_v4_hint(slot + (c * 8 + j) * 32 + lane,
+                              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                              pol_keep);
         }
         __threadfence();
         __syncwarp();
