@@ -1244,31 +1244,34 @@ k_head4_pose(const bf16* __restrict__ hd3, int ld,              // [B*P, ld]: ro
   __shared__ __align__(16) float w[8][132];
   __shared__ float bias[8];
   const int b = blockIdx.y;
-  int fg = class_id[b] - 1;
-  if (fg < 0) fg += nfg;                  // python-style wrap of the reference's fancy index
-  fg = min(max(fg, 0), nfg - 1);
-  for (int e = threadIdx.x; e < 8 * 128; e += 256) {
-    int r = e >> 7, k = e & 127;
-    const bf16* src = r < 4 ? w_rot + (size_t)(fg * 4 + r) * 128
-                    : r < 7 ? w_trans + (size_t)(fg * 3 + r - 4) * 128
-                            : w_conf + (size_t)fg * 128;
-    w[r][k] = __bfloat162float(src[k]);
-  }
-  if (threadIdx.x < 8) {
-    int r = threadIdx.x;
-    bias[r] = r < 4 ? b_rot[fg * 4 + r] : r < 7 ? b_trans[fg * 3 + r - 4] : b_conf[fg];
-  }
-  __syncthreads();
   const int r = threadIdx.x & 7;
   const int p = blockIdx.x * kH4Pts + (threadIdx.x >> 3);
   const bool ok = p < P;
   const long long n = (long long)b * P + (ok ? p : 0);
   const int seg = r < 4 ? 0 : r < 7 ? 1 : 2;               // rot / trans / conf feature block
   const uint4* hv = reinterpret_cast<const uint4*>(hd3 + n * ld + seg * 128);
+  uint4 hu[16];     // the whole 256-byte row segment in flight, under the weight staging below
+#pragma unroll
+  for (int v = 0; v < 16; ++v) hu[v] = __ldg(hv + v);
+  int fg = class_id[b] - 1;
+  if (fg < 0) fg += nfg;                  // python-style wrap of the reference's fancy index
+  fg = min(max(fg, 0), nfg - 1);
+  for (int e = threadIdx.x; e < 8 * 128; e += 256) {
+    int rr = e >> 7, k = e & 127;
+    const bf16* src = rr < 4 ? w_rot + (size_t)(fg * 4 + rr) * 128
+                    : rr < 7 ? w_trans + (size_t)(fg * 3 + rr - 4) * 128
+                             : w_conf + (size_t)fg * 128;
+    w[rr][k] = __bfloat162float(src[k]);
+  }
+  if (threadIdx.x < 8) {
+    int rr = threadIdx.x;
+    bias[rr] = rr < 4 ? b_rot[fg * 4 + rr] : rr < 7 ? b_trans[fg * 3 + rr - 4] : b_conf[fg];
+  }
+  __syncthreads();
   float acc = 0.f;
-#pragma unroll 4
+#pragma unroll
   for (int v = 0; v < 16; ++v) {
-    const uint4 u = __ldg(hv + v);
+    const uint4 u = hu[v];
     const bf16* hb = reinterpret_cast<const bf16*>(&u);
     const float4 w0 = *reinterpret_cast<const float4*>(&w[r][v * 8]);
     const float4 w1 = *reinterpret_cast<const float4*>(&w[r][v * 8 + 4]);
