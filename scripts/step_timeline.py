@@ -36,13 +36,17 @@ class flush:
             rbuf.max()          # 192 MiB read: L2 left full of clean lines
 
 
+E2E = "--e2e" in sys.argv
+run = r.run_e2e if E2E else r.run
 for _ in range(5):
-    flush.zero_(); r.run()
+    flush.zero_(); run()
 torch.cuda.synchronize()
 N = 10
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(N):
-        flush.zero_(); r.run()
+        flush.zero_(); run()
+        if E2E:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)

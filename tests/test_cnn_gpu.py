@@ -280,6 +280,14 @@ def test_runner_graph_equals_forward_features(cuda_device):
         torch.cuda.synchronize()
         for a, b in zip(got, want):
             assert torch.equal(a, b.cpu())
+        # the end-to-end graph (both copies inside, `values` copied under the occupancy branch):
+        # scribble over the device inputs and the host outputs first
+        runner.in_blob.fill_(0x55)
+        runner.host_out_blob.zero_()
+        host = runner.run_e2e()
+        torch.cuda.synchronize()
+        for k, b in zip(("rot", "trans", "conf"), want):
+            assert torch.equal(host[k], b.cpu()), k
 
 
 @pytest.mark.parametrize("D,C,s2d", [(8, 512, 0), (8, 64, 0), (8, 48, 0), (16, 256, 0), (16, 256, 1)])
