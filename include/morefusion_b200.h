@@ -499,6 +499,19 @@ int mf_average_distance_bwd(const float* gout, const float* points, int n_points
                             const int32_t* nn_indices /*NULL: identity*/,
                             float* g_transforms_pred /*[M,4,4]*/, float* g_transform_true /*[4,4]*/,
                             float* workspace /*[n_pred,12] floats*/, void* stream);
+/* the same over the B objects of a training batch from one call (model.py:416-431 calls
+ * average_distance per object): points [B,n_points,3], transform_true [B,4,4], transforms_pred
+ * [B,n_pred,4,4], out [B,n_pred], nn_indices [B,n_pred,n_points]; symmetric = HOST array [B] */
+int mf_average_distance_fwd_batched(const float* points, int n_points, const float* transform_true,
+                                    const float* transforms_pred, int n_pred, int B,
+                                    const int32_t* symmetric_host, float* out, int32_t* nn_indices,
+                                    void* stream);
+int mf_average_distance_bwd_batched(const float* gout, const float* points, int n_points,
+                                    const float* transform_true, const float* transforms_pred,
+                                    int n_pred, int B, const int32_t* symmetric_host,
+                                    const int32_t* nn_indices, float* g_transforms_pred,
+                                    float* g_transform_true, float* workspace /*[B,n_pred,12]*/,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

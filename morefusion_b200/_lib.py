@@ -94,6 +94,8 @@ SIGNATURES = {
     "mf_average_distance_fwd": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "mf_average_distance_fwd_parts": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "mf_average_distance_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "mf_average_distance_fwd_batched": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "mf_average_distance_bwd_batched": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mf_icc_run_profiled": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9
                             + [c_i, c_i, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_i, c_p, c_sz, c_p, c_p]),
 }

@@ -386,13 +386,14 @@ class Model(torch.nn.Module):
         from .... import functions, metrics
         from ....metrics.average_distance import average_distance_device
         dev = self.conv3.weight.device
-        t = lambda x: torch.as_tensor(x, device=dev).detach().to(torch.float32)   # noqa: E731
+        t = lambda x, tag: _util.h2d(x, dev, torch.float32, tag).detach()   # noqa: E731
         cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
         B = cid.shape[0]
         self.flush_reports()
         main = torch.cuda.current_stream(dev)
         side = self._side(dev, 2) if self.training else main
-        q_t, t_t, q_p, t_p = t(quaternion_true), t(translation_true), t(quaternion_pred), t(translation_pred)
+        q_t, t_t = t(quaternion_true, "eval/q"), t(translation_true, "eval/t")
+        q_p, t_p = t(quaternion_pred, "eval/qp"), t(translation_pred, "eval/tp")
         side.wait_stream(main)
         with torch.cuda.stream(side):
             T_true = functions.transformation_matrix(q_t, t_t)
@@ -455,8 +456,8 @@ class Model(torch.nn.Module):
                 "the '+occupancy' loss terms call pseudo_occupancy_voxelization with a stale "
                 "signature in the reference (model.py:454-459) and cannot run there either")
         dev = quaternion_pred.device
-        t = lambda x: torch.as_tensor(x, device=dev).to(torch.float32)   # noqa: E731
-        quaternion_true, translation_true = t(quaternion_true), t(translation_true)
+        quaternion_true = _util.h2d(quaternion_true, dev, torch.float32, "loss/q")
+        translation_true = _util.h2d(translation_true, dev, torch.float32, "loss/t")
         cid = np.asarray(class_id.cpu() if isinstance(class_id, torch.Tensor) else class_id)
         B, P = confidence_pred.shape
         T_pred = functions.transformation_matrix(
@@ -465,18 +466,19 @@ class Model(torch.nn.Module):
         # 500 random CAD points per object (model.py:416-418): indices drawn on the host with
         # numpy's global RNG as in the reference, one upload for the batch, gather on the device
         pcds = [self._pcd_device(int(cid[i]), dev) for i in range(B)]
-        sel = torch.as_tensor(np.stack([np.random.permutation(p.shape[0])[:500] for p in pcds]),
-                              device=dev)
+        sel = _util.h2d(np.stack([np.random.permutation(p.shape[0])[:500] for p in pcds]), dev,
+                        torch.int64, "loss/sel")
         cads = torch.stack([pcds[i][sel[i]] for i in range(B)])
-        adds = []
+        syms = []
         for i in range(B):
             sym = int(cid[i]) in self._models.class_ids_symmetric
             if self._loss == "add":
                 sym = False
             elif self._loss == "add_s":
                 sym = True
-            adds.append(functions.average_distance(cads[i], T_true[i], T_pred[i], symmetric=sym))
-        add = torch.stack(adds)                                              # [B,P]
+            syms.append(sym)
+        from ....functions.loss.average_distance import average_distance_batched
+        add = average_distance_batched(cads, T_true, T_pred, syms)           # [B,P]
         conf = confidence_pred
         keep = conf.detach() > 0
         safe = torch.where(keep, conf, torch.ones_like(conf))
@@ -517,7 +519,7 @@ class Model(torch.nn.Module):
         dev = values.device
         st = dict(
             values=values.contiguous().float(), points=points.contiguous().float(),
-            class_id=torch.as_tensor(class_id).to(device=dev, dtype=torch.int32).contiguous(),
+            class_id=_util.h2d(class_id, dev, torch.int32, "ff/class_id").contiguous(),
             pitch=torch.as_tensor(pitch, dtype=torch.float32, device=dev).contiguous(),
             origin=torch.as_tensor(origin, dtype=torch.float32, device=dev).contiguous(),
             gne=None if grid_nontarget_empty is None

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from .... import _lib
+from ....functions.geometry import _util
 from . import model as M
 
 HEADS = ("rot", "trans", "conf")
@@ -149,7 +150,7 @@ def forward_features_with_grad(model, *, class_id, values, points, pitch, origin
     if not model.fused_head4 or not model.fused_voxelize or not model.use_tensor_cores:
         raise RuntimeError("the training step runs on the fused tensor-core forward")
     st = dict(points=points.detach().contiguous().float(),
-              class_id=torch.as_tensor(class_id).to(device=dev, dtype=torch.int32).contiguous(),
+              class_id=_util.h2d(class_id, dev, torch.int32, "train/class_id").contiguous(),
               pitch=torch.as_tensor(pitch, dtype=torch.float32, device=dev).contiguous(),
               origin=torch.as_tensor(origin, dtype=torch.float32, device=dev).contiguous(),
               gne=None if grid_nontarget_empty is None

@@ -201,3 +201,51 @@ extern "C" int mf_average_distance_bwd(const float* gout, const float* points, i
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
+
+// ---- the training loss calls average_distance once per object of the batch (model.py:416-431):
+// the same kernels over B objects from ONE call (B small launches back to back, no per-object
+// trip through the host binding).  symmetric: HOST array of B flags.  Layouts: points
+// [B,n_points,3], transform_true [B,4,4], transforms_pred [B,n_pred,4,4], out [B,n_pred],
+// nn_indices [B,n_pred,n_points] (rows of non-symmetric objects unused).
+extern "C" int mf_average_distance_fwd_batched(const float* points, int n_points,
+                                               const float* transform_true,
+                                               const float* transforms_pred, int n_pred, int B,
+                                               const int32_t* symmetric_host, float* out,
+                                               int32_t* nn_indices, void* stream_) {
+  if (B <= 0 || !symmetric_host) return MF_E_BADARG;
+  for (int b = 0; b < B; ++b) {
+    int32_t* idx = nn_indices ? nn_indices + (size_t)b * n_pred * n_points : nullptr;
+    if (symmetric_host[b] && !idx) return MF_E_BADARG;
+    int rc = mf_average_distance_fwd(points + (size_t)b * n_points * 3, n_points,
+                                     transform_true + (size_t)b * 16,
+                                     transforms_pred + (size_t)b * n_pred * 16, n_pred,
+                                     symmetric_host[b] ? 1 : 0, out + (size_t)b * n_pred,
+                                     symmetric_host[b] ? idx : nullptr, stream_);
+    if (rc) return rc;
+  }
+  return MF_OK;
+}
+
+extern "C" int mf_average_distance_bwd_batched(const float* gout, const float* points, int n_points,
+                                               const float* transform_true,
+                                               const float* transforms_pred, int n_pred, int B,
+                                               const int32_t* symmetric_host,
+                                               const int32_t* nn_indices, float* g_transforms_pred,
+                                               float* g_transform_true,
+                                               float* workspace /*[B,n_pred,12]*/, void* stream_) {
+  if (B <= 0 || !symmetric_host) return MF_E_BADARG;
+  for (int b = 0; b < B; ++b) {
+    const int32_t* idx = (symmetric_host[b] && nn_indices)
+                             ? nn_indices + (size_t)b * n_pred * n_points : nullptr;
+    if (symmetric_host[b] && !idx) return MF_E_BADARG;
+    int rc = mf_average_distance_bwd(gout + (size_t)b * n_pred, points + (size_t)b * n_points * 3,
+                                     n_points, transform_true + (size_t)b * 16,
+                                     transforms_pred + (size_t)b * n_pred * 16, n_pred, idx,
+                                     g_transforms_pred + (size_t)b * n_pred * 16,
+                                     g_transform_true + (size_t)b * 16,
+                                     workspace + (size_t)b * n_pred * 12, stream_);
+    if (rc) return rc;
+  }
+  return MF_OK;
+}
+

@@ -113,3 +113,43 @@ def workspace(nbytes, device):
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf
+
+
+_PIN = {}
+_COPY_STREAMS = {}
+
+
+def h2d(x, device, dtype=None, tag=""):
+    """Host array -> device tensor WITHOUT a host synchronisation: the array is copied into a
+    cached pinned staging tensor (one per tag / shape / dtype) and uploaded with a non-blocking
+    copy on a dedicated copy stream that the current stream then waits for.  The event that
+    guards the staging tensor against being overwritten while an upload is in flight therefore
+    completes as soon as that copy is done, not when the compute stream's queue has drained, so
+    the host keeps running ahead of the GPU.  CUDA tensors pass through (dtype applied).
+    (torch.as_tensor(numpy, device=...) uploads from pageable memory, which synchronises the
+    stream: seven of those per training step were 1.3 ms of idle GPU.)"""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        return x if dtype is None else x.to(dtype)
+    device = torch.device(device)
+    a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    td = dtype if dtype is not None else torch.from_numpy(np.empty(0, a.dtype)).dtype
+    key = (tag, str(device), tuple(a.shape), td)
+    slot = _PIN.get(key)
+    if slot is None:
+        slot = [torch.empty(tuple(a.shape), dtype=td, pin_memory=True), None]
+        _PIN[key] = slot
+    if slot[1] is not None:
+        slot[1].synchronize()
+    slot[0].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    cs = _COPY_STREAMS.get(str(device))
+    if cs is None:
+        cs = _COPY_STREAMS[str(device)] = torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    with torch.cuda.stream(cs):
+        out = slot[0].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    cur.wait_event(ev)
+    out.record_stream(cur)
+    slot[1] = ev
+    return out
