@@ -615,7 +615,7 @@ def train_bench(rank, world, local, steps, warmup):
                     f"{len(tr.buckets)} buckets overlapped with the backward, fused unscale + Adam",
                     parameters=n_params, allreduce_bytes_per_step=4 * n_params if world > 1 else 0,
                     l2="working set (activations + 124 MB of gradients) exceeds L2"),
-        loss_last=float(loss), clocks=clocks, gemms=gemms,
+        loss_last=float(loss.detach()), clocks=clocks, gemms=gemms,
         roofline=dict(bound="tensor", kernel="k_gemm_train<256,4> conv3 wgrad (MN-major implicit GEMM)",
                       achieved=gemms["conv3_wgrad"]["tflops"], peak=pk["bf16"], unit="TFLOP/s",
                       frac=gemms["conv3_wgrad"]["frac_of_bf16_burst_peak"], traffic=None),
