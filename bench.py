@@ -281,6 +281,73 @@ def bench_icc(dev, pk, quick):
     return out
 
 
+def bench_mapping(dev, pk, quick):
+    """Occupancy-grid producer: per 640x480 frame, 8 instance scans + the
+    background scan into the device hash map (MultiInstanceOctreeMapping.integrate), then the three
+    32^3 grids of all 8 targets from one launch.  Inputs resident in HBM; CUDA events."""
+    from morefusion_b200 import synthetic
+    from morefusion_b200.contrib import MultiInstanceOctreeMapping
+    n_frames = 3 if quick else 6
+    frames = []
+    for i in range(n_frames):
+        pcd, label, _, pitches = synthetic.make_depth_frame(seed=i)
+        frames.append((torch.as_tensor(pcd, device=dev), torch.as_tensor(label, device=dev)))
+    ids = sorted(pitches)
+    masks = [[(lab == ins) for ins in ids] for _, lab in frames]
+    m = MultiInstanceOctreeMapping(device=dev)
+    for ins in ids:
+        m.initialize(ins, pitch=pitches[ins])
+    ts = []
+    for f, (pcd, lab) in enumerate(frames):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for k, ins in enumerate(ids):
+            m.integrate(ins, masks[f][k], pcd)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    # ray cells of the background scan of the last frame (the dominant scan): device counter
+    bg_cells = int(m._counters[2 + 2 * (m._scan & 1)].item())
+    tids = [i for i in ids if i != 0]
+    pcd0, lab0 = frames[0][0].cpu().numpy(), frames[0][1].cpu().numpy()
+    origins = [np.nanmedian(pcd0[lab0 == t], axis=0) - 15.5 * pitches[t] for t in tids]
+    q = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g = m.get_target_grids_batch(tids, dimensions=(32, 32, 32), pitches=[pitches[t] for t in tids],
+                                     origins=origins)
+        e1.record()
+        torch.cuda.synchronize()
+        q.append(e0.elapsed_time(e1))
+    steady = sorted(ts[1:])[len(ts[1:]) // 2]
+    n_valid = int((~torch.isnan(frames[-1][0]).any(-1)).sum().item())
+    out = dict(frame="640x480, 8 instances (class pitch) + background (1 cm), OctoMap sensor model",
+               ms_per_frame_integrate=steady, first_frame_ms=ts[0], rays_per_frame=n_valid,
+               rays_per_s=n_valid / (steady * 1e-3), background_scan_ray_cells=bg_cells,
+               map_cells=m.n_cells(), table_slots=m._cap,
+               query_ms_8_targets_32cubed=min(q), occupied_target_voxels=int((g[0] > 0).sum().item()),
+               lookups_per_query=8 * 32 ** 3 * len(ids),
+               kernels="k_map_scan_rays + k_map_free_apply per scan; k_map_query_grids per query",
+               bound="L2 / atomic latency (random probes of a hash table; not a streaming kernel)",
+               timed="CUDA events around the 9 integrate() calls of a frame (median of frames 2..n) "
+                     "and around get_target_grids_batch (min of 4); inputs resident in HBM")
+    # CPU side: the oracle's restatement of the OctoMap calls on a bounded sample of rays
+    import time
+    from oracle import octomap as oc
+    tree = oc.OcTree(pitches[0])
+    sample = pcd0[lab0 == 0]
+    sample = sample[~np.isnan(sample).any(1)][:: max(1, len(sample) // 400)]
+    t0 = time.time()
+    tree.insertPointCloud(sample, origin=np.zeros(3))
+    dt = time.time() - t0
+    out["cpu_port"] = dict(rays_per_s=len(sample) / dt, rays=len(sample), cores=1, kind="port",
+                           sample="oracle/octomap.py insertPointCloud on a strided sample of the "
+                                  "background scan (pure Python; OctoMap itself is not in the image)")
+    return out
+
+
 def bench_chain(dev, model, runner, rank, world, quick):
     """BASELINE config 5: per-frame chain voxelise -> 3D-CNN -> ICC through HOST buffers.  A frame
     = 8 objects: H2D of the frame's CNN inputs and of its two 32^3 grids per object, the CNN step
@@ -478,7 +545,8 @@ def run_ours(args, rank, world, local):
                                "ncu --set full capture (profiles/r02_conv3_pair_ncu_summary.json), not measured in this run")
     # ---- the two HBM-bound targets north_star names + the per-frame chain (BASELINE configs 1/4/5)
     for name, fn in (("avg_vox", lambda: bench_avg_vox(dev, pk, flush)),
-                     ("icc", lambda: bench_icc(dev, pk, args.quick))):
+                     ("icc", lambda: bench_icc(dev, pk, args.quick)),
+                     ("mapping", lambda: bench_mapping(dev, pk, args.quick))):
         try:
             records[name] = fn()
         except Exception as e:      # a sub-record must not take the headline line down

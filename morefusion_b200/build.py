@@ -38,6 +38,7 @@ SOURCES = {
     "gemm_train.cu": [],
     "train.cu": [],
     "frontend.cu": ["-fmad=false"],
+    "mapping.cu": ["-fmad=false"],
     "precise.cu": [],
 }
 

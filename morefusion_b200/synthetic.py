@@ -305,3 +305,30 @@ def make_icc_scene(N=8, seed=0, D=32, t_noise=0.01, rot_noise_deg=10.0,
                 grid_target=gt_grid, grid_nontarget_empty=gne,
                 transform_init=np.stack(T_init).astype(F32), transform_true=T_true.astype(F32),
                 primitives=prims)
+
+
+def make_depth_frame(seed=0, H=480, W=640, n_objects=8):
+    """A 640x480 synthetic RGB-D frame for the occupancy-map producer (SURVEY.md 8f-3, cfg5
+    geometry): `n_objects` YCB-sized boxes at 0.55-0.65 m in front of a tilted table at 0.9-1.1 m,
+    camera intrinsics of examples/ycb_video/pose_refinement/data/camera_info.yaml scale (fx ~ 600),
+    3 mm depth noise and 5 % dropout (datasets/rgbd_pose_estimation/reindexed.py:70-75).
+    Returns (pcd [H,W,3] f32 with NaN rows, instance label [H,W] int32 (0 = background),
+    class_ids [n_objects], pitches {instance_id: voxel pitch}); instance ids are 1..n_objects."""
+    rs = np.random.RandomState(seed)
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    fx = 600.0
+    z = 0.9 + 0.2 * (v / H)
+    label = np.zeros((H, W), np.int32)
+    class_ids = [1 + (seed + 3 * i) % 21 for i in range(n_objects)]
+    pitches = {0: 0.01}
+    for ins in range(1, n_objects + 1):
+        cu = int(W * (ins - 0.5) / n_objects) + rs.randint(-8, 9)
+        cv = H // 2 - 60 + 30 * (ins % 4)
+        m = (np.abs(u - cu) < 28) & (np.abs(v - cv) < 36)
+        z = np.where(m, 0.55 + 0.03 * (ins % 3) + 0.01 * ((u - cu) / 28.0) ** 2, z)
+        label[m] = ins
+        pitches[ins] = float(YCB_VOXEL_PITCH_32[class_ids[ins - 1]])
+    z = z + 0.003 * rs.randn(H, W)
+    pcd = np.stack([(u - W / 2) * z / fx, (v - H / 2) * z / fx, z], -1).astype(F32)
+    pcd[rs.rand(H, W) < 0.05] = np.nan
+    return pcd, label, class_ids, pitches

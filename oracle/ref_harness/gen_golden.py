@@ -10,7 +10,9 @@ executed through oracle/ref_harness/shim.py (``*_cpu`` = the reference's NumPy
 ``forward_cpu``/``backward_cpu``; ``*_gpu`` = its CuPy kernel source string run
 serially on the CPU).  Inputs are seeded; nothing here reads the oracle except
 ``quaternion_from_matrix`` (a trimesh stand-in used only to initialise the ICC
-link, see shim.install).
+link, see shim.install) and, for ``octree_mapping``, the OctoMap stand-in
+(oracle/octomap.py: the library is absent, so the reference's own
+``MultiInstanceOctreeMapping`` code runs on the restated ``OcTree``).
 """
 
 import os
@@ -305,8 +307,64 @@ def gen_average_distance():
     _save("average_distance", **out)
 
 
+# ---------------------------------------------------------------- occupancy-grid producer
+def octree_mapping_scene(seed=21, H=48, W=64):
+    """Two depth frames (second one from a shifted sensor origin) of three objects in front of a
+    tilted background; instance label image; NaN dropout."""
+    rs = np.random.RandomState(seed)
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    f = 90.0
+    frames = []
+    for fr, org in enumerate(((0.0, 0.0, 0.0), (0.021, -0.013, 0.006))):
+        z = 0.62 + 0.12 * (u / W) + 0.004 * rs.rand(H, W)
+        label = np.zeros((H, W), np.int32)
+        for ins, (cu, cv, ru, rv, zz) in {1: (16, 14, 9, 8, 0.40), 2: (40, 24, 11, 9, 0.45),
+                                          3: (28, 36, 8, 7, 0.36)}.items():
+            m = (np.abs(u - cu - 2 * fr) < ru) & (np.abs(v - cv) < rv)
+            z = np.where(m, zz + 0.02 * ((u - cu) / ru) ** 2 + 0.003 * rs.rand(H, W), z)
+            label[m] = ins
+        pcd = np.stack([(u - W / 2) * z / f, (v - H / 2) * z / f, z], -1).astype(F32)
+        pcd = pcd + np.asarray(org, F32)
+        pcd[rs.rand(H, W) < 0.04] = np.nan
+        frames.append((pcd, label, np.asarray(org, np.float64)))
+    return frames
+
+
+def gen_octree_mapping():
+    shim.install()
+    mod = shim.ref_module("contrib.multi_instance_octree_mapping")
+    frames = octree_mapping_scene()
+    pitches = {1: 0.006, 2: 0.0075, 3: 0.005, 0: 0.01}
+    mapping = mod.MultiInstanceOctreeMapping()
+    for ins in (1, 2, 3, 0):                          # build_octomap order: foreground, then background
+        mapping.initialize(ins, pitch=pitches[ins])
+    for pcd, label, org in frames:
+        for ins in (1, 2, 3, 0):
+            mapping.integrate(ins, label == ins, pcd, origin=org)
+    out = dict(instance_ids=np.array([1, 2, 3, 0]), pitches=np.array([pitches[i] for i in (1, 2, 3, 0)]))
+    for n, (pcd, label, org) in enumerate(frames):
+        out[f"pcd{n}"], out[f"label{n}"], out[f"origin{n}"] = pcd, label, org
+    pcd0, label0, _ = frames[0]
+    for tid in (1, 3):
+        center = np.nanmedian(pcd0[label0 == tid], axis=0)
+        origin = center - (32 / 2 - 0.5) * pitches[tid]       # datasets/rgbd_pose_estimation/base.py:153-156
+        gt, gn, ge = mapping.get_target_grids(tid, dimensions=(32, 32, 32), pitch=pitches[tid], origin=origin)
+        out[f"grid_origin_{tid}"] = origin
+        out[f"ref_grid_target_{tid}"], out[f"ref_grid_nontarget_{tid}"], out[f"ref_grid_empty_{tid}"] = gt, gn, ge
+    for ins in (1, 2, 3, 0):                          # the map itself: keys and float32 log-odds
+        cells = mapping._octrees[ins].cells
+        keys = np.array(sorted(cells), dtype=np.int32).reshape(-1, 3)
+        out[f"cells_keys_{ins}"] = keys
+        out[f"cells_logodds_{ins}"] = np.array([cells[tuple(k)] for k in keys], dtype=F32)
+    occ, emp = mapping.get_target_pcds(2)
+    order = lambda a: a[np.lexsort(a.T[::-1])]
+    out["ref_pcd_occupied_2"], out["ref_pcd_empty_2"] = order(occ), order(emp)
+    _save("octree_mapping", **out)
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
+    gen_octree_mapping()
     gen_average_distance()
     gen_voxelization()
     gen_interpolate()

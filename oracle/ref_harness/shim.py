@@ -368,6 +368,24 @@ def install():
     trimesh.transformations = ttf
     sys.modules["trimesh"] = trimesh
     sys.modules["trimesh.transformations"] = ttf
+    # trimesh.voxel.ops: the two index <-> point helpers get_target_grids touches
+    # (contrib/multi_instance_octree_mapping.py:64-70); trimesh>=3.5 (requirements.txt:23) defines
+    # them as indices * pitch + origin and round((points - origin) / pitch).astype(int).
+    tvox = types.ModuleType("trimesh.voxel")
+    tops = types.ModuleType("trimesh.voxel.ops")
+    tops.matrix_to_points = lambda matrix, pitch, origin: (
+        np.column_stack(np.nonzero(matrix)) * pitch + np.asanyarray(origin, dtype=np.float64))
+    tops.points_to_indices = lambda points, pitch, origin: np.round(
+        (np.asanyarray(points, dtype=np.float64) - np.asanyarray(origin, dtype=np.float64)) / pitch).astype(int)
+    tvox.ops = tops
+    trimesh.voxel = tvox
+    sys.modules["trimesh.voxel"] = tvox
+    sys.modules["trimesh.voxel.ops"] = tops
+    # octomap (octomap-python, requirements.txt:11): absent; the oracle's restatement of the
+    # OcTree calls the reference makes stands in, so that the reference's OWN grid-assembly code
+    # (get_target_grids) runs on top of it.
+    from .. import octomap as _octomap
+    sys.modules["octomap"] = _octomap
 
     base = os.path.join(REF_ROOT, "morefusion")
     for name, sub in [

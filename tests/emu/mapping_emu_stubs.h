@@ -1,0 +1,33 @@
+// TEST INFRASTRUCTURE: host spellings of the CUDA constructs morefusion_b200/csrc/mapping.cu uses,
+// so that g++ can run its kernels serially (tests/test_mapping_emu.py).  One thread at a time, warps
+// of one lane; compiled with -ffp-contract=off (the .cu is built with -fmad=false).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __launch_bounds__(x)
+#define __restrict__
+
+struct emu_dim3 { unsigned x, y, z; };
+static emu_dim3 blockIdx, threadIdx, blockDim, gridDim;
+
+using std::isnan;
+using std::min;
+
+template <class T> static inline T atomicCAS(T* p, T cmp, T val) { T o = *p; if (o == cmp) *p = val; return o; }
+template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }

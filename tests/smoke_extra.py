@@ -85,3 +85,18 @@ def run(dev):
     g, r = m.conv3.weight.grad.float().cpu().numpy().ravel(), want["conv3/W"].ravel()
     cos = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
     assert cos > 0.995, f"conv3 weight gradient (tcgen05 MN-major wgrad) cos={cos}"
+    # ---- occupancy-grid producer: one small scan + query vs the OctoMap restatement
+    from oracle import octomap as oc
+    from test_mapping_emu import make_scene
+    pcd, fg = make_scene(4)
+    ours, ref = mf.contrib.MultiInstanceOctreeMapping(capacity=1 << 14), oc.MultiInstanceOctreeMapping()
+    for mp in (ours, ref):
+        mp.initialize(1, pitch=0.008)
+        mp.initialize(0, pitch=0.02)
+        mp.integrate(1, fg, pcd)
+        mp.integrate(0, ~fg, pcd)
+    org = np.nanmedian(pcd[fg], axis=0) - 7.5 * 0.008
+    got = ours.get_target_grids(1, dimensions=(16, 16, 16), pitch=0.008, origin=org)
+    want = ref.get_target_grids(1, dimensions=(16, 16, 16), pitch=0.008, origin=org)
+    for a, b in zip(got, want):
+        assert np.array_equal(a > 0, b > 0) and np.allclose(a, b, rtol=0, atol=1e-7), "occupancy map"

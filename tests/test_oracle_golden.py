@@ -401,3 +401,30 @@ def test_training_oracle_gradients_match_finite_differences():
         fd = (loss64(wp) - loss64(wm)) / (2 * eps)
         an = float((g64[k].astype(np.float64) * d).sum())
         assert abs(fd - an) <= 2e-3 * abs(an) + 2e-7, (k, fd, an)     # 2e-7: fp64 FD noise floor
+
+
+def test_octree_mapping_oracle_equals_reference_code_over_it():
+    """tests/golden/octree_mapping.npz = the reference's own MultiInstanceOctreeMapping code
+    (integrate / get_target_grids / get_target_pcds) run over the restated OcTree; the oracle's
+    restatement of that class must reproduce it bit for bit (grid assembly, overwrite order)."""
+    from oracle import octomap as oc
+    g = golden("octree_mapping")
+    m = oc.MultiInstanceOctreeMapping()
+    for ins, pitch in zip(g["instance_ids"], g["pitches"]):
+        m.initialize(int(ins), pitch=float(pitch))
+    for n in range(2):
+        for ins in g["instance_ids"]:
+            m.integrate(int(ins), g[f"label{n}"] == ins, g[f"pcd{n}"], origin=g[f"origin{n}"])
+    for ins in g["instance_ids"]:
+        cells = m._octrees[int(ins)].cells
+        keys = g[f"cells_keys_{ins}"]
+        assert len(cells) == len(keys)
+        got = np.array([cells[tuple(k)] for k in keys], np.float32)
+        assert np.array_equal(got, g[f"cells_logodds_{ins}"])
+    for tid, pitch in ((1, 0.006), (3, 0.005)):
+        grids = m.get_target_grids(tid, dimensions=(32, 32, 32), pitch=pitch, origin=g[f"grid_origin_{tid}"])
+        for name, a in zip(("target", "nontarget", "empty"), grids):
+            assert a.dtype == np.float32
+            assert np.array_equal(a, g[f"ref_grid_{name}_{tid}"]), (tid, name)
+    occ, emp = m.get_target_pcds(2)
+    assert np.array_equal(occ, g["ref_pcd_occupied_2"]) and np.array_equal(emp, g["ref_pcd_empty_2"])
