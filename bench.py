@@ -292,7 +292,7 @@ def bench_mapping(dev, pk, quick):
     for i in range(n_frames):
         pcd, label, _, pitches = synthetic.make_depth_frame(seed=i)
         frames.append((torch.as_tensor(pcd, device=dev), torch.as_tensor(label, device=dev)))
-    ids = sorted(pitches)
+    ids = sorted(i for i in pitches if i != 0) + [0]          # foreground instances, then background
     masks = [[(lab == ins) for ins in ids] for _, lab in frames]
     m = MultiInstanceOctreeMapping(device=dev)
     for ins in ids:
@@ -307,8 +307,6 @@ def bench_mapping(dev, pk, quick):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    # ray cells of the background scan of the last frame (the dominant scan): device counter
-    bg_cells = int(m._counters[2 + 2 * (m._scan & 1)].item())
     tids = [i for i in ids if i != 0]
     pcd0, lab0 = frames[0][0].cpu().numpy(), frames[0][1].cpu().numpy()
     origins = [np.nanmedian(pcd0[lab0 == t], axis=0) - 15.5 * pitches[t] for t in tids]
@@ -322,17 +320,35 @@ def bench_mapping(dev, pk, quick):
         torch.cuda.synchronize()
         q.append(e0.elapsed_time(e1))
     steady = sorted(ts[1:])[len(ts[1:]) // 2]
+    # the same frames as ONE labelled scan each (two launches per frame)
+    m2 = MultiInstanceOctreeMapping(device=dev)
+    for ins in ids:
+        m2.initialize(ins, pitch=pitches[ins])
+    labs = [lab.to(torch.int32) for _, lab in frames]
+    tl = []
+    for f, (pcd, _) in enumerate(frames):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        m2.integrate_labels(labs[f], pcd)
+        e1.record()
+        torch.cuda.synchronize()
+        tl.append(e0.elapsed_time(e1))
+    steady_l = sorted(tl[1:])[len(tl[1:]) // 2]
+    assert m2.n_cells() == m.n_cells()
     n_valid = int((~torch.isnan(frames[-1][0]).any(-1)).sum().item())
     out = dict(frame="640x480, 8 instances (class pitch) + background (1 cm), OctoMap sensor model",
-               ms_per_frame_integrate=steady, first_frame_ms=ts[0], rays_per_frame=n_valid,
-               rays_per_s=n_valid / (steady * 1e-3), background_scan_ray_cells=bg_cells,
+               ms_per_frame_labelled_scan=steady_l, first_frame_ms_labelled=tl[0],
+               rays_per_s=n_valid / (steady_l * 1e-3),
+               ms_per_frame_9_integrate_calls=steady, first_frame_ms=ts[0], rays_per_frame=n_valid,
                map_cells=m.n_cells(), table_slots=m._cap,
                query_ms_8_targets_32cubed=min(q), occupied_target_voxels=int((g[0] > 0).sum().item()),
                lookups_per_query=8 * 32 ** 3 * len(ids),
-               kernels="k_map_scan_rays + k_map_free_apply per scan; k_map_query_grids per query",
+               kernels="k_map_scan_hits + k_map_scan_free per scan; k_map_query_grids per query",
                bound="L2 / atomic latency (random probes of a hash table; not a streaming kernel)",
-               timed="CUDA events around the 9 integrate() calls of a frame (median of frames 2..n) "
-                     "and around get_target_grids_batch (min of 4); inputs resident in HBM")
+               timed="CUDA events around integrate_labels() of a frame / around the 9 integrate() calls "
+                     "of a frame (median of frames 2..n) and around get_target_grids_batch (min of 4); "
+                     "inputs resident in HBM")
     # CPU side: the oracle's restatement of the OctoMap calls on a bounded sample of rays
     import time
     from oracle import octomap as oc

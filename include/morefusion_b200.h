@@ -482,38 +482,45 @@ int mf_masks_to_bboxes(const uint8_t* masks, int N, int H, int W, int32_t* bboxe
  * f3  occupancy-grid producer: replaces the OctoMap trees behind
  *     morefusion/contrib/multi_instance_octree_mapping.py:16-34 (initialize / integrate / update)
  *     and :35-94 (get_target_grids).  One caller-owned open-addressing hash table holds the cells
- *     of every instance: keys u64 [capacity] (initialised to all ones), lo f32 / stamp u32 / cnt u32
- *     [capacity] and counters int32 [8] (all initialised to zero ONCE, at allocation; the kernels
- *     keep them consistent afterwards).  capacity is a power of two.  counters[0] = live cells,
- *     counters[1] = table full (sticky; updates were dropped), counters[2 + 2 (scan & 1)] = ray
- *     cells of that scan, counters[3 + 2 (scan & 1)] = its key buffer was too small (the scan's free
- *     cells were NOT applied).  `instance` is the caller's dense index (order of initialize()).
+ *     of every instance: cells [capacity] 16-byte entries {u64 key, f32 log-odds, u32 scan stamp}
+ *     (16-byte aligned; initialised ONCE to key = all ones, rest zero), cnt u32 [capacity] and
+ *     counters int32 [8] (zero at allocation; the kernels keep them consistent afterwards).
+ *     capacity is a power of two.  counters[0] = live cells, counters[1] = table full (sticky;
+ *     updates were dropped).  `instance` is the caller's dense index (order of initialize()).
  * mf_map_integrate: octree.insertPointCloud(points[mask], origin) (:24): points [n,3] f32 (NaN rows
  *     and rows with mask == 0 are skipped; mask may be NULL), sensor origin as floats, OctoMap's
- *     sensor model as float32 log-odds; scan = 1, 2, ... increasing per table; ray_buf u64
- *     [ray_capacity] scratch.
+ *     sensor model as float32 log-odds; scan = 1, 2, ... increasing per table.  Two launches, no
+ *     scratch memory.
+ * mf_map_integrate_labelled: the same for every instance of a labelled frame in ONE scan (what
+ *     datasets/rgbd_pose_estimation/base.py:30-50 and the ROS OctomapServer::insertScan,
+ *     ros/.../OctomapServer.cpp:286-395, do instance by instance): labels [n] int32; lut [lut_n]
+ *     int32 maps label - lut_lo to the dense instance index (-1 = not mapped: pixel skipped);
+ *     inst_resolution [n_instances] f64 -- device arrays.  Equal to one mf_map_integrate per
+ *     instance with mask = (labels == id), the instances' cells being disjoint.
  * mf_map_update_points: octree.updateNodes(points, True) (:30): points [m,3] f64, update = the
  *     log-odds increment applied once per row.
  * mf_map_query_grids: get_target_grids for T targets in one launch: target_index [T] int32 (dense
  *     instance index of each target), pitch [T] f64, origin [T,3] f64, res_factor [n_instances] f64
  *     (= 1 / resolution) -- device arrays; outputs [T,X,Y,Z] f32, every element written.
- * mf_map_rehash: move every cell of the old arrays into a larger, freshly initialised table.
+ * mf_map_rehash: move every cell of the old table into a larger, freshly initialised one.
  * ------------------------------------------------------------------------ */
 int mf_map_integrate(const float* points, const uint8_t* mask, int64_t n, float ox, float oy,
                      float oz, double resolution, int instance, uint32_t scan, float hit,
-                     float miss, float lo_min, float lo_max, void* keys, void* lo, void* stamp,
-                     void* cnt, int64_t capacity, int32_t* counters, void* ray_buf,
-                     int64_t ray_capacity, void* stream);
+                     float miss, float lo_min, float lo_max, void* cells, void* cnt,
+                     int64_t capacity, int32_t* counters, void* stream);
+int mf_map_integrate_labelled(const float* points, const int32_t* labels, int64_t n, float ox,
+                              float oy, float oz, const int32_t* lut, int lut_lo, int lut_n,
+                              const double* inst_resolution, uint32_t scan, float hit, float miss,
+                              float lo_min, float lo_max, void* cells, void* cnt, int64_t capacity,
+                              int32_t* counters, void* stream);
 int mf_map_update_points(const double* points, int64_t m, double resolution, int instance,
-                         float update, float lo_min, float lo_max, void* keys, void* lo,
-                         void* stamp, void* cnt, int64_t capacity, int32_t* counters, void* stream);
+                         float update, float lo_min, float lo_max, void* cells, void* cnt,
+                         int64_t capacity, int32_t* counters, void* stream);
 int mf_map_query_grids(const int32_t* target_index, const double* pitch, const double* origin,
                        int T, int X, int Y, int Z, const double* res_factor, int n_instances,
-                       void* keys, void* lo, void* stamp, void* cnt, int64_t capacity,
-                       int32_t* counters, float* grid_target, float* grid_nontarget,
-                       float* grid_empty, void* stream);
-int mf_map_rehash(const void* old_keys, const void* old_lo, const void* old_stamp,
-                  int64_t old_capacity, void* keys, void* lo, void* stamp, void* cnt,
+                       void* cells, void* cnt, int64_t capacity, int32_t* counters,
+                       float* grid_target, float* grid_nontarget, float* grid_empty, void* stream);
+int mf_map_rehash(const void* old_cells, int64_t old_capacity, void* cells, void* cnt,
                   int64_t capacity, int32_t* counters, void* stream);
 
 /* ------------------------------------------------------------------------

@@ -88,11 +88,13 @@ SIGNATURES = {
     "mf_pointcloud_from_depth": (c_i, [c_p, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_p, c_p]),
     "mf_masks_to_bboxes": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
     "mf_map_integrate": (c_i, [c_p, c_p, c_i64, c_f, c_f, c_f, c_d, c_i, ctypes.c_uint32, c_f, c_f, c_f, c_f,
-                                c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_p]),
-    "mf_map_update_points": (c_i, [c_p, c_i64, c_d, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
-    "mf_map_query_grids": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64,
-                                  c_p, c_p, c_p, c_p, c_p]),
-    "mf_map_rehash": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+                                c_p, c_p, c_i64, c_p, c_p]),
+    "mf_map_integrate_labelled": (c_i, [c_p, c_p, c_i64, c_f, c_f, c_f, c_p, c_i, c_i, c_p, ctypes.c_uint32,
+                                         c_f, c_f, c_f, c_f, c_p, c_p, c_i64, c_p, c_p]),
+    "mf_map_update_points": (c_i, [c_p, c_i64, c_d, c_i, c_f, c_f, c_f, c_p, c_p, c_i64, c_p, c_p]),
+    "mf_map_query_grids": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i64, c_p,
+                                  c_p, c_p, c_p, c_p]),
+    "mf_map_rehash": (c_i, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p]),
     "mf_icc_max_group_size": (c_i, [c_i]),
     "mf_icc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
     "mf_icc_run": (c_i, [c_i, c_i, c_i, c_f, c_f] + [c_p] * 7 + [c_i] + [c_p] * 9

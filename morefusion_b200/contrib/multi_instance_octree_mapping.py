@@ -34,10 +34,9 @@ def _logodds(p):
 class MultiInstanceOctreeMapping:
     PROB_HIT, PROB_MISS, CLAMP_MIN, CLAMP_MAX = 0.7, 0.4, 0.1192, 0.971     # OctoMap defaults
 
-    def __init__(self, device=None, capacity=1 << 22, ray_capacity=1 << 26):
-        """capacity: initial number of hash slots (power of two; grows x4 when a quarter full).
-        ray_capacity: cells one scan's rays may cross in total (8 bytes each, allocated at the first
-        scan; a 640x480 background scan at 1 cm crosses ~4e7)."""
+    def __init__(self, device=None, capacity=1 << 22):
+        """capacity: initial number of hash slots (power of two, 20 bytes each; the table grows x4
+        when a quarter full)."""
         if capacity < 64 or capacity & (capacity - 1):
             raise ValueError("capacity must be a power of two >= 64")
         self.device = torch.device("cuda" if device is None else device)
@@ -45,28 +44,36 @@ class MultiInstanceOctreeMapping:
         self._pitch = []                         # per dense index
         self._scan = 0
         self._cap = int(capacity)
-        self._ray_cap = int(ray_capacity)
         self._hit, self._miss = _logodds(self.PROB_HIT), _logodds(self.PROB_MISS)
         self._lo_min, self._lo_max = _logodds(self.CLAMP_MIN), _logodds(self.CLAMP_MAX)
         self._alloc_table(self._cap)
         self._counters = torch.zeros(8, dtype=torch.int32, device=self.device)
-        self._ray_buf = None
         self._host_counters = None
         self._pending = None                     # event of the last asynchronous counter read-back
         self._res_factor = None                  # cached device array of 1 / pitch
+        self._lut = None                         # cached (lut, lut_lo, resolutions) device arrays
 
     # ------------------------------------------------------------------ table management
     def _alloc_table(self, cap):
         dev = self.device
-        self._keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
-        self._lo = torch.zeros(cap, dtype=torch.float32, device=dev)
-        self._stamp = torch.zeros(cap, dtype=torch.int32, device=dev)
+        # 16-byte cells {u64 key | f32 log-odds, u32 stamp}: column 0 = key (-1 = free slot),
+        # column 1 = the value / stamp pair
+        self._cells = torch.zeros((cap, 2), dtype=torch.int64, device=dev)
+        self._cells[:, 0] = -1
         self._cnt = torch.zeros(cap, dtype=torch.int32, device=dev)
         self._cap = cap
 
+    @property
+    def _keys(self):
+        return self._cells[:, 0]
+
+    @property
+    def _lo(self):
+        return self._cells.view(torch.float32)[:, 2]
+
     def _table_args(self):
         p = _lib.ptr
-        return (p(self._keys), p(self._lo), p(self._stamp), p(self._cnt), self._cap, p(self._counters))
+        return (p(self._cells), p(self._cnt), self._cap, p(self._counters))
 
     def _read_back(self):
         """Asynchronous copy of the counters into pinned host memory; looked at by the next call."""
@@ -87,20 +94,16 @@ class MultiInstanceOctreeMapping:
             raise RuntimeError(
                 f"occupancy map: hash table of {self._cap} slots overflowed during the previous "
                 "operation and updates were dropped; construct the mapping with a larger capacity")
-        if c[3] or c[5]:
-            raise RuntimeError(
-                f"occupancy map: the previous scan's rays cross more than ray_capacity="
-                f"{self._ray_cap} cells; its free-space update was not applied")
         if c[0] * 4 > self._cap:
             self._grow(self._cap * 4)
 
     def _grow(self, new_cap):
         L = _lib.lib()
-        old = (self._keys, self._lo, self._stamp, self._cap)
+        old = (self._cells, self._cap)
         self._alloc_table(new_cap)
         with self._dev_ctx():
-            _lib.check(L.mf_map_rehash(_lib.ptr(old[0]), _lib.ptr(old[1]), _lib.ptr(old[2]), old[3],
-                                       *self._table_args(), _lib.stream()), "map_rehash")
+            _lib.check(L.mf_map_rehash(_lib.ptr(old[0]), old[1], *self._table_args(), _lib.stream()),
+                       "map_rehash")
 
     def _dev_ctx(self):
         return torch.cuda.device(self.device)
@@ -120,6 +123,7 @@ class MultiInstanceOctreeMapping:
         self._ids[instance_id] = len(self._ids)
         self._pitch.append(float(pitch))
         self._res_factor = None
+        self._lut = None
 
     def integrate(self, instance_id, mask, pcd, origin=(0, 0, 0)):
         """octree.insertPointCloud(pcd[mask & nonnan], origin) (:21-27).  mask [H,W] bool, pcd
@@ -139,15 +143,52 @@ class MultiInstanceOctreeMapping:
         self._check()
         if n == 0:
             return
-        if self._ray_buf is None:
-            self._ray_buf = torch.empty(self._ray_cap, dtype=torch.int64, device=dev)
         self._scan += 1
         with self._dev_ctx():
             _lib.check(_lib.lib().mf_map_integrate(
                 _lib.ptr(pts), _lib.ptr(msk), n, float(org[0]), float(org[1]), float(org[2]),
                 self._pitch[idx], idx, self._scan, float(self._hit), float(self._miss),
-                float(self._lo_min), float(self._lo_max), *self._table_args(),
-                _lib.ptr(self._ray_buf), self._ray_cap, _lib.stream()), "map_integrate")
+                float(self._lo_min), float(self._lo_max), *self._table_args(), _lib.stream()),
+                "map_integrate")
+            self._read_back()
+
+    def integrate_labels(self, label, pcd, origin=(0, 0, 0)):
+        """Every initialised instance of a labelled frame in one scan: equal to
+        ``for i in instance_ids: integrate(i, label == i, pcd, origin)`` (what build_octomap,
+        datasets/rgbd_pose_estimation/base.py:30-50, does instance by instance), as two launches.
+        label [H,W] integer image; pixels whose label is not an initialised instance are skipped."""
+        dev = self.device
+        pts = torch.as_tensor(pcd).to(device=dev, dtype=torch.float32).contiguous()
+        lab = torch.as_tensor(label).to(device=dev)
+        if pts.dim() < 2 or pts.shape[-1] != 3 or tuple(lab.shape) != tuple(pts.shape[:-1]):
+            raise ValueError("pcd must be [..., 3] and label its leading shape")
+        if lab.dtype.is_floating_point or lab.dtype == torch.bool:
+            raise ValueError("label must be an integer image")
+        _lib.require_cuda(pts, lab)
+        lab = lab.to(torch.int32).contiguous()
+        n = pts.numel() // 3
+        org = np.asarray(origin, dtype=np.float64).astype(np.float32)
+        self._check()
+        if n == 0 or not self._ids:
+            return
+        if self._lut is None:
+            ids = [int(i) for i in self._ids]            # instance ids must be integers here
+            lo, hi = min(ids), max(ids)
+            if hi - lo >= 1 << 20:
+                raise ValueError("instance ids span too wide a range for a label look-up table")
+            lut = np.full(hi - lo + 1, -1, np.int32)
+            for i, idx in self._ids.items():
+                lut[int(i) - lo] = idx
+            self._lut = (torch.as_tensor(lut).to(dev), lo,
+                         torch.as_tensor(np.asarray(self._pitch, dtype=np.float64)).to(dev))
+        lut, lo, res = self._lut
+        self._scan += 1
+        with self._dev_ctx():
+            _lib.check(_lib.lib().mf_map_integrate_labelled(
+                _lib.ptr(pts), _lib.ptr(lab), n, float(org[0]), float(org[1]), float(org[2]),
+                _lib.ptr(lut), lo, lut.numel(), _lib.ptr(res), self._scan, float(self._hit),
+                float(self._miss), float(self._lo_min), float(self._lo_max), *self._table_args(),
+                _lib.stream()), "map_integrate_labelled")
             self._read_back()
 
     def update(self, instance_id, occupied):
@@ -232,8 +273,9 @@ class MultiInstanceOctreeMapping:
     def cells(self, instance_id):
         """{(kx, ky, kz): log-odds} of one instance (host dict; for tests)."""
         idx = self._ids[instance_id]
-        keys = self._keys.cpu().numpy()
-        lo = self._lo.cpu().numpy()
+        cells = self._cells.cpu()
+        keys = cells[:, 0].numpy()
+        lo = cells.view(torch.float32)[:, 2].numpy()
         sel = (keys != -1) & (((keys >> 48) & 0xFFFF) == idx)
         out = {}
         for k, v in zip(keys[sel].tolist(), lo[sel].tolist()):

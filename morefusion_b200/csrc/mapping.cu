@@ -7,17 +7,21 @@
 // at most once per scan, end points win over free cells" (OccupancyOcTreeBase::computeUpdate).
 //
 // B200 design.  A pruned octree is, for search(depth=0), a flat key -> log-odds map: ONE open-
-// addressing hash table in HBM holds every instance's cells (key = instance:16 | kx:16 | ky:16 |
-// kz:16), so a scan is two launches and the three 32^3 grids of all targets are one launch:
-//   k_map_scan_rays   one thread per pixel: end-point ("hit") update + the DDA, run twice - once
-//                     to count the ray's cells, once to write their keys into a slice of the key
-//                     buffer obtained with one warp-aggregated atomicAdd.  The DDA is sequential
-//                     double arithmetic per ray (tMax accumulates rounding exactly as the library's
-//                     does), so the memory work is split off:
-//   k_map_free_apply  one thread per (ray, cell) key: probe / insert, test-before-atomic on the
-//                     cell's scan stamp; the first toucher of a cell in this scan applies the miss
-//                     update.  Millions of independent probes keep the L2 / HBM pipes full, which a
-//                     thread-per-ray walk with dependent probes cannot.
+// addressing hash table in HBM holds every instance's cells as 16-byte entries
+// {key = instance:16 | kx:16 | ky:16 | kz:16, float log-odds, u32 scan stamp}: a probe is one
+// 16-byte L2 access that brings the key, the value and the stamp together.  A scan is two launches,
+// the three 32^3 grids of all targets are one launch:
+//   k_map_scan_hits   one thread per pixel: end-point ("hit") update.
+//   k_map_scan_free   one thread per pixel walks its ray (the DDA is sequential double arithmetic:
+//                     tMax accumulates rounding exactly as the library's does).  The 32 lanes of a
+//                     warp are 32 neighbouring pixels; at a 1 cm cell and <1.7 mm between rays they
+//                     sit in the same one to five cells at every step, so the lanes of a step are
+//                     grouped by key (__match_any_sync) and only one lane per distinct cell probes
+//                     the table; a cell already stamped by this scan costs that one read
+//                     (test-before-atomic), the first toucher applies the miss update.  No key
+//                     buffer: the first version wrote every (ray, cell) key to HBM and applied them
+//                     in a second kernel (profiles/r02_mapping_history.md: 39 M keys, 310 MB written
+//                     and read back, 130 visits per distinct cell).
 //   k_map_query_grids one thread per (target, voxel): looks the voxel centre up in every instance,
 //                     in insertion order, and writes grid_target / grid_nontarget / grid_empty with
 //                     the reference's overwrite rules (multi_instance_octree_mapping.py:85-92).
@@ -38,22 +42,18 @@ namespace mf {
 typedef unsigned long long u64;
 static constexpr u64 MAP_EMPTY = ~0ull;
 static constexpr int TREE_MAX_VAL = 32768;
-#ifdef MF_HOST_EMU
-static constexpr int WARP_LAST = 0;
-#else
-static constexpr int WARP_LAST = 31;
-#endif
+
+struct __align__(16) MapCell {
+  u64 key;          // MAP_EMPTY = free slot
+  float lo;         // log-odds, 0 for a slot that has never been updated
+  unsigned stamp;   // 2*scan (missed in scan) / 2*scan+1 (hit in scan), monotonic
+};
 
 struct MapTable {
-  u64* keys;        // [cap]   MAP_EMPTY = free slot
-  float* lo;        // [cap]   log-odds, 0 for a slot that has never been updated
-  unsigned* stamp;  // [cap]   2*scan (missed in scan) / 2*scan+1 (hit in scan), monotonic
+  MapCell* cells;   // [cap]
   unsigned* cnt;    // [cap]   pending updateNodes() multiplicity (0 between calls)
   unsigned mask;    // cap - 1 (cap is a power of two)
-  int* counters;    // [0] live entries  [1] table overflow (sticky)
-                    // [2 + 2 (scan & 1)] ray keys of the scan, [3 + 2 (scan & 1)] key buffer too small:
-                    // the scan's second launch re-zeroes the other parity's pair, so there is no
-                    // memset node and the host can still read a scan's pair until the next scan ends
+  int* counters;    // [0] live entries  [1] table full (sticky; updates were dropped)
 };
 
 __device__ __forceinline__ unsigned map_hash(u64 k) {
@@ -63,16 +63,31 @@ __device__ __forceinline__ unsigned map_hash(u64 k) {
   return (unsigned)(k >> 32);
 }
 
-// slot of `key`, inserting it when absent; -1 when the table is full (overflow flag raised)
-__device__ __forceinline__ int map_find_or_insert(const MapTable& t, u64 key) {
+// one 16-byte L2 access (other SMs update cells during a scan: never through the incoherent L1)
+__device__ __forceinline__ MapCell map_load(const MapCell* c) {
+  const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(c));
+  MapCell r;
+  r.key = v.x;
+  r.lo = __uint_as_float((unsigned)(v.y & 0xffffffffull));
+  r.stamp = (unsigned)(v.y >> 32);
+  return r;
+}
+
+// slot of `key`, inserting it when absent; -1 when the table is full (overflow flag raised).
+// *seen = the cell as loaded (stamp 0 for a cell this call inserted or lost the race for: a stale
+// stamp only costs a redundant atomicMax, never an update).
+__device__ __forceinline__ int map_find_or_insert(const MapTable& t, u64 key, MapCell* seen) {
   unsigned s = map_hash(key) & t.mask;
   for (unsigned n = 0; n <= t.mask; ++n) {
-    u64 k = t.keys[s];
-    if (k == key) return (int)s;
-    if (k == MAP_EMPTY) {
-      const u64 old = atomicCAS(t.keys + s, MAP_EMPTY, key);
-      if (old == MAP_EMPTY) { atomicAdd(t.counters, 1); return (int)s; }
-      if (old == key) return (int)s;
+    const MapCell c = map_load(t.cells + s);
+    if (c.key == key) { *seen = c; return (int)s; }
+    if (c.key == MAP_EMPTY) {
+      const u64 old = atomicCAS(&t.cells[s].key, MAP_EMPTY, key);
+      if (old == MAP_EMPTY || old == key) {
+        if (old == MAP_EMPTY) atomicAdd(t.counters, 1);
+        seen->key = key; seen->lo = 0.f; seen->stamp = 0u;
+        return (int)s;
+      }
     }
     s = (s + 1) & t.mask;
   }
@@ -80,12 +95,12 @@ __device__ __forceinline__ int map_find_or_insert(const MapTable& t, u64 key) {
   return -1;
 }
 
-__device__ __forceinline__ int map_find(const MapTable& t, u64 key) {
+__device__ __forceinline__ int map_find(const MapTable& t, u64 key, MapCell* seen) {
   unsigned s = map_hash(key) & t.mask;
   for (unsigned n = 0; n <= t.mask; ++n) {
-    const u64 k = __ldg(t.keys + s);
-    if (k == key) return (int)s;
-    if (k == MAP_EMPTY) return -1;
+    const MapCell c = map_load(t.cells + s);
+    if (c.key == key) { *seen = c; return (int)s; }
+    if (c.key == MAP_EMPTY) return -1;
     s = (s + 1) & t.mask;
   }
   return -1;
@@ -96,6 +111,17 @@ __device__ __forceinline__ float map_clamped_add(float v, float upd, float lo_mi
   if (v < lo_min) v = lo_min;
   if (v > lo_max) v = lo_max;
   return v;
+}
+
+// the once-per-scan update of a cell: the thread whose atomicMax raises the stamp to `want` owns it
+__device__ __forceinline__ void map_scan_update(const MapTable& t, int s, const MapCell& seen,
+                                                unsigned want, float upd, float lo_min, float lo_max) {
+  if (seen.stamp >= want) return;                                  // already done in this scan
+  if (atomicMax(&t.cells[s].stamp, want) < want) {
+    // nobody else writes lo in this launch; the value is from an earlier launch (or 0)
+    const float v = __ldcg(&t.cells[s].lo);
+    t.cells[s].lo = map_clamped_add(v, upd, lo_min, lo_max);
+  }
 }
 
 // OcTreeBaseImpl::coordToKeyChecked for one axis: floor(coord / resolution) + 32768, -1 if outside
@@ -109,137 +135,155 @@ __device__ __forceinline__ u64 pack_key(int inst, int kx, int ky, int kz) {
          (u64)(unsigned)kz;
 }
 
-// The key ray of computeRayKeys (oracle/octomap.py::OcTree.computeRayKeys has the line-by-line
-// commentary): first cell included, end cell excluded.  Returns the number of cells; when `out`
-// is non-null also writes their packed keys.
-__device__ int ray_keys(const float o[3], const float e[3], const int ko[3], const int ke[3],
-                        double res, int inst, u64* out) {
-  if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return 0;
-  int n = 0;
-  if (out) out[n] = pack_key(inst, ko[0], ko[1], ko[2]);
-  ++n;
-  float d[3] = {__fsub_rn(e[0], o[0]), __fsub_rn(e[1], o[1]), __fsub_rn(e[2], o[2])};
-  const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])),
-                              __fmul_rn(d[2], d[2]));
-  const float length = (float)sqrt((double)nsq);
-  int step[3], cur[3];
-  double tmax[3], tdelta[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    d[i] = __fdiv_rn(d[i], length);
-    cur[i] = ko[i];
-    step[i] = d[i] > 0.f ? 1 : (d[i] < 0.f ? -1 : 0);
-    if (step[i] != 0) {
-      double border = ((double)(cur[i] - TREE_MAX_VAL) + 0.5) * res;
-      border += (double)(float)((double)step[i] * res * 0.5);
-      tmax[i] = (border - (double)o[i]) / (double)d[i];
-      tdelta[i] = res / fabs((double)d[i]);
-    } else {
-      tmax[i] = 1.7976931348623157e308;
-      tdelta[i] = 1.7976931348623157e308;
-    }
-  }
-  const double flen = (double)length;
-  for (;;) {
-    int dim;
-    if (tmax[0] < tmax[1]) dim = (tmax[0] < tmax[2]) ? 0 : 2;
-    else dim = (tmax[1] < tmax[2]) ? 1 : 2;
-    // no dynamic indexing of the register arrays
-    if (dim == 0) { cur[0] += step[0]; tmax[0] += tdelta[0]; }
-    else if (dim == 1) { cur[1] += step[1]; tmax[1] += tdelta[1]; }
-    else { cur[2] += step[2]; tmax[2] += tdelta[2]; }
-    if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
-    if (fmin(fmin(tmax[0], tmax[1]), tmax[2]) > flen) break;
-    const int c = dim == 0 ? cur[0] : (dim == 1 ? cur[1] : cur[2]);
-    if (c < 0 || c >= 2 * TREE_MAX_VAL) break;
-    if (out) out[n] = pack_key(inst, cur[0], cur[1], cur[2]);
-    ++n;
-  }
-  return n;
-}
-
 struct ScanParams {
   const float* points;        // [n,3]
-  const unsigned char* mask;  // [n] or null
+  const unsigned char* mask;  // [n] or null          (single-instance scan)
+  const int* labels;          // [n] or null          (labelled frame: every instance in one scan)
+  const int* lut;             // [lut_n] label - lut_lo -> dense instance index, -1 = not mapped
+  const double* inst_res;     // [n_inst] resolution of each instance (labelled frame)
+  int lut_lo, lut_n;
   int n;
   float ox, oy, oz;           // sensor origin (point3d: floats)
-  double res, res_factor;
+  double res;                 // single-instance scan
   int inst;
   unsigned scan;
   float hit, miss, lo_min, lo_max;
-  u64* ray_buf;
-  int ray_cap;
 };
 
-__global__ void __launch_bounds__(256)
-k_map_scan_rays(ScanParams p, MapTable t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+// a pixel's end point, its instance / resolution and the keys of both ends; false for masked,
+// unmapped and NaN pixels
+__device__ __forceinline__ bool scan_pixel(const ScanParams& p, int i, float e[3], int ko[3],
+                                           int ke[3], bool* ok_o, bool* ok_e, int* inst,
+                                           double* res) {
   bool valid = i < p.n;
-  float e[3] = {0.f, 0.f, 0.f};
+  e[0] = e[1] = e[2] = 0.f;
+  *inst = p.inst;
+  *res = p.res;
   if (valid) {
     e[0] = p.points[3 * (size_t)i];
     e[1] = p.points[3 * (size_t)i + 1];
     e[2] = p.points[3 * (size_t)i + 2];
     valid = !(isnan(e[0]) || isnan(e[1]) || isnan(e[2])) && (!p.mask || p.mask[i]);
-  }
-  const float o[3] = {p.ox, p.oy, p.oz};
-  int ko[3], ke[3];
-  bool ok_o = true, ok_e = true;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    ko[a] = coord_to_key((double)o[a], p.res_factor);
-    ke[a] = coord_to_key((double)e[a], p.res_factor);
-    ok_o &= ko[a] >= 0;
-    ok_e &= ke[a] >= 0;
-  }
-  // end point: hit update by the first thread that reaches the cell in this scan
-  if (valid && ok_e) {
-    const int s = map_find_or_insert(t, pack_key(p.inst, ke[0], ke[1], ke[2]));
-    if (s >= 0) {
-      const unsigned want = 2u * p.scan + 1u;
-      if (atomicMax(t.stamp + s, want) < want)
-        t.lo[s] = map_clamped_add(t.lo[s], p.hit, p.lo_min, p.lo_max);
+    if (valid && p.labels) {
+      const int l = p.labels[i] - p.lut_lo;
+      const int q = (l >= 0 && l < p.lut_n) ? p.lut[l] : -1;
+      valid = q >= 0;
+      if (valid) { *inst = q; *res = p.inst_res[q]; }
     }
   }
-  // free cells: count, take a slice of the key buffer (one atomic per warp), write the keys
-  const bool ray = valid && ok_o && ok_e;
-  const int n = ray ? ray_keys(o, e, ko, ke, p.res, p.inst, nullptr) : 0;
-  int incl = n;
+  const double res_factor = 1.0 / *res;
+  const float o[3] = {p.ox, p.oy, p.oz};
+  *ok_o = *ok_e = true;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
+  for (int a = 0; a < 3; ++a) {
+    ko[a] = coord_to_key((double)o[a], res_factor);
+    ke[a] = coord_to_key((double)e[a], res_factor);
+    *ok_o &= ko[a] >= 0;
+    *ok_e &= ke[a] >= 0;
   }
-  const int total = __shfl_sync(0xffffffffu, incl, WARP_LAST);
-  int base = 0;
-  int* ctr = t.counters + 2 + 2 * (int)(p.scan & 1u);
-  if (lane == WARP_LAST && total > 0) base = atomicAdd(ctr, total);
-  base = __shfl_sync(0xffffffffu, base, WARP_LAST);
-  if (n > 0) {
-    const long long off = (long long)base + incl - n;
-    if (off + n <= (long long)p.ray_cap) ray_keys(o, e, ko, ke, p.res, p.inst, p.ray_buf + off);
-    else ctr[1] = 1;
-  }
+  return valid;
 }
 
 __global__ void __launch_bounds__(256)
-k_map_free_apply(const u64* __restrict__ ray_buf, int ray_cap, unsigned scan, float miss,
-                 float lo_min, float lo_max, MapTable t) {
-  const int* ctr = t.counters + 2 + 2 * (int)(scan & 1u);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {    // next scan's pair (nobody reads it during this scan)
-    t.counters[2 + 2 * (int)(~scan & 1u)] = 0;
-    t.counters[3 + 2 * (int)(~scan & 1u)] = 0;
+k_map_scan_hits(ScanParams p, MapTable t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float e[3];
+  int ko[3], ke[3], inst;
+  double res;
+  bool ok_o, ok_e;
+  if (!scan_pixel(p, i, e, ko, ke, &ok_o, &ok_e, &inst, &res) || !ok_e) return;
+  MapCell seen;
+  const int s = map_find_or_insert(t, pack_key(inst, ke[0], ke[1], ke[2]), &seen);
+  if (s >= 0) map_scan_update(t, s, seen, 2u * p.scan + 1u, p.hit, p.lo_min, p.lo_max);
+}
+
+// The key ray of computeRayKeys (oracle/octomap.py::OcTree.computeRayKeys has the line-by-line
+// commentary): first cell included, end cell excluded; every cell of the ray that this scan has not
+// hit gets the miss update.  Runs after k_map_scan_hits of the same scan (stream order).
+__global__ void __launch_bounds__(256)
+k_map_scan_free(ScanParams p, MapTable t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  float e[3];
+  int ko[3], ke[3], inst;
+  double res;
+  bool ok_o, ok_e;
+  const bool valid = scan_pixel(p, i, e, ko, ke, &ok_o, &ok_e, &inst, &res);
+  bool act = valid && ok_o && ok_e && !(ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]);
+  const float o[3] = {p.ox, p.oy, p.oz};
+  int step0 = 0, step1 = 0, step2 = 0, cur0 = ko[0], cur1 = ko[1], cur2 = ko[2];
+  double tmax0 = 0.0, tmax1 = 0.0, tmax2 = 0.0, td0 = 0.0, td1 = 0.0, td2 = 0.0, flen = 0.0;
+  if (act) {
+    float d[3] = {__fsub_rn(e[0], o[0]), __fsub_rn(e[1], o[1]), __fsub_rn(e[2], o[2])};
+    const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])),
+                                __fmul_rn(d[2], d[2]));
+    const float length = (float)sqrt((double)nsq);
+    flen = (double)length;
+    int step[3];
+    double tmax[3], tdelta[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      d[a] = __fdiv_rn(d[a], length);
+      step[a] = d[a] > 0.f ? 1 : (d[a] < 0.f ? -1 : 0);
+      if (step[a] != 0) {
+        double border = ((double)(ko[a] - TREE_MAX_VAL) + 0.5) * res;
+        border += (double)(float)((double)step[a] * res * 0.5);
+        tmax[a] = (border - (double)o[a]) / (double)d[a];
+        tdelta[a] = res / fabs((double)d[a]);
+      } else {
+        tmax[a] = 1.7976931348623157e308;
+        tdelta[a] = 1.7976931348623157e308;
+      }
+    }
+    step0 = step[0]; step1 = step[1]; step2 = step[2];
+    tmax0 = tmax[0]; tmax1 = tmax[1]; tmax2 = tmax[2];
+    td0 = tdelta[0]; td1 = tdelta[1]; td2 = tdelta[2];
   }
-  if (ctr[1]) return;                           // scan did not fit the key buffer: leave it unapplied
-  const int total = min(ctr[0], ray_cap);
-  const unsigned want = 2u * scan;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int s = map_find_or_insert(t, ray_buf[i]);
-    if (s < 0) continue;
-    if (*(volatile unsigned*)(t.stamp + s) >= want) continue;      // already missed or hit in this scan
-    if (atomicMax(t.stamp + s, want) < want)
-      t.lo[s] = map_clamped_add(t.lo[s], miss, lo_min, lo_max);
+  const unsigned want = 2u * p.scan;
+  u64 key = pack_key(inst, cur0, cur1, cur2);
+  for (;;) {
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (!bal) break;
+    if (act) {
+      // lanes of this step that stand in the same cell: the lowest one does the table work.  Its
+      // 16-byte probe is issued here and looked at after the DDA advance below (ALU work that
+      // does not depend on it), which hides most of the L2 latency.
+      const unsigned peers = __match_any_sync(bal, key);
+      const bool lead = (__ffs(peers) - 1) == lane;
+      const unsigned s0 = map_hash(key) & t.mask;
+      MapCell c;
+      c.key = 0; c.lo = 0.f; c.stamp = 0u;
+      if (lead) c = map_load(t.cells + s0);
+      const u64 kcur = key;
+      // advance to the next cell.  The library's selection
+      //   if (tMax0 < tMax1) dim = tMax0 < tMax2 ? 0 : 2;  else dim = tMax1 < tMax2 ? 1 : 2;
+      // as predicates (no divergence); "min(tMax) > length" <=> every tMax > length
+      const bool lt01 = tmax0 < tmax1, lt02 = tmax0 < tmax2, lt12 = tmax1 < tmax2;
+      const bool a0 = lt01 && lt02, a1 = !lt01 && lt12;
+      const bool a2 = !(a0 || a1);
+      const double n0 = tmax0 + td0, n1 = tmax1 + td1, n2 = tmax2 + td2;
+      tmax0 = a0 ? n0 : tmax0;
+      tmax1 = a1 ? n1 : tmax1;
+      tmax2 = a2 ? n2 : tmax2;
+      cur0 += a0 ? step0 : 0;
+      cur1 += a1 ? step1 : 0;
+      cur2 += a2 ? step2 : 0;
+      const int cc = a0 ? cur0 : (a1 ? cur1 : cur2);
+      const bool at_end = cur0 == ke[0] && cur1 == ke[1] && cur2 == ke[2];
+      const bool over = tmax0 > flen && tmax1 > flen && tmax2 > flen;
+      act = !(at_end || over || cc < 0 || cc >= 2 * TREE_MAX_VAL);
+      key = pack_key(inst, cur0, cur1, cur2);
+      // the probe: the common case is "first slot holds the key and is already stamped"
+      if (lead) {
+        if (c.key == kcur) {
+          map_scan_update(t, (int)s0, c, want, p.miss, p.lo_min, p.lo_max);
+        } else {
+          MapCell seen;
+          const int s = map_find_or_insert(t, kcur, &seen);
+          if (s >= 0) map_scan_update(t, s, seen, want, p.miss, p.lo_min, p.lo_max);
+        }
+      }
+    }
   }
 }
 
@@ -254,8 +298,9 @@ k_map_update_count(const double* __restrict__ pts, int m, double res_factor, int
   const int kx = coord_to_key(pts[3 * (size_t)i], res_factor);
   const int ky = coord_to_key(pts[3 * (size_t)i + 1], res_factor);
   const int kz = coord_to_key(pts[3 * (size_t)i + 2], res_factor);
-  if (kx < 0 || ky < 0 || kz < 0) return;       // NaN lands here too: floor(NaN) -> INT_MIN
-  const int s = map_find_or_insert(t, pack_key(inst, kx, ky, kz));
+  if (kx < 0 || ky < 0 || kz < 0) return;       // NaN rows land here too
+  MapCell seen;
+  const int s = map_find_or_insert(t, pack_key(inst, kx, ky, kz), &seen);
   if (s >= 0) atomicAdd(t.cnt + s, 1u);
 }
 
@@ -268,13 +313,14 @@ k_map_update_apply(const double* __restrict__ pts, int m, double res_factor, int
   const int ky = coord_to_key(pts[3 * (size_t)i + 1], res_factor);
   const int kz = coord_to_key(pts[3 * (size_t)i + 2], res_factor);
   if (kx < 0 || ky < 0 || kz < 0) return;
-  const int s = map_find(t, pack_key(inst, kx, ky, kz));
+  MapCell seen;
+  const int s = map_find(t, pack_key(inst, kx, ky, kz), &seen);
   if (s < 0) return;
   unsigned k = atomicExch(t.cnt + s, 0u);
   if (!k) return;
-  float v = t.lo[s];
+  float v = seen.lo;                            // written by an earlier launch only
   for (; k; --k) v = map_clamped_add(v, upd, lo_min, lo_max);
-  t.lo[s] = v;
+  t.cells[s].lo = v;
 }
 
 // get_target_grids for T targets at once (multi_instance_octree_mapping.py:35-94)
@@ -301,9 +347,9 @@ k_map_query_grids(const int* __restrict__ target_index, const double* __restrict
     const double rf = res_factor[q];
     const int kx = coord_to_key(cx, rf), ky = coord_to_key(cy, rf), kz = coord_to_key(cz, rf);
     if (kx < 0 || ky < 0 || kz < 0) continue;
-    const int s = map_find(t, pack_key(q, kx, ky, kz));
-    if (s < 0) continue;
-    const double occ = 1.0 - (1.0 / (1.0 + exp((double)t.lo[s])));   // octomap::probability
+    MapCell c;
+    if (map_find(t, pack_key(q, kx, ky, kz), &c) < 0) continue;
+    const double occ = 1.0 - (1.0 / (1.0 + exp((double)c.lo)));      // octomap::probability
     if (occ >= 0.5) {
       if (q == tin) gt = (float)occ; else gn = (float)occ;
     } else if (occ >= 0.0) {
@@ -316,13 +362,13 @@ k_map_query_grids(const int* __restrict__ target_index, const double* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-k_map_rehash(const u64* __restrict__ keys, const float* __restrict__ lo,
-             const unsigned* __restrict__ stamp, unsigned old_cap, MapTable t) {
+k_map_rehash(const MapCell* __restrict__ old, unsigned old_cap, MapTable t) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += gridDim.x * blockDim.x) {
-    const u64 k = keys[i];
-    if (k == MAP_EMPTY) continue;
-    const int s = map_find_or_insert(t, k);
-    if (s >= 0) { t.lo[s] = lo[i]; t.stamp[s] = stamp[i]; }
+    const MapCell c = map_load(old + i);
+    if (c.key == MAP_EMPTY) continue;
+    MapCell seen;
+    const int s = map_find_or_insert(t, c.key, &seen);
+    if (s >= 0) { t.cells[s].lo = c.lo; t.cells[s].stamp = c.stamp; }
   }
 }
 
@@ -331,56 +377,73 @@ k_map_rehash(const u64* __restrict__ keys, const float* __restrict__ lo,
 #ifndef MF_HOST_EMU
 using namespace mf;
 
-static bool table_ok(const void* keys, const void* lo, const void* stamp, const void* cnt,
-                     long long cap, const void* counters) {
-  return keys && lo && stamp && cnt && counters && cap >= 64 && cap <= (1LL << 31) &&
-         (cap & (cap - 1)) == 0;
+static bool table_ok(const void* cells, const void* cnt, long long cap, const void* counters) {
+  return cells && cnt && counters && cap >= 64 && cap <= (1LL << 31) && (cap & (cap - 1)) == 0 &&
+         ((uintptr_t)cells & 15) == 0;
 }
 
-static MapTable make_table(void* keys, void* lo, void* stamp, void* cnt, long long cap, void* counters) {
+static MapTable make_table(void* cells, void* cnt, long long cap, void* counters) {
   MapTable t;
-  t.keys = (u64*)keys; t.lo = (float*)lo; t.stamp = (unsigned*)stamp; t.cnt = (unsigned*)cnt;
-  t.mask = (unsigned)(cap - 1); t.counters = (int*)counters;
+  t.cells = (MapCell*)cells; t.cnt = (unsigned*)cnt; t.mask = (unsigned)(cap - 1);
+  t.counters = (int*)counters;
   return t;
 }
 
 extern "C" int mf_map_integrate(const float* points, const uint8_t* mask, int64_t n, float ox,
                                 float oy, float oz, double resolution, int instance,
                                 uint32_t scan, float hit, float miss, float lo_min, float lo_max,
-                                void* keys, void* lo, void* stamp, void* cnt, int64_t capacity,
-                                int32_t* counters, void* ray_buf, int64_t ray_capacity,
+                                void* cells, void* cnt, int64_t capacity, int32_t* counters,
                                 void* stream_) {
   if (!points || n <= 0 || n >= (1LL << 31) || !(resolution > 0.0) || instance < 0 ||
-      instance >= 0xFFFF || scan == 0 || scan >= (1u << 31) || !ray_buf || ray_capacity <= 0 ||
-      ray_capacity >= (1LL << 31) || !table_ok(keys, lo, stamp, cnt, capacity, counters))
+      instance >= 0xFFFF || scan == 0 || scan >= (1u << 31) ||
+      !table_ok(cells, cnt, capacity, counters))
     return MF_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
-  MapTable t = make_table(keys, lo, stamp, cnt, capacity, counters);
+  MapTable t = make_table(cells, cnt, capacity, counters);
   ScanParams p;
-  p.points = points; p.mask = mask; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
-  p.res = resolution; p.res_factor = 1.0 / resolution; p.inst = instance; p.scan = scan;
+  p.points = points; p.mask = mask; p.labels = nullptr; p.lut = nullptr; p.inst_res = nullptr;
+  p.lut_lo = 0; p.lut_n = 0; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
+  p.res = resolution; p.inst = instance; p.scan = scan;
   p.hit = hit; p.miss = miss; p.lo_min = lo_min; p.lo_max = lo_max;
-  p.ray_buf = (u64*)ray_buf; p.ray_cap = (int)ray_capacity;
-  k_map_scan_rays<<<div_up(n, 256), 256, 0, st>>>(p, t);
+  k_map_scan_hits<<<div_up(n, 256), 256, 0, st>>>(p, t);
   MF_LAUNCH_CHECK();
-  int dev = 0, n_sm = 0;
-  MF_CUDA_TRY(cudaGetDevice(&dev));
-  MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  k_map_free_apply<<<n_sm * 8, 256, 0, st>>>((const u64*)ray_buf, (int)ray_capacity, scan, miss,
-                                              lo_min, lo_max, t);
+  k_map_scan_free<<<div_up(n, 256), 256, 0, st>>>(p, t);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+extern "C" int mf_map_integrate_labelled(const float* points, const int32_t* labels, int64_t n,
+                                         float ox, float oy, float oz, const int32_t* lut,
+                                         int lut_lo, int lut_n, const double* inst_resolution,
+                                         uint32_t scan, float hit, float miss, float lo_min,
+                                         float lo_max, void* cells, void* cnt, int64_t capacity,
+                                         int32_t* counters, void* stream_) {
+  if (!points || !labels || !lut || lut_n <= 0 || !inst_resolution || n <= 0 || n >= (1LL << 31) ||
+      scan == 0 || scan >= (1u << 31) || !table_ok(cells, cnt, capacity, counters))
+    return MF_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream_;
+  MapTable t = make_table(cells, cnt, capacity, counters);
+  ScanParams p;
+  p.points = points; p.mask = nullptr; p.labels = labels; p.lut = lut; p.inst_res = inst_resolution;
+  p.lut_lo = lut_lo; p.lut_n = lut_n; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
+  p.res = 1.0; p.inst = 0; p.scan = scan;
+  p.hit = hit; p.miss = miss; p.lo_min = lo_min; p.lo_max = lo_max;
+  k_map_scan_hits<<<div_up(n, 256), 256, 0, st>>>(p, t);
+  MF_LAUNCH_CHECK();
+  k_map_scan_free<<<div_up(n, 256), 256, 0, st>>>(p, t);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
 
 extern "C" int mf_map_update_points(const double* points, int64_t m, double resolution,
                                     int instance, float update, float lo_min, float lo_max,
-                                    void* keys, void* lo, void* stamp, void* cnt,
-                                    int64_t capacity, int32_t* counters, void* stream_) {
+                                    void* cells, void* cnt, int64_t capacity, int32_t* counters,
+                                    void* stream_) {
   if (!points || m <= 0 || m >= (1LL << 31) || !(resolution > 0.0) || instance < 0 ||
-      instance >= 0xFFFF || !table_ok(keys, lo, stamp, cnt, capacity, counters))
+      instance >= 0xFFFF || !table_ok(cells, cnt, capacity, counters))
     return MF_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
-  MapTable t = make_table(keys, lo, stamp, cnt, capacity, counters);
+  MapTable t = make_table(cells, cnt, capacity, counters);
   k_map_update_count<<<div_up(m, 256), 256, 0, st>>>(points, (int)m, 1.0 / resolution, instance, t);
   MF_LAUNCH_CHECK();
   k_map_update_apply<<<div_up(m, 256), 256, 0, st>>>(points, (int)m, 1.0 / resolution, instance,
@@ -391,15 +454,15 @@ extern "C" int mf_map_update_points(const double* points, int64_t m, double reso
 
 extern "C" int mf_map_query_grids(const int32_t* target_index, const double* pitch,
                                   const double* origin, int T, int X, int Y, int Z,
-                                  const double* res_factor, int n_instances, void* keys, void* lo,
-                                  void* stamp, void* cnt, int64_t capacity, int32_t* counters,
+                                  const double* res_factor, int n_instances, void* cells,
+                                  void* cnt, int64_t capacity, int32_t* counters,
                                   float* grid_target, float* grid_nontarget, float* grid_empty,
                                   void* stream_) {
   if (!target_index || !pitch || !origin || T <= 0 || X <= 0 || Y <= 0 || Z <= 0 || !res_factor ||
       n_instances < 0 || !grid_target || !grid_nontarget || !grid_empty ||
-      (long long)T * X * Y * Z >= (1LL << 40) || !table_ok(keys, lo, stamp, cnt, capacity, counters))
+      (long long)T * X * Y * Z >= (1LL << 40) || !table_ok(cells, cnt, capacity, counters))
     return MF_E_BADARG;
-  MapTable t = make_table(keys, lo, stamp, cnt, capacity, counters);
+  MapTable t = make_table(cells, cnt, capacity, counters);
   const long long total = (long long)T * X * Y * Z;
   k_map_query_grids<<<div_up(total, 256), 256, 0, (cudaStream_t)stream_>>>(
       target_index, pitch, origin, T, X, Y, Z, res_factor, n_instances, t, grid_target,
@@ -408,20 +471,19 @@ extern "C" int mf_map_query_grids(const int32_t* target_index, const double* pit
   return MF_OK;
 }
 
-extern "C" int mf_map_rehash(const void* old_keys, const void* old_lo, const void* old_stamp,
-                             int64_t old_capacity, void* keys, void* lo, void* stamp, void* cnt,
+// growth (rare, never on the per-frame path): `counters` restarts from the re-inserted cells
+extern "C" int mf_map_rehash(const void* old_cells, int64_t old_capacity, void* cells, void* cnt,
                              int64_t capacity, int32_t* counters, void* stream_) {
-  if (!old_keys || !old_lo || !old_stamp || old_capacity <= 0 || old_capacity > (1LL << 31) ||
-      capacity < old_capacity || !table_ok(keys, lo, stamp, cnt, capacity, counters))
+  if (!old_cells || old_capacity <= 0 || old_capacity > (1LL << 31) || capacity < old_capacity ||
+      !table_ok(cells, cnt, capacity, counters))
     return MF_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream_;
-  MapTable t = make_table(keys, lo, stamp, cnt, capacity, counters);
-  MF_CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));   // entries recounted by the inserts
+  MapTable t = make_table(cells, cnt, capacity, counters);
+  MF_CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
   int dev = 0, n_sm = 0;
   MF_CUDA_TRY(cudaGetDevice(&dev));
   MF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  k_map_rehash<<<n_sm * 8, 256, 0, st>>>((const u64*)old_keys, (const float*)old_lo,
-                                          (const unsigned*)old_stamp, (unsigned)old_capacity, t);
+  k_map_rehash<<<n_sm * 8, 256, 0, st>>>((const MapCell*)old_cells, (unsigned)old_capacity, t);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }

@@ -17,34 +17,49 @@ template <class F> static void run(unsigned grid, unsigned block, F f) {
     }
 }
 
-static MapTable tab(void* keys, void* lo, void* stamp, void* cnt, long long cap, void* counters) {
+static MapTable tab(void* cells, void* cnt, long long cap, void* counters) {
   MapTable t;
-  t.keys = (u64*)keys; t.lo = (float*)lo; t.stamp = (unsigned*)stamp; t.cnt = (unsigned*)cnt;
-  t.mask = (unsigned)(cap - 1); t.counters = (int*)counters;
+  t.cells = (MapCell*)cells; t.cnt = (unsigned*)cnt; t.mask = (unsigned)(cap - 1);
+  t.counters = (int*)counters;
   return t;
 }
 
 extern "C" int emu_map_integrate(const float* points, const uint8_t* mask, int64_t n, float ox,
                                  float oy, float oz, double resolution, int instance,
                                  uint32_t scan, float hit, float miss, float lo_min, float lo_max,
-                                 void* keys, void* lo, void* stamp, void* cnt, int64_t capacity,
-                                 int32_t* counters, void* ray_buf, int64_t ray_capacity) {
-  MapTable t = tab(keys, lo, stamp, cnt, capacity, counters);
+                                 void* cells, void* cnt, int64_t capacity, int32_t* counters) {
+  MapTable t = tab(cells, cnt, capacity, counters);
   ScanParams p;
-  p.points = points; p.mask = mask; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
-  p.res = resolution; p.res_factor = 1.0 / resolution; p.inst = instance; p.scan = scan;
+  p.points = points; p.mask = mask; p.labels = nullptr; p.lut = nullptr; p.inst_res = nullptr;
+  p.lut_lo = 0; p.lut_n = 0; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
+  p.res = resolution; p.inst = instance; p.scan = scan;
   p.hit = hit; p.miss = miss; p.lo_min = lo_min; p.lo_max = lo_max;
-  p.ray_buf = (u64*)ray_buf; p.ray_cap = (int)ray_capacity;
-  run((unsigned)n, 1, [&] { k_map_scan_rays(p, t); });          // blockDim 1: lane 0 only
-  run(7, 3, [&] { k_map_free_apply((const u64*)ray_buf, (int)ray_capacity, scan, miss, lo_min, lo_max, t); });
+  run((unsigned)n, 1, [&] { k_map_scan_hits(p, t); });          // blockDim 1: lane 0 only
+  run((unsigned)n, 1, [&] { k_map_scan_free(p, t); });
+  return 0;
+}
+
+extern "C" int emu_map_integrate_labelled(const float* points, const int32_t* labels, int64_t n,
+                                          float ox, float oy, float oz, const int32_t* lut,
+                                          int lut_lo, int lut_n, const double* inst_resolution,
+                                          uint32_t scan, float hit, float miss, float lo_min,
+                                          float lo_max, void* cells, void* cnt, int64_t capacity,
+                                          int32_t* counters) {
+  MapTable t = tab(cells, cnt, capacity, counters);
+  ScanParams p;
+  p.points = points; p.mask = nullptr; p.labels = labels; p.lut = lut; p.inst_res = inst_resolution;
+  p.lut_lo = lut_lo; p.lut_n = lut_n; p.n = (int)n; p.ox = ox; p.oy = oy; p.oz = oz;
+  p.res = 1.0; p.inst = 0; p.scan = scan;
+  p.hit = hit; p.miss = miss; p.lo_min = lo_min; p.lo_max = lo_max;
+  run((unsigned)n, 1, [&] { k_map_scan_hits(p, t); });
+  run((unsigned)n, 1, [&] { k_map_scan_free(p, t); });
   return 0;
 }
 
 extern "C" int emu_map_update_points(const double* points, int64_t m, double resolution,
                                      int instance, float update, float lo_min, float lo_max,
-                                     void* keys, void* lo, void* stamp, void* cnt,
-                                     int64_t capacity, int32_t* counters) {
-  MapTable t = tab(keys, lo, stamp, cnt, capacity, counters);
+                                     void* cells, void* cnt, int64_t capacity, int32_t* counters) {
+  MapTable t = tab(cells, cnt, capacity, counters);
   run((unsigned)m, 1, [&] { k_map_update_count(points, (int)m, 1.0 / resolution, instance, t); });
   run((unsigned)m, 1, [&] { k_map_update_apply(points, (int)m, 1.0 / resolution, instance, update, lo_min, lo_max, t); });
   return 0;
@@ -52,10 +67,10 @@ extern "C" int emu_map_update_points(const double* points, int64_t m, double res
 
 extern "C" int emu_map_query_grids(const int32_t* target_index, const double* pitch,
                                    const double* origin, int T, int X, int Y, int Z,
-                                   const double* res_factor, int n_instances, void* keys, void* lo,
-                                   void* stamp, void* cnt, int64_t capacity, int32_t* counters,
+                                   const double* res_factor, int n_instances, void* cells,
+                                   void* cnt, int64_t capacity, int32_t* counters,
                                    float* g_target, float* g_nontarget, float* g_empty) {
-  MapTable t = tab(keys, lo, stamp, cnt, capacity, counters);
+  MapTable t = tab(cells, cnt, capacity, counters);
   const long long total = (long long)T * X * Y * Z;
   run((unsigned)((total + 63) / 64), 64, [&] {
     k_map_query_grids(target_index, pitch, origin, T, X, Y, Z, res_factor, n_instances, t,
@@ -64,12 +79,10 @@ extern "C" int emu_map_query_grids(const int32_t* target_index, const double* pi
   return 0;
 }
 
-extern "C" int emu_map_rehash(const void* old_keys, const void* old_lo, const void* old_stamp,
-                              int64_t old_capacity, void* keys, void* lo, void* stamp, void* cnt,
+extern "C" int emu_map_rehash(const void* old_cells, int64_t old_capacity, void* cells, void* cnt,
                               int64_t capacity, int32_t* counters) {
-  MapTable t = tab(keys, lo, stamp, cnt, capacity, counters);
+  MapTable t = tab(cells, cnt, capacity, counters);
   counters[0] = 0; counters[1] = 0;
-  run(5, 4, [&] { k_map_rehash((const u64*)old_keys, (const float*)old_lo, (const unsigned*)old_stamp,
-                               (unsigned)old_capacity, t); });
+  run(5, 4, [&] { k_map_rehash((const MapCell*)old_cells, (unsigned)old_capacity, t); });
   return 0;
 }

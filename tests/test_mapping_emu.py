@@ -28,7 +28,8 @@ def emu(tmp_path_factory):
                     os.path.join(ROOT, "tests", "emu", "mapping_emu.cpp"), "-o", so], check=True)
     L = ctypes.CDLL(so)
     from morefusion_b200 import _lib
-    for name in ("integrate", "update_points", "query_grids", "rehash"):
+    names = ("integrate", "integrate_labelled", "update_points", "query_grids", "rehash")
+    for name in names:
         res, args = _lib.SIGNATURES["mf_map_" + name]
         fn = getattr(L, "emu_map_" + name)
         fn.restype = res
@@ -37,7 +38,7 @@ def emu(tmp_path_factory):
     class Adapter:
         pass
     a = Adapter()
-    for name in ("integrate", "update_points", "query_grids", "rehash"):
+    for name in names:
         setattr(a, "mf_map_" + name, (lambda f: (lambda *args: f(*args[:-1])))(getattr(L, "emu_map_" + name)))
     return a
 
@@ -78,8 +79,8 @@ def emu_mapping(emu, monkeypatch):
     return EmuMapping
 
 
-def build_pair(cls, scans, capacity=1 << 12, ray_capacity=1 << 16):
-    ours = cls(device="cpu", capacity=capacity, ray_capacity=ray_capacity)
+def build_pair(cls, scans, capacity=1 << 12, device="cpu"):
+    ours = cls(device=device, capacity=capacity)
     ref = oc.MultiInstanceOctreeMapping()
     for ins, pitch in ((3, 0.008), (7, 0.011), (0, 0.02)):
         ours.initialize(ins, pitch=pitch)
@@ -163,15 +164,15 @@ def test_table_growth_keeps_every_cell(emu_mapping):
 
 def test_overflow_is_reported_not_silent(emu_mapping):
     pcd, fg = make_scene(0)
-    m = emu_mapping(device="cpu", capacity=64, ray_capacity=1 << 16)
+    m = emu_mapping(device="cpu", capacity=64)
     m.initialize(1, pitch=0.008)
     m.integrate(1, fg, pcd)                                     # far more than 64 cells
     with pytest.raises(RuntimeError, match="overflowed"):
         m.integrate(1, fg, pcd)
-    m = emu_mapping(device="cpu", capacity=1 << 14, ray_capacity=100)
+    m = emu_mapping(device="cpu", capacity=64)
     m.initialize(1, pitch=0.008)
     m.integrate(1, fg, pcd)
-    with pytest.raises(RuntimeError, match="ray_capacity"):
+    with pytest.raises(RuntimeError, match="overflowed"):       # queries check too
         m.get_target_grids(1, dimensions=(4, 4, 4), pitch=0.01, origin=(0, 0, 0))
 
 
@@ -223,11 +224,40 @@ def check_golden(m, g, to_np=lambda a: a):
 def test_golden_reference_run(emu_mapping):
     from conftest import golden
     g = golden("octree_mapping")
-    check_golden(run_golden(emu_mapping, g, device="cpu", capacity=1 << 14, ray_capacity=1 << 20), g)
+    check_golden(run_golden(emu_mapping, g, device="cpu", capacity=1 << 14), g)
 
 
-def test_ray_keys_against_oracle_dense(emu):
-    """The DDA alone over many random rays, including axis-aligned, zero-length and far rays."""
+def test_labelled_frame_equals_per_instance_scans(emu_mapping):
+    from conftest import golden
+    g = golden("octree_mapping")
+    m = emu_mapping(device="cpu", capacity=1 << 18)
+    for ins, pitch in zip(g["instance_ids"], g["pitches"]):
+        m.initialize(int(ins), pitch=float(pitch))
+    for n in range(2):
+        lab = g[f"label{n}"].copy()
+        lab[0, :5] = 77                                           # a label nobody initialised: skipped
+        lab[1, :5] = -3
+        pcd = g[f"pcd{n}"].copy()
+        pcd[0, :5] = np.nan
+        pcd[1, :5] = np.nan
+        m.integrate_labels(lab, pcd, origin=g[f"origin{n}"])
+    ref = run_golden(emu_mapping, dict(g, pcd0=_nan_rows(g["pcd0"]), pcd1=_nan_rows(g["pcd1"])),
+                     device="cpu", capacity=1 << 18)
+    for ins in g["instance_ids"]:
+        assert m.cells(int(ins)) == ref.cells(int(ins))
+    assert m._scan == 2 and ref._scan == 8                        # 2 launches pairs instead of 8
+
+
+def _nan_rows(pcd):
+    pcd = pcd.copy()
+    pcd[0, :5] = np.nan
+    pcd[1, :5] = np.nan
+    return pcd
+
+
+def test_ray_walk_against_oracle_dense(emu_mapping):
+    """The DDA over many random rays, including axis-aligned, zero-length and far rays, from an
+    origin that sits exactly on cell borders."""
     rs = np.random.RandomState(3)
     ends = rs.uniform(-0.6, 0.6, (400, 3)).astype(np.float32)
     ends[:20, 0] = 0.25                                          # shared coordinates with the origin
@@ -235,23 +265,15 @@ def test_ray_keys_against_oracle_dense(emu):
     ends[40] = [0.25, -0.125, 0.0625]                            # same cell as the origin
     origin = np.float32([0.25, -0.125, 0.0625])
     res = 0.0125
-    cap = 1 << 16
-    keys = np.full(cap, -1, np.int64)
-    lo = np.zeros(cap, np.float32)
-    stamp = np.zeros(cap, np.int32)
-    cnt = np.zeros(cap, np.int32)
-    counters = np.zeros(8, np.int32)
-    ray = np.zeros(1 << 17, np.int64)
-    P = lambda a: ctypes.c_void_p(a.ctypes.data)
-    hit, miss, lmin, lmax = (float(np.float32(oc.logodds(p))) for p in (0.7, 0.4, 0.1192, 0.971))
-    emu.mf_map_integrate(P(ends), None, len(ends), float(origin[0]), float(origin[1]), float(origin[2]),
-                         res, 2, 1, hit, miss, lmin, lmax, P(keys), P(lo), P(stamp), P(cnt), cap,
-                         P(counters), P(ray), len(ray), None)
+    m = emu_mapping(device="cpu", capacity=1 << 17)
+    m.initialize(2, pitch=res)
+    m.integrate(2, np.ones((20, 20), bool), ends.reshape(20, 20, 3), origin=origin)
     t = oc.OcTree(res)
-    want = []
+    t.insertPointCloud(ends, origin=origin)
+    got = m.cells(2)
+    assert set(got) == set(t.cells)
+    assert all(got[k] == t.cells[k] for k in got)
+    walked = set()
     for e in ends:
-        want += t.computeRayKeys(origin, e)
-    got = ray[: counters[2 + 2 * (1 & 1)]]                      # scan 1: odd parity pair
-    unpack = lambda k: ((k >> 32) & 0xFFFF, (k >> 16) & 0xFFFF, k & 0xFFFF)
-    assert [unpack(int(k)) for k in got] == want                 # serial emulation: ray order kept
-    assert all((int(k) >> 48) == 2 for k in got)
+        walked.update(t.computeRayKeys(origin, e))
+    assert len(walked) > 5000 and walked <= set(got)

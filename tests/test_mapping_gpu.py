@@ -28,7 +28,7 @@ def test_golden_reference_run_gpu(Mapping):
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_scans_and_grids_vs_oracle(Mapping, seed):
-    ours, ref = build_pair(Mapping, scans_for(seed), capacity=1 << 16)
+    ours, ref = build_pair(Mapping, scans_for(seed), capacity=1 << 16, device="cuda")
     assert_cells_equal(ours, ref)
     pcd, fg = make_scene(seed)
     center = np.nanmedian(pcd[fg], axis=0)
@@ -42,7 +42,7 @@ def test_scans_and_grids_vs_oracle(Mapping, seed):
 
 
 def test_update_points_vs_oracle(Mapping):
-    ours, ref = build_pair(Mapping, scans_for(1)[:2], capacity=1 << 16)
+    ours, ref = build_pair(Mapping, scans_for(1)[:2], capacity=1 << 16, device="cuda")
     rs = np.random.RandomState(5)
     occupied = np.concatenate([rs.uniform(-0.05, 0.05, (3000, 3)) + [0, 0, 0.4],
                                np.repeat([[0.001, 0.002, 0.4]], 9, 0), [[np.nan, 0, 0], [1e9, 0, 0]]])
@@ -135,6 +135,24 @@ def test_full_frame_properties(Mapping):
     # (5) grids only hold values the reference's thresholds allow
     assert float(gt.min()) >= 0 and float(gt[gt > 0].min()) >= 0.5
     assert float(ge[ge > 0].min()) > 0.5                              # 1 - occ with occ < 0.5
+
+
+def test_labelled_frame_equals_per_instance_scans_full_size(Mapping):
+    pcd, label = full_frame(2)
+    pitches = {i: 0.004 + 0.0005 * i for i in range(1, 9)}
+    pitches[0] = 0.01
+    a, b = Mapping(), Mapping()
+    for m in (a, b):
+        for ins in list(range(1, 9)) + [0]:
+            m.initialize(ins, pitch=pitches[ins])
+    integrate_frame(a, pcd, label)
+    b.integrate_labels(torch.as_tensor(label).cuda(), torch.as_tensor(pcd).cuda())
+    assert a.n_cells() == b.n_cells() > 100000
+    ka, kb = a._cells.cpu(), b._cells.cpu()
+    # same set of (key, log-odds) pairs, wherever the slots ended up
+    ea = sorted(zip(ka[:, 0].tolist(), ka.view(torch.float32)[:, 2].tolist()))
+    eb = sorted(zip(kb[:, 0].tolist(), kb.view(torch.float32)[:, 2].tolist()))
+    assert ea == eb
 
 
 def test_no_cpu_tensors(Mapping):
