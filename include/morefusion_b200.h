@@ -479,6 +479,19 @@ int mf_pointcloud_from_depth(const float* depth, int H, int W, float fx, float f
 int mf_masks_to_bboxes(const uint8_t* masks, int N, int H, int W, int32_t* bboxes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * f1  2-D extractor tail at the sampled pixels only: replaces the dense
+ *     up3 (resize x2 + Conv2D 64->64 3x3 + PReLU), Conv2D 64->32 1x1 and log_softmax of
+ *     morefusion/models/dense_fusion/pspnet.py:64-82 followed by the 1000-pixel gather of
+ *     contrib/singleview_3d/models/model.py:222.
+ * up2_nhwc [B,Hs,Ws,64] f32 channels-last (output of up2), pix [B,P] int64 row-major pixel index
+ * into the 2Hs x 2Ws image, w3t [576,64] = W3[co][ci][dy][dx] transposed to [(ci,dy,dx)][co],
+ * b3 [64], prelu_slope [1] (device), w1t [64,32] = W1 transposed, b1 [32] -> out [B,32,P] f32.
+ * ------------------------------------------------------------------------ */
+int mf_psp_tail_sampled(const float* up2_nhwc, const int64_t* pix, int B, int P, int Hs, int Ws,
+                        const float* w3t, const float* b3, const float* prelu_slope,
+                        const float* w1t, const float* b1, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
  * f3  occupancy-grid producer: replaces the OctoMap trees behind
  *     morefusion/contrib/multi_instance_octree_mapping.py:16-34 (initialize / integrate / update)
  *     and :35-94 (get_target_grids).  One caller-owned open-addressing hash table holds the cells

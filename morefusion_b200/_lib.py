@@ -87,6 +87,7 @@ SIGNATURES = {
     "mf_train_adam": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_f, c_d, c_d, c_d, c_d, c_f, c_p]),
     "mf_pointcloud_from_depth": (c_i, [c_p, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_p, c_p]),
     "mf_masks_to_bboxes": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p]),
+    "mf_psp_tail_sampled": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mf_map_integrate": (c_i, [c_p, c_p, c_i64, c_f, c_f, c_f, c_d, c_i, ctypes.c_uint32, c_f, c_f, c_f, c_f,
                                 c_p, c_p, c_i64, c_p, c_p]),
     "mf_map_integrate_labelled": (c_i, [c_p, c_p, c_i64, c_f, c_f, c_f, c_p, c_i, c_i, c_p, ctypes.c_uint32,

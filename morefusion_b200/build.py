@@ -39,6 +39,7 @@ SOURCES = {
     "train.cu": [],
     "frontend.cu": ["-fmad=false"],
     "mapping.cu": ["-fmad=false"],
+    "extractor_tail.cu": [],
     "precise.cu": [],
 }
 

@@ -122,6 +122,9 @@ class Model(torch.nn.Module):
         # independent branches (occupancy stencil || point MLP + voxelisation; conv3-level gather
         # || conv4) run on a second stream; captured into the CUDA graphs as parallel branches
         self.fused_head4 = True     # last head layer + class select + pose epilogue in one kernel
+        # inference: up3 + 1x1 conv + log-softmax of the 2-D extractor only at the sampled pixels
+        # (csrc/extractor_tail.cu); training keeps the dense torch path (dropout, autograd)
+        self.fused_extractor_tail = True
         self.concurrent_branches = True
         self.fused_occ = True       # conv1_occ + conv2_occ in one kernel (no global intermediate)
         self.stream_k = True        # conv3 / conv4: equal K-block ranges per SM, reduction in the epilogue
@@ -331,7 +334,16 @@ class Model(torch.nn.Module):
         if class_id_h is not None and ((class_id_h < 1) | (class_id_h > self._n_fg_class)).any():
             raise IndexError("class_id out of range for n_fg_class")     # fancy index at :266-269
         mask = ~torch.isnan(pcd).any(dim=3)                              # [B,H,W]   (:178)
-        h_rgb = self.pspnet_extractor(self.resnet_extractor(rgb.permute(0, 3, 1, 2).to(f32)))
+        sparse_tail = (self.fused_extractor_tail and not self.training
+                       and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())))
+        h_res = self.resnet_extractor(rgb.permute(0, 3, 1, 2).to(f32))
+        if sparse_tail:
+            h_up2 = self.pspnet_extractor.forward_up2(h_res)             # [B,64,H/2,W/2]
+            if h_up2.shape[2] * 2 != H or h_up2.shape[3] * 2 != W:
+                raise ValueError("image sides must be multiples of 8 (the extractor returns H x W features)")
+        else:
+            h_rgb = self.pspnet_extractor.up3(self.pspnet_extractor.forward_up2(h_res))
+            h_rgb = torch.log_softmax(self.pspnet_extractor.conv1(h_rgb), dim=1)
         flat_mask = mask.flatten(1)
         n_point = flat_mask.sum(1).cpu().numpy()                         # the one host read
         keep = torch.as_tensor(np.stack([self._keep_indices(n) for n in n_point]), device=dev)
@@ -339,7 +351,10 @@ class Model(torch.nn.Module):
         pix = torch.searchsorted(cums, keep + 1)                         # k-th valid pixel, row-major
         pcd_f = pcd.permute(0, 3, 1, 2).flatten(2)                       # [B,3,HW]
         points = pcd_f.gather(2, pix[:, None, :].expand(B, 3, P))
-        values = h_rgb.flatten(2).gather(2, pix[:, None, :].expand(B, h_rgb.shape[1], P))
+        if sparse_tail:
+            values = self._extractor_tail(h_up2, pix)
+        else:
+            values = h_rgb.flatten(2).gather(2, pix[:, None, :].expand(B, h_rgb.shape[1], P))
         # defaults (:197-205)
         pitch_l = [None] * B if pitch is None else list(pitch)
         if any(p is None for p in pitch_l):
@@ -369,6 +384,34 @@ class Model(torch.nn.Module):
         points = (points - origin_t[:, :, None]) / pitch_t[:, None, None]      # (:236)
         return self._features(class_id=class_id, values=values, points=points, pitch=pitch_t,
                               origin=origin_t, grid_nontarget_empty=grid_nontarget_empty)
+
+    def _extractor_tail(self, h_up2, pix):
+        """up3 + conv1 + log-softmax of the PSPNet upsampler (pspnet.py:64-82) at the sampled pixels
+        only: h_up2 [B,64,Hs,Ws], pix [B,P] int64 -> values [B,32,P] (csrc/extractor_tail.cu)."""
+        ex = self.pspnet_extractor
+        ps = (ex.up3.conv.weight, ex.up3.conv.bias, ex.up3.prelu.weight, ex.conv1.weight, ex.conv1.bias)
+        ver = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = self.__dict__.get("_tail_pack")
+        if cache is None or cache[0] != ver:
+            with torch.no_grad():
+                w3t = ps[0].detach().float().reshape(64, 576).t().contiguous()
+                w1t = ps[3].detach().float().reshape(32, 64).t().contiguous()
+                packed = (w3t, ps[1].detach().float().contiguous(), ps[2].detach().float().contiguous(),
+                          w1t, ps[4].detach().float().contiguous())
+            cache = (ver, packed)
+            self.__dict__["_tail_pack"] = cache
+        w3t, b3, slope, w1t, b1 = cache[1]
+        B, C, Hs, Ws = h_up2.shape
+        assert C == 64 and slope.numel() == 1
+        x = h_up2.detach().float().permute(0, 2, 3, 1).contiguous()      # channels-last rows
+        pix = pix.to(torch.int64).contiguous()
+        P = pix.shape[1]
+        out = torch.empty((B, 32, P), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mf_psp_tail_sampled(
+                _lib.ptr(x), _lib.ptr(pix), B, P, Hs, Ws, _lib.ptr(w3t), _lib.ptr(b3), _lib.ptr(slope),
+                _lib.ptr(w1t), _lib.ptr(b1), _lib.ptr(out), _lib.stream()), "psp_tail_sampled")
+        return out
 
     def _features(self, **kw):
         """forward_features with autograd when gradients are enabled (training)."""

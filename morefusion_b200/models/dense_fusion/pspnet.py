@@ -55,9 +55,12 @@ class PSPNetExtractor(nn.Module):
         self.up3 = PSPUpsample(64, 64)               # 1/2 -> 1
         self.conv1 = nn.Conv2d(64, 32, 1)
 
-    def forward(self, x):
+    def forward_up2(self, x):
+        """Everything up to and including up2 (+ its dropout): [B,64,H/2,W/2]."""
         h = F.dropout(self.psp(x), 0.3, self.training)
         h = F.dropout(self.up1(h), 0.15, self.training)
-        h = F.dropout(self.up2(h), 0.15, self.training)
-        h = self.up3(h)
+        return F.dropout(self.up2(h), 0.15, self.training)
+
+    def forward(self, x):
+        h = self.up3(self.forward_up2(x))
         return F.log_softmax(self.conv1(h), dim=1)

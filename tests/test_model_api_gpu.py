@@ -73,11 +73,44 @@ def test_predict_sampling_defaults_and_frames(cuda_device):
         np.testing.assert_allclose(seen["origin"][i].cpu().numpy(), origin, rtol=0, atol=1e-7)
         want = ((pts - origin[:, None]) / pitch).astype(F32)
         np.testing.assert_allclose(seen["points"][i].cpu().numpy(), want, rtol=0, atol=2e-4)
-        np.testing.assert_array_equal(seen["values"][i].cpu().numpy(), h_rgb[i][:, iy[keep], ix[keep]])
+        # the extractor tail runs at the sampled pixels only (csrc/extractor_tail.cu): same numbers
+        # as the dense up3 / conv1 / log_softmax up to fp32 summation order
+        np.testing.assert_allclose(seen["values"][i].cpu().numpy(), h_rgb[i][:, iy[keep], ix[keep]],
+                                   rtol=0, atol=3e-5)
     q = rot.cpu().numpy()
     assert np.isfinite(q).all() and np.allclose(np.linalg.norm(q, axis=2), 1.0, atol=1e-3)
     with pytest.raises(IndexError):
         m.predict(class_id=np.array([0, 1, 2], np.int32), rgb=rgb, pcd=pcd, grid_nontarget_empty=gne)
+
+
+def test_extractor_tail_at_sampled_pixels_equals_dense_path(cuda_device):
+    """csrc/extractor_tail.cu against the dense torch layers it replaces (pspnet.py:64-82 +
+    model.py:222), including image corners / borders (zero padding of the 3x3 conv, clamped
+    bilinear taps), non-square images, and the exact gather when the switch is off."""
+    m = _model(cuda_device)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        m.pspnet_extractor.up3.prelu.weight.fill_(0.2)
+        for B, Hs, Ws, P in ((2, 32, 32, 1000), (1, 24, 40, 77), (3, 128, 128, 1000)):
+            up2 = torch.randn(B, 64, Hs, Ws, device=cuda_device)
+            H, W = 2 * Hs, 2 * Ws
+            pix = torch.randint(0, H * W, (B, P), device=cuda_device)
+            pix[:, :8] = torch.tensor([0, W - 1, (H - 1) * W, H * W - 1, W, 2 * W - 1, 1, H * W - 2],
+                                      device=cuda_device)
+            got = m._extractor_tail(up2, pix)
+            dense = torch.log_softmax(m.pspnet_extractor.conv1(m.pspnet_extractor.up3(up2)), dim=1)
+            want = dense.flatten(2).gather(2, pix[:, None, :].expand(B, 32, P))
+            assert got.shape == want.shape
+            err = (got - want).abs().max().item()
+            assert err < 5e-5, (B, Hs, Ws, err)
+    class_id, rgb, pcd = _frame()
+    gne = np.zeros((3, 32, 32, 32), bool)
+    with torch.no_grad():
+        a = m.predict(class_id=class_id, rgb=rgb, pcd=pcd, grid_nontarget_empty=gne)
+        m.fused_extractor_tail = False
+        b = m.predict(class_id=class_id, rgb=rgb, pcd=pcd, grid_nontarget_empty=gne)
+    for x, y in zip(a, b):                       # bf16 3-D section downstream: same inputs to 3e-5
+        assert (x - y).abs().max().item() < 2e-2
 
 
 def test_metrics_average_distance_vs_reference_definition(cuda_device):
