@@ -51,7 +51,7 @@ def test_predict_sampling_defaults_and_frames(cuda_device):
         seen.update(kw)
         return m.forward_features(**kw)
     m._features = capture
-    with torch.no_grad():
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         h_rgb = m.pspnet_extractor(m.resnet_extractor(
             torch.as_tensor(rgb, device=cuda_device).permute(0, 3, 1, 2).float())).cpu().numpy()
         gne = np.zeros((B, 32, 32, 32), bool)
@@ -89,7 +89,8 @@ def test_extractor_tail_at_sampled_pixels_equals_dense_path(cuda_device):
     bilinear taps), non-square images, and the exact gather when the switch is off."""
     m = _model(cuda_device)
     torch.manual_seed(3)
-    with torch.no_grad():
+    # the dense comparison path must be fp32 too (cuDNN convs default to TF32: 3e-4 on its own)
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         m.pspnet_extractor.up3.prelu.weight.fill_(0.2)
         for B, Hs, Ws, P in ((2, 32, 32, 1000), (1, 24, 40, 77), (3, 128, 128, 1000)):
             up2 = torch.randn(B, 64, Hs, Ws, device=cuda_device)
