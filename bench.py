@@ -422,10 +422,61 @@ def bench_chain(dev, model, runner, rank, world, quick):
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     h2d = cnn_blobs[0].numel() + grids[0].numel() * 4
-    return dict(metric="objects/sec per-frame chain voxelise->3D-CNN->ICC", value=len(my) * world * 8 / (ms * 1e-3),
-                unit="objects/s", frames=len(my) * world, objects_per_frame=8, icc_iterations=icc_iter,
-                ms_per_frame=ms / len(my), h2d_bytes_per_frame=int(h2d), d2h_bytes_per_frame=int(out_pose.numel() * 4),
-                n_gpus=world, timed="CUDA events around the frame loop incl. H2D/D2H, max over ranks")
+
+    # ---- throughput mode: F frames in flight share ONE ICC launch (their scenes are independent
+    # groups of the same persistent kernel): every frame still goes H2D -> CNN -> pose -> ICC -> D2H
+    # through host buffers; what changes is that the refinement of F frames runs together, which
+    # is where the fused ICC kernel's throughput comes from (a single scene is barrier-bound).
+    F = 4
+    fb = ICCBatch([scenes[j % 2] for j in range(F)], sdf_offset=0.02, device=dev)
+    fq0, ft0 = fb.quaternion.clone(), fb.translation.clone()
+    out_pose_f = torch.empty((F * 8, 14), dtype=torch.float32).pin_memory()
+    gt_rows = fb.prob.grid_target.reshape(F, -1)
+    gne_rows = fb.prob.gne.reshape(F, -1)
+
+    def frames(i0):
+        cnn_poses = []
+        for j in range(F):
+            k = (i0 + j) % 2
+            runner.upload(cnn_blobs[k])
+            gt_rows[j].copy_(grids[k][0].reshape(-1), non_blocking=True)
+            gne_rows[j].copy_(grids[k][1].reshape(-1), non_blocking=True)
+            runner.run()
+            best = runner.out["conf"].argmax(dim=1)
+            ar = torch.arange(B_PER_RANK, device=dev)
+            cnn_poses.append(torch.cat([runner.out["rot"][ar, best], runner.out["trans"][ar, best]], 1))
+        fb.quaternion.copy_(fq0); fb.translation.copy_(ft0)
+        fb.adam_state.zero_(); fb.adam_t = 0
+        fb.refine(n_iter=icc_iter)
+        dev_pose = torch.cat([torch.cat(cnn_poses), fb.quaternion, fb.translation], 1)
+        out_pose_f.copy_(dev_pose, non_blocking=True)
+
+    frames(0)
+    torch.cuda.synchronize()
+    n_groups = max(1, len(my) // F)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for g in range(n_groups):
+        frames(g * F)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_f = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    per_frame_f = ms_f / (n_groups * F)
+    return dict(metric="objects/sec per-frame chain voxelise->3D-CNN->ICC",
+                value=n_groups * F * world * 8 / (ms_f * 1e-3), unit="objects/s",
+                frames=n_groups * F * world, objects_per_frame=8, icc_iterations=icc_iter,
+                ms_per_frame=per_frame_f, frames_per_icc_launch=F,
+                latency_of_a_frame_group_ms=ms_f / n_groups,
+                single_frame_mode=dict(value=len(my) * world * 8 / (ms * 1e-3), ms_per_frame=ms / len(my),
+                                       frames=len(my) * world, frames_per_icc_launch=1),
+                h2d_bytes_per_frame=int(h2d), d2h_bytes_per_frame=int(out_pose.numel() * 4),
+                n_gpus=world,
+                timed="CUDA events around the frame loop incl. H2D/D2H, max over ranks; `value` = "
+                      f"{F} frames in flight per ICC launch (each frame: H2D, CNN graph, pose select, "
+                      "then one fused 30-iteration ICC launch over the group's scenes, D2H); "
+                      "single_frame_mode = one frame per ICC launch (lowest latency)")
 
 
 # ------------------------------------------------------------------ our arm
