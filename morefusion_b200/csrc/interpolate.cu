@@ -150,7 +150,7 @@ k_interp_fwd_planes(const float* __restrict__ vox, const float* __restrict__ poi
         }
       }
       float* dst = values + n * C + c0;
-      if (cg == CG && ((C & 3) == 0)) {
+      if (CG >= 4 && cg == CG && ((C & 3) == 0)) {
         float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
         for (int k = 0; k < CG / 4; ++k)
@@ -164,9 +164,98 @@ k_interp_fwd_planes(const float* __restrict__ vox, const float* __restrict__ poi
   }
 }
 
+// ---- plane-staged backward for the reference layout [B,C,X,Y,Z] ----------------------------
+// Mirror image of the forward above: a CTA owns (batch b, CG consecutive channel planes) in shared
+// memory, zeroes them, lets every point of batch b add its 8 weighted corner contributions with
+// SHARED-memory atomics, then streams the planes out with coalesced 16-byte stores.  Every element
+// of the gradient grid is written exactly once: no memset of the 33 MB output, no global atomics
+// (the simple kernel issues 8 P C of them into a channel-major grid: 16-32 M scattered float
+// atomics at the model shapes).
+template <int CG>
+__global__ void __launch_bounds__(256)
+k_interp_bwd_planes(const float* __restrict__ gvalues, const float* __restrict__ points,
+                    const int* __restrict__ bi, long long P, int B, int C, int X, int Y, int Z,
+                    float* __restrict__ gvox) {
+  extern __shared__ __align__(16) float planes[];          // [CG][V]
+  const int V = X * Y * Z;
+  const int b = blockIdx.y, c0 = blockIdx.x * CG;
+  const int cg = min(CG, C - c0);
+  const bool vec = (V & 3) == 0;
+  if (vec) {
+    float4* d4 = reinterpret_cast<float4*>(planes);
+    for (int e = threadIdx.x; e < cg * (V >> 2); e += 256) d4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int e = threadIdx.x; e < cg * V; e += 256) planes[e] = 0.f;
+  }
+  __syncthreads();
+  for (long long base = 0; base < P; base += 256 * 8) {
+    int bb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      long long n = base + u * 256 + threadIdx.x;
+      bb[u] = (n < P) ? __ldg(bi + n) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (bb[u] != b) continue;
+      const long long n = base + u * 256 + threadIdx.x;
+      Tri t;
+      trilinear(points[3 * n], points[3 * n + 1], points[3 * n + 2], t);
+      float g[CG];
+      const float* src = gvalues + n * C + c0;
+      if (CG >= 4 && cg == CG && ((C & 3) == 0)) {
+#pragma unroll
+        for (int k = 0; k < CG / 4; ++k) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src) + k);
+          g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CG; ++k) g[k] = (k < cg) ? __ldg(src + k) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (t.ix[j] >= 0 && t.ix[j] < X && t.iy[j] >= 0 && t.iy[j] < Y && t.iz[j] >= 0 &&
+            t.iz[j] < Z) {
+          const int flat = (t.ix[j] * Y + t.iy[j]) * Z + t.iz[j];
+#pragma unroll
+          for (int k = 0; k < CG; ++k)
+            if (k < cg) atomicAdd(planes + k * V + flat, __fmul_rn(t.w[j], g[k]));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = gvox + ((long long)b * C + c0) * V;          // the cg planes are contiguous
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(planes);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int e = threadIdx.x; e < cg * (V >> 2); e += 256) __stcs(d4 + e, s4[e]);
+  } else {
+    for (int e = threadIdx.x; e < cg * V; e += 256) dst[e] = planes[e];
+  }
+}
+
+// channel planes per CTA: ~64 KB of shared memory (3 CTAs per SM) and enough CTAs to fill 148 SMs
+static int planes_per_cta(long long V) {
+  if (V * 4 > 160 * 1024) return 0;          // a plane does not fit: simple kernels
+  if (V > 8192) return 1;
+  if (V > 4096) return 2;
+  if (V > 2048) return 4;
+  if (V > 1024) return 8;
+  return 16;
+}
+
 }  // namespace mf
 
 using namespace mf;
+
+#define MF_INTERP_PLANES(KERNEL, CGV, ...)                                              \
+  do {                                                                                  \
+    MF_ENSURE_DYN_SMEM(KERNEL<CGV>, 160 * 1024);                                        \
+    dim3 grid((C + CGV - 1) / CGV, B);                                                  \
+    KERNEL<CGV><<<grid, 256, (size_t)V * 4 * CGV, stream>>>(__VA_ARGS__);               \
+  } while (0)
 
 extern "C" int mf_interpolate_voxel_grid_fwd(const float* voxelized, const float* points,
                                              const int32_t* batch_indices, int64_t P, int B, int C,
@@ -180,13 +269,15 @@ extern "C" int mf_interpolate_voxel_grid_fwd(const float* voxelized, const float
   if (channels_last) {
     k_interp_fwd<true><<<div_up(P * C, 256), 256, 0, stream>>>(voxelized, points, batch_indices, P,
                                                                B, C, X, Y, Z, values);
-  } else if (V * 4 * 8 <= 160 * 1024 && C >= 8 && P <= (1LL << 22) && B <= 65535) {
-    // plane-staged path: 8 channel planes per CTA in shared memory
-    constexpr int CG = 8;
-    MF_ENSURE_DYN_SMEM(k_interp_fwd_planes<CG>, 160 * 1024);
-    dim3 grid((C + CG - 1) / CG, B);
-    k_interp_fwd_planes<CG><<<grid, 256, (size_t)V * 4 * CG, stream>>>(
-        voxelized, points, batch_indices, P, B, C, X, Y, Z, values);
+  } else if (planes_per_cta(V) > 0 && P <= (1LL << 22) && B <= 65535) {
+    // plane-staged path: CG channel planes per CTA in shared memory
+    switch (planes_per_cta(V)) {
+      case 1: MF_INTERP_PLANES(k_interp_fwd_planes, 1, voxelized, points, batch_indices, P, B, C, X, Y, Z, values); break;
+      case 2: MF_INTERP_PLANES(k_interp_fwd_planes, 2, voxelized, points, batch_indices, P, B, C, X, Y, Z, values); break;
+      case 4: MF_INTERP_PLANES(k_interp_fwd_planes, 4, voxelized, points, batch_indices, P, B, C, X, Y, Z, values); break;
+      case 8: MF_INTERP_PLANES(k_interp_fwd_planes, 8, voxelized, points, batch_indices, P, B, C, X, Y, Z, values); break;
+      default: MF_INTERP_PLANES(k_interp_fwd_planes, 16, voxelized, points, batch_indices, P, B, C, X, Y, Z, values); break;
+    }
   } else {
     k_interp_fwd<false><<<div_up(P * C, 256), 256, 0, stream>>>(voxelized, points, batch_indices,
                                                                 P, B, C, X, Y, Z, values);
@@ -202,9 +293,23 @@ extern "C" int mf_interpolate_voxel_grid_bwd(const float* gvalues, const float* 
   cudaStream_t stream = (cudaStream_t)stream_;
   if (P < 0 || B <= 0 || C <= 0 || X <= 0 || Y <= 0 || Z <= 0) return MF_E_BADARG;
   if (!gvoxelized) return MF_E_BADARG;
+  if (P > 0 && (!gvalues || !points || !batch_indices)) return MF_E_BADARG;
+  const long long V = (long long)X * Y * Z;
+  if (!channels_last && P > 0 && planes_per_cta(V) > 0 && P <= (1LL << 22) && B <= 65535) {
+    // plane-staged path: every output element written once, no memset, no global atomics
+    switch (planes_per_cta(V)) {
+      case 1: MF_INTERP_PLANES(k_interp_bwd_planes, 1, gvalues, points, batch_indices, P, B, C, X, Y, Z, gvoxelized); break;
+      case 2: MF_INTERP_PLANES(k_interp_bwd_planes, 2, gvalues, points, batch_indices, P, B, C, X, Y, Z, gvoxelized); break;
+      case 4: MF_INTERP_PLANES(k_interp_bwd_planes, 4, gvalues, points, batch_indices, P, B, C, X, Y, Z, gvoxelized); break;
+      case 8: MF_INTERP_PLANES(k_interp_bwd_planes, 8, gvalues, points, batch_indices, P, B, C, X, Y, Z, gvoxelized); break;
+      default: MF_INTERP_PLANES(k_interp_bwd_planes, 16, gvalues, points, batch_indices, P, B, C, X, Y, Z, gvoxelized); break;
+    }
+    MF_LAUNCH_CHECK();
+    return MF_OK;
+  }
+  // fallback (channels-last grids, planes that do not fit shared memory): zero + global atomics
   MF_CUDA_TRY(cudaMemsetAsync(gvoxelized, 0, (size_t)B * C * X * Y * Z * 4, stream));
   if (P == 0) return MF_OK;
-  if (!gvalues || !points || !batch_indices) return MF_E_BADARG;
   if (channels_last)
     k_interp_bwd<true><<<div_up(P * C, 256), 256, 0, stream>>>(gvalues, points, batch_indices, P, B,
                                                                C, X, Y, Z, gvoxelized);
