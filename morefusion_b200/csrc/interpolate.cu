@@ -9,6 +9,7 @@
 // correct (Y*Z, Z, 1) strides (the reference forward's (X*Y, Y, 1) is equal
 // for cubic grids only).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mf {
 
@@ -130,12 +131,23 @@ k_interp_fwd_planes(const float* __restrict__ vox, const float* __restrict__ poi
       long long n = base + u * 256 + threadIdx.x;
       bb[u] = (n < P) ? __ldg(bi + n) : -1;
     }
+    // the coordinates of every matching point of the chunk are requested before the first one is
+    // used: one memory round trip per chunk instead of one per point
+    float px[8], py[8], pz[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      px[u] = py[u] = pz[u] = 0.f;
+      if (bb[u] == b) {
+        const long long n = base + u * 256 + threadIdx.x;
+        px[u] = __ldg(points + 3 * n); py[u] = __ldg(points + 3 * n + 1); pz[u] = __ldg(points + 3 * n + 2);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (bb[u] != b) continue;
       const long long n = base + u * 256 + threadIdx.x;
       Tri t;
-      trilinear(points[3 * n], points[3 * n + 1], points[3 * n + 2], t);
+      trilinear(px[u], py[u], pz[u], t);
       float acc[CG];
 #pragma unroll
       for (int k = 0; k < CG; ++k) acc[k] = 0.f;
@@ -195,15 +207,35 @@ k_interp_bwd_planes(const float* __restrict__ gvalues, const float* __restrict__
       long long n = base + u * 256 + threadIdx.x;
       bb[u] = (n < P) ? __ldg(bi + n) : -1;
     }
+    // coordinates and (for narrow channel groups) the gradient rows of every matching point of
+    // the chunk are requested before the first one is used
+    constexpr bool kPrefetchG = CG <= 4;
+    float px[8], py[8], pz[8];
+    float gpre[kPrefetchG ? 8 : 1][CG];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      px[u] = py[u] = pz[u] = 0.f;
+      if (bb[u] == b) {
+        const long long n = base + u * 256 + threadIdx.x;
+        px[u] = __ldg(points + 3 * n); py[u] = __ldg(points + 3 * n + 1); pz[u] = __ldg(points + 3 * n + 2);
+        if (kPrefetchG) {
+#pragma unroll
+          for (int k = 0; k < CG; ++k) gpre[kPrefetchG ? u : 0][k] = (k < cg) ? __ldg(gvalues + n * C + c0 + k) : 0.f;
+        }
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (bb[u] != b) continue;
       const long long n = base + u * 256 + threadIdx.x;
       Tri t;
-      trilinear(points[3 * n], points[3 * n + 1], points[3 * n + 2], t);
+      trilinear(px[u], py[u], pz[u], t);
       float g[CG];
       const float* src = gvalues + n * C + c0;
-      if (CG >= 4 && cg == CG && ((C & 3) == 0)) {
+      if (kPrefetchG) {
+#pragma unroll
+        for (int k = 0; k < CG; ++k) g[k] = gpre[kPrefetchG ? u : 0][k];
+      } else if (CG >= 4 && cg == CG && ((C & 3) == 0)) {
 #pragma unroll
         for (int k = 0; k < CG / 4; ++k) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(src) + k);
@@ -236,19 +268,302 @@ k_interp_bwd_planes(const float* __restrict__ gvalues, const float* __restrict__
   }
 }
 
-// channel planes per CTA: ~64 KB of shared memory (3 CTAs per SM) and enough CTAs to fill 148 SMs
+
+// ---- streaming (persistent) plane kernels for the reference layout [B,C,X,Y,Z] ---------------
+// The plane-staged kernels above are latency-bound: a CTA does load -> scan -> gather once and
+// exits, 512 short dependent chains in 1.15 waves (ncu: 36 / 71 us, warps 33 % active, DRAM 33 MB).
+// Here ONE CTA per SM walks a contiguous range of work items (batch b, CG channel planes),
+// batch-major, with
+//   * the planes of item k+1 arriving by cp.async.bulk (UBLKCP, mbarrier complete_tx) into the
+//     second shared-memory buffer while item k is being gathered (forward), or the planes of item
+//     k leaving by cp.async.bulk shared -> global while item k+1 accumulates (backward);
+//   * the points of batch b found ONCE per batch (all batch-index loads of the scan in flight
+//     together) and kept in shared memory (index + coordinates) for every item of that batch.
+// Arithmetic per (point, channel) is unchanged (corner order j = 0..7, explicit _rn ops): the
+// forward stays bit-identical.
+constexpr int ST_THREADS = 256;
+constexpr int ST_CHUNK = ST_THREADS * 8;   // batch indices scanned per step (all loads in flight)
+constexpr int ST_MAXP = 2 * ST_CHUNK;      // cached points per pass (index + xyz = 16 B each): a batch
+                                           // of <= ST_CHUNK points is always cached whole
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct StreamArgs {
+  const float* grid_in;    // fwd: voxelized            bwd: unused
+  float* grid_out;         // fwd: unused               bwd: gvoxelized
+  const float* rows_in;    // fwd: unused               bwd: gvalues [P,C]
+  float* rows_out;         // fwd: values [P,C]         bwd: unused
+  const float* points;
+  const int* bi;
+  long long P;
+  int B, C, X, Y, Z;
+  int n_groups, n_items;
+};
+
+struct PointCache {
+  int n[ST_MAXP];
+  float x[ST_MAXP], y[ST_MAXP], z[ST_MAXP];
+  int count;
+  int next;                // scan position after this pass
+};
+
+// points of batch b with index >= from, up to ST_MAXP of them, into the cache (any order)
+__device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a, int b, long long from) {
+  __syncthreads();
+  if (threadIdx.x == 0) { pc.count = 0; pc.next = (int)a.P; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  // chunks of 8 x 256 indices; a chunk is only taken if it is certain to fit
+  for (long long base = from; base < a.P; base += ST_CHUNK) {
+    if (pc.count + ST_CHUNK > ST_MAXP) {        // uniform: read after the barrier below
+      if (threadIdx.x == 0) pc.next = (int)base;
+      break;
+    }
+    int bb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long n = base + u * ST_THREADS + threadIdx.x;
+      bb[u] = (n < a.P) ? __ldg(a.bi + n) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool m = bb[u] == b;
+      const unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (bal) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&pc.count, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+        if (m) {
+          const long long n = base + u * ST_THREADS + threadIdx.x;
+          pc.n[pos] = (int)n;
+          pc.x[pos] = __ldg(a.points + 3 * n);
+          pc.y[pos] = __ldg(a.points + 3 * n + 1);
+          pc.z[pos] = __ldg(a.points + 3 * n + 2);
+        }
+      }
+    }
+    __syncthreads();                                   // pc.count is final for this chunk
+  }
+  __syncthreads();
+}
+
+template <int CG, bool kBackward>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_interp_stream(StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int V = a.X * a.Y * a.Z;
+  float* buf0 = reinterpret_cast<float*>(smem_raw);
+  float* buf1 = buf0 + (size_t)CG * V;
+  PointCache& pc = *reinterpret_cast<PointCache*>(buf1 + (size_t)CG * V);
+  uint64_t* full = reinterpret_cast<uint64_t*>(&pc + 1);          // [2]
+  const int tid = threadIdx.x;
+  // contiguous range of items for this CTA (batch-major: neighbours share the point cache)
+  const int per = (a.n_items + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per, it1 = min(a.n_items, it0 + per);
+  if (it0 >= it1) return;
+  if (!kBackward && tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto item_planes = [&](int item, int* b, int* c0, int* cg) {
+    *b = item / a.n_groups;
+    *c0 = (item - *b * a.n_groups) * CG;
+    *cg = min(CG, a.C - *c0);
+  };
+  if (!kBackward && tid == 0) {
+    int b, c0, cg;
+    item_planes(it0, &b, &c0, &cg);
+    mbar_expect_tx(full, (uint32_t)(cg * V * 4));
+    bulk_g2s(buf0, a.grid_in + ((long long)b * a.C + c0) * V, (uint32_t)(cg * V * 4), full);
+  }
+  int cached_b = -1;
+  bool cache_whole = false;
+  for (int item = it0; item < it1; ++item) {
+    const int k = item - it0;
+    float* buf = (k & 1) ? buf1 : buf0;
+    int b, c0, cg;
+    item_planes(item, &b, &c0, &cg);
+    if (kBackward) {
+      // the bulk store that last read this buffer (item k-2) must have finished reading it
+      if (tid == 0) bulk_wait_read<1>();
+      __syncthreads();
+      float4* d4 = reinterpret_cast<float4*>(buf);
+      for (int e = tid; e < cg * (V >> 2); e += ST_THREADS) d4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+    } else {
+      // request the next item's planes into the other buffer (its readers finished at the
+      // barrier that ended item k-1)
+      if (tid == 0 && item + 1 < it1) {
+        int nb, nc0, ncg;
+        item_planes(item + 1, &nb, &nc0, &ncg);
+        float* nbuf = (k & 1) ? buf0 : buf1;
+        mbar_expect_tx(full + ((k + 1) & 1), (uint32_t)(ncg * V * 4));
+        bulk_g2s(nbuf, a.grid_in + ((long long)nb * a.C + nc0) * V, (uint32_t)(ncg * V * 4),
+                 full + ((k + 1) & 1));
+      }
+    }
+    bool waited = false;
+    long long from = 0;
+    for (;;) {                                   // passes over the batch's points (one, normally)
+      if (!(cached_b == b && cache_whole)) {
+        cache_points(pc, a, b, from);
+        cached_b = b;
+        cache_whole = (from == 0 && pc.next >= (int)a.P);
+      }
+      if (!kBackward && !waited) {
+        mbar_wait(full + (k & 1), (uint32_t)((k >> 1) & 1), nullptr, 0);
+        waited = true;
+      }
+      const int count = pc.count;
+      for (int e0 = tid; e0 < count; e0 += ST_THREADS * 4) {
+        // up to 4 cached points per thread with their row loads in flight together (backward)
+        float g[kBackward ? 4 : 1][CG];
+        if (kBackward) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int e = e0 + q * ST_THREADS;
+            if (e < count) {
+              const float* src = a.rows_in + (long long)pc.n[e] * a.C + c0;
+#pragma unroll
+              for (int kk = 0; kk < CG; ++kk) g[kBackward ? q : 0][kk] = (kk < cg) ? __ldg(src + kk) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = e0 + q * ST_THREADS;
+          if (e >= count) continue;
+          Tri t;
+          trilinear(pc.x[e], pc.y[e], pc.z[e], t);
+          if (kBackward) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (t.ix[j] >= 0 && t.ix[j] < a.X && t.iy[j] >= 0 && t.iy[j] < a.Y && t.iz[j] >= 0 &&
+                  t.iz[j] < a.Z) {
+                const int flat = (t.ix[j] * a.Y + t.iy[j]) * a.Z + t.iz[j];
+#pragma unroll
+                for (int kk = 0; kk < CG; ++kk)
+                  if (kk < cg) atomicAdd(buf + kk * V + flat, __fmul_rn(t.w[j], g[kBackward ? q : 0][kk]));
+              }
+            }
+          } else {
+            float acc[CG];
+#pragma unroll
+            for (int kk = 0; kk < CG; ++kk) acc[kk] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (t.ix[j] >= 0 && t.ix[j] < a.X && t.iy[j] >= 0 && t.iy[j] < a.Y && t.iz[j] >= 0 &&
+                  t.iz[j] < a.Z) {
+                const int flat = (t.ix[j] * a.Y + t.iy[j]) * a.Z + t.iz[j];
+#pragma unroll
+                for (int kk = 0; kk < CG; ++kk)
+                  if (kk < cg) acc[kk] = __fadd_rn(acc[kk], __fmul_rn(t.w[j], buf[kk * V + flat]));
+              }
+            }
+            float* dst = a.rows_out + (long long)pc.n[e] * a.C + c0;
+            if (CG >= 4 && cg == CG && ((a.C & 3) == 0)) {
+#pragma unroll
+              for (int kk = 0; kk < CG / 4; ++kk)
+                reinterpret_cast<float4*>(dst)[kk] =
+                    make_float4(acc[4 * kk], acc[4 * kk + 1], acc[4 * kk + 2], acc[4 * kk + 3]);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < CG; ++kk)
+                if (kk < cg) dst[kk] = acc[kk];
+            }
+          }
+        }
+      }
+      if (pc.next >= (int)a.P) break;
+      from = pc.next;
+      cached_b = -1;                             // partial cache: rebuild on the next pass / item
+    }
+    if (kBackward) {
+      fence_async_smem();                        // generic-proxy writes -> visible to the bulk copy
+      __syncthreads();
+      if (tid == 0)
+        bulk_s2g(a.grid_out + ((long long)b * a.C + c0) * V, buf, (uint32_t)(cg * V * 4));
+    } else {
+      __syncthreads();                           // everybody is done reading buf
+    }
+  }
+  if (kBackward && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// channel planes per item of the streaming kernels: buffers of <= 64 KB and, if possible, at
+// least three items per SM
+static int stream_planes(long long V, int C, int B, int n_sm) {
+  if ((V & 3) != 0 || V * 4 > 64 * 1024) return 0;
+  int cg = 16;
+  while (cg > 1 && (cg * V * 4 > 64 * 1024 || (long long)((C + cg - 1) / cg) * B < 3LL * n_sm)) cg >>= 1;
+  return cg;
+}
+
+template <int CG, bool kBackward>
+static int launch_stream(const StreamArgs& a0, int n_sm, cudaStream_t stream) {
+  StreamArgs a = a0;
+  a.n_groups = (a.C + CG - 1) / CG;
+  a.n_items = a.n_groups * a.B;
+  const size_t V = (size_t)a.X * a.Y * a.Z;
+  const size_t smem = 2 * CG * V * 4 + sizeof(PointCache) + 2 * sizeof(uint64_t) + 128;
+  MF_ENSURE_DYN_SMEM((k_interp_stream<CG, kBackward>), smem);
+  const int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  k_interp_stream<CG, kBackward><<<grid, ST_THREADS, smem, stream>>>(a);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+template <bool kBackward>
+static int dispatch_stream(int cg, const StreamArgs& a, int n_sm, cudaStream_t stream) {
+  switch (cg) {
+    case 1: return launch_stream<1, kBackward>(a, n_sm, stream);
+    case 2: return launch_stream<2, kBackward>(a, n_sm, stream);
+    case 4: return launch_stream<4, kBackward>(a, n_sm, stream);
+    case 8: return launch_stream<8, kBackward>(a, n_sm, stream);
+    default: return launch_stream<16, kBackward>(a, n_sm, stream);
+  }
+}
+
+// channel planes per CTA: ~32 KB of shared memory, i.e. 7 CTAs (56 warps) per SM and, at the model
+// shapes, all CTAs of the launch resident in one wave (measured: 64 KB / 3 CTAs per SM ran 1.15
+// waves of latency-bound CTAs at 33 % warp occupancy)
 static int planes_per_cta(long long V) {
   if (V * 4 > 160 * 1024) return 0;          // a plane does not fit: simple kernels
-  if (V > 8192) return 1;
-  if (V > 4096) return 2;
-  if (V > 2048) return 4;
-  if (V > 1024) return 8;
+  if (V > 4096) return 1;
+  if (V > 2048) return 2;
+  if (V > 1024) return 4;
+  if (V > 512) return 8;
   return 16;
 }
 
 }  // namespace mf
 
 using namespace mf;
+
+static int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+static int stream_cg(long long V, int C, int B) { return stream_planes(V, C, B, sm_count()); }
 
 #define MF_INTERP_PLANES(KERNEL, CGV, ...)                                              \
   do {                                                                                  \
@@ -269,6 +584,12 @@ extern "C" int mf_interpolate_voxel_grid_fwd(const float* voxelized, const float
   if (channels_last) {
     k_interp_fwd<true><<<div_up(P * C, 256), 256, 0, stream>>>(voxelized, points, batch_indices, P,
                                                                B, C, X, Y, Z, values);
+  } else if (P < (1LL << 31) && stream_cg(V, C, B) > 0) {
+    // persistent streaming path: bulk-copied planes double-buffered in shared memory
+    StreamArgs a;
+    a.grid_in = voxelized; a.grid_out = nullptr; a.rows_in = nullptr; a.rows_out = values;
+    a.points = points; a.bi = batch_indices; a.P = P; a.B = B; a.C = C; a.X = X; a.Y = Y; a.Z = Z;
+    return dispatch_stream<false>(stream_cg(V, C, B), a, sm_count(), stream);
   } else if (planes_per_cta(V) > 0 && P <= (1LL << 22) && B <= 65535) {
     // plane-staged path: CG channel planes per CTA in shared memory
     switch (planes_per_cta(V)) {
@@ -295,6 +616,12 @@ extern "C" int mf_interpolate_voxel_grid_bwd(const float* gvalues, const float* 
   if (!gvoxelized) return MF_E_BADARG;
   if (P > 0 && (!gvalues || !points || !batch_indices)) return MF_E_BADARG;
   const long long V = (long long)X * Y * Z;
+  if (!channels_last && P > 0 && P < (1LL << 31) && stream_cg(V, C, B) > 0) {
+    StreamArgs a;
+    a.grid_in = nullptr; a.grid_out = gvoxelized; a.rows_in = gvalues; a.rows_out = nullptr;
+    a.points = points; a.bi = batch_indices; a.P = P; a.B = B; a.C = C; a.X = X; a.Y = Y; a.Z = Z;
+    return dispatch_stream<true>(stream_cg(V, C, B), a, sm_count(), stream);
+  }
   if (!channels_last && P > 0 && planes_per_cta(V) > 0 && P <= (1LL << 22) && B <= 65535) {
     // plane-staged path: every output element written once, no memset, no global atomics
     switch (planes_per_cta(V)) {
