@@ -322,34 +322,37 @@ struct PointCache {
   int next;                // scan position after this pass
 };
 
-// points of batch b with index >= from, up to ST_MAXP of them, into the cache (any order)
-__device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a, int b, long long from) {
+// points of batch b with index >= from, up to `cap` (<= ST_MAXP) of them, into the cache (any order)
+template <int NT>
+__device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a, int b, long long from,
+                                             int cap = ST_MAXP) {
+  constexpr int PER = ST_CHUNK / NT;
   __syncthreads();
   if (threadIdx.x == 0) { pc.count = 0; pc.next = (int)a.P; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  // chunks of 8 x 256 indices; a chunk is only taken if it is certain to fit
+  // chunks of ST_CHUNK indices; a chunk is only taken if it is certain to fit
   for (long long base = from; base < a.P; base += ST_CHUNK) {
-    if (pc.count + ST_CHUNK > ST_MAXP) {        // uniform: read after the barrier below
+    if (pc.count + ST_CHUNK > cap && pc.count > 0) {   // uniform: read after the barrier below
       if (threadIdx.x == 0) pc.next = (int)base;
       break;
     }
-    int bb[8];
+    int bb[PER];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const long long n = base + u * ST_THREADS + threadIdx.x;
+    for (int u = 0; u < PER; ++u) {
+      const long long n = base + u * NT + threadIdx.x;
       bb[u] = (n < a.P) ? __ldg(a.bi + n) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < PER; ++u) {
       const bool m = bb[u] == b;
       const unsigned bal = __ballot_sync(0xffffffffu, m);
       if (bal) {
         int pos = 0;
         if (lane == 0) pos = atomicAdd(&pc.count, __popc(bal));
         pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-        if (m) {
-          const long long n = base + u * ST_THREADS + threadIdx.x;
+        if (m && pos < ST_MAXP) {
+          const long long n = base + u * NT + threadIdx.x;
           pc.n[pos] = (int)n;
           pc.x[pos] = __ldg(a.points + 3 * n);
           pc.y[pos] = __ldg(a.points + 3 * n + 1);
@@ -360,6 +363,144 @@ __device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a
     __syncthreads();                                   // pc.count is final for this chunk
   }
   __syncthreads();
+}
+
+// ---- voxel-centric backward --------------------------------------------------------------
+// Scattering 8 P C products needs atomics, and shared-memory float atomics are CAS loops on this
+// architecture (ATOMS.CAST.SPIN in the SASS; measured 115 / 290 us with the planes in shared
+// memory, worse than the global-atomic kernel).  Inverted here: per batch the points are binned
+// by their base cell (counting sort in shared memory, each cell's list ordered by point index),
+// then every VOXEL of an item's planes sums the contributions of the <= 8 cells whose corners
+// land on it -- no atomics, deterministic order (corner j = 0..7, then point index), every output
+// element written exactly once with coalesced stores, no memset.
+constexpr int GB_THREADS = 512;
+constexpr int GB_MAX_CELLS = 8192;       // (X+1)(Y+1)(Z+1) base cells that can touch the grid
+
+template <int CG>
+__global__ void __launch_bounds__(GB_THREADS, 1)
+k_interp_bwd_gather(StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int X = a.X, Y = a.Y, Z = a.Z, V = X * Y * Z;
+  const int NC = (X + 1) * (Y + 1) * (Z + 1);
+  PointCache& pc = *reinterpret_cast<PointCache*>(smem_raw);
+  int* cell_start = reinterpret_cast<int*>(&pc + 1);       // [NC + 1]
+  int* cursor = cell_start + NC + 1;                        // [NC]
+  int* perm = cursor + NC;                                  // [ST_MAXP] cache slots in cell order
+  float* rows = reinterpret_cast<float*>(perm + ST_MAXP);   // [ST_MAXP][CG] staged gradient rows
+  __shared__ int warp_tot[GB_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (a.n_items + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per, it1 = min(a.n_items, it0 + per);
+  if (it0 >= it1) return;
+  int cached_b = -1;
+  bool cache_whole = false;
+  for (int item = it0; item < it1; ++item) {
+    const int b = item / a.n_groups;
+    const int c0 = (item - b * a.n_groups) * CG;
+    const int cg = min(CG, a.C - c0);
+    long long from = 0;
+    int pass = 0;
+    for (;;) {
+      if (!(cached_b == b && cache_whole)) {
+        cache_points<GB_THREADS>(pc, a, b, from);
+        cached_b = b;
+        cache_whole = (from == 0 && pc.next >= (int)a.P);
+        // ---- bin the cached points by base cell
+        const int count = min(pc.count, ST_MAXP);
+        for (int c = tid; c < NC; c += GB_THREADS) cursor[c] = 0;
+        __syncthreads();
+        for (int e = tid; e < count; e += GB_THREADS) {
+          const int x0 = (int)pc.x[e], y0 = (int)pc.y[e], z0 = (int)pc.z[e];
+          if (x0 >= -1 && x0 < X && y0 >= -1 && y0 < Y && z0 >= -1 && z0 < Z)
+            atomicAdd(cursor + ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1), 1);
+        }
+        __syncthreads();
+        {   // exclusive scan of the NC counts: contiguous slice per thread, warp scan, warp totals
+          const int chunk = (NC + GB_THREADS - 1) / GB_THREADS;
+          const int cb = tid * chunk, ce = min(NC, cb + chunk);
+          int sum = 0;
+          for (int c = cb; c < ce; ++c) sum += cursor[c];
+          int incl = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+          }
+          if (lane == 31) warp_tot[warp] = incl;
+          __syncthreads();
+          int off = incl - sum;
+          for (int w = 0; w < warp; ++w) off += warp_tot[w];
+          for (int c = cb; c < ce; ++c) {
+            const int n_c = cursor[c];
+            cell_start[c] = off;
+            cursor[c] = off;
+            off += n_c;
+          }
+          if (tid == GB_THREADS - 1) cell_start[NC] = off;   // chunk * GB_THREADS >= NC: last thread ends at NC
+          __syncthreads();
+        }
+        for (int e = tid; e < count; e += GB_THREADS) {
+          const int x0 = (int)pc.x[e], y0 = (int)pc.y[e], z0 = (int)pc.z[e];
+          if (x0 >= -1 && x0 < X && y0 >= -1 && y0 < Y && z0 >= -1 && z0 < Z)
+            perm[atomicAdd(cursor + ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1), 1)] = e;
+        }
+        __syncthreads();
+        // each cell's list in ascending point index: the sum order is then fixed
+        for (int c = tid; c < NC; c += GB_THREADS) {
+          const int s0 = cell_start[c], s1 = cell_start[c + 1];
+          for (int i = s0 + 1; i < s1; ++i) {
+            const int e = perm[i], key = pc.n[e];
+            int j = i - 1;
+            while (j >= s0 && pc.n[perm[j]] > key) { perm[j + 1] = perm[j]; --j; }
+            perm[j + 1] = e;
+          }
+        }
+        __syncthreads();
+      }
+      // ---- stage the gradient rows of the cached points for this item's channels
+      const int count = min(pc.count, ST_MAXP);
+      for (int i = tid; i < count * CG; i += GB_THREADS) {
+        const int e = i / CG, kk = i - e * CG;
+        rows[i] = (kk < cg) ? __ldg(a.rows_in + (long long)pc.n[e] * a.C + c0 + kk) : 0.f;
+      }
+      __syncthreads();
+      // ---- one voxel per thread and step
+      for (int v = tid; v < V; v += GB_THREADS) {
+        const int iz = v % Z, iy = (v / Z) % Y, ix = v / (Z * Y);
+        float acc[CG];
+#pragma unroll
+        for (int kk = 0; kk < CG; ++kk) acc[kk] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // corner order of the reference: w000 w100 w010 w001 w110 w011 w101 w111
+          const int dx = (0xD2 >> j) & 1, dy = (0xB4 >> j) & 1, dz = (0xE8 >> j) & 1;
+          const int x0 = ix - dx, y0 = iy - dy, z0 = iz - dz;
+          const int c = ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1);
+          const int s0 = cell_start[c], s1 = cell_start[c + 1];
+          for (int i = s0; i < s1; ++i) {
+            const int e = perm[i];
+            const float lx = __fsub_rn(pc.x[e], (float)x0), ly = __fsub_rn(pc.y[e], (float)y0),
+                        lz = __fsub_rn(pc.z[e], (float)z0);
+            const float wx = dx ? lx : __fsub_rn(1.f, lx), wy = dy ? ly : __fsub_rn(1.f, ly),
+                        wz = dz ? lz : __fsub_rn(1.f, lz);
+            const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+#pragma unroll
+            for (int kk = 0; kk < CG; ++kk)
+              acc[kk] = __fadd_rn(acc[kk], __fmul_rn(w, rows[e * CG + kk]));
+          }
+        }
+        float* dst = a.grid_out + ((long long)b * a.C + c0) * V + v;
+#pragma unroll
+        for (int kk = 0; kk < CG; ++kk)
+          if (kk < cg) dst[(long long)kk * V] = pass == 0 ? acc[kk] : __fadd_rn(dst[(long long)kk * V], acc[kk]);
+      }
+      __syncthreads();
+      if (pc.next >= (int)a.P) break;
+      from = pc.next;
+      cached_b = -1;
+      ++pass;
+    }
+  }
 }
 
 template <int CG, bool kBackward>
@@ -423,7 +564,7 @@ k_interp_stream(StreamArgs a) {
     long long from = 0;
     for (;;) {                                   // passes over the batch's points (one, normally)
       if (!(cached_b == b && cache_whole)) {
-        cache_points(pc, a, b, from);
+        cache_points<ST_THREADS>(pc, a, b, from);
         cached_b = b;
         cache_whole = (from == 0 && pc.next >= (int)a.P);
       }
@@ -530,6 +671,35 @@ static int launch_stream(const StreamArgs& a0, int n_sm, cudaStream_t stream) {
   return MF_OK;
 }
 
+static size_t bwd_gather_smem(int X, int Y, int Z, int cg) {
+  const size_t NC = (size_t)(X + 1) * (Y + 1) * (Z + 1);
+  return sizeof(PointCache) + (2 * NC + 1 + ST_MAXP) * 4 + (size_t)ST_MAXP * cg * 4 + 128;
+}
+
+template <int CG>
+static int launch_bwd_gather(const StreamArgs& a0, int n_sm, cudaStream_t stream) {
+  StreamArgs a = a0;
+  a.n_groups = (a.C + CG - 1) / CG;
+  a.n_items = a.n_groups * a.B;
+  const size_t smem = bwd_gather_smem(a.X, a.Y, a.Z, CG);
+  MF_ENSURE_DYN_SMEM((k_interp_bwd_gather<CG>), smem);
+  const int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  k_interp_bwd_gather<CG><<<grid, GB_THREADS, smem, stream>>>(a);
+  MF_LAUNCH_CHECK();
+  return MF_OK;
+}
+
+static int dispatch_bwd_gather(int cg, const StreamArgs& a, int n_sm, cudaStream_t stream) {
+  if (cg > 8) cg = 8;
+  while (cg > 1 && bwd_gather_smem(a.X, a.Y, a.Z, cg) > 220 * 1024) cg >>= 1;
+  switch (cg) {
+    case 1: return launch_bwd_gather<1>(a, n_sm, stream);
+    case 2: return launch_bwd_gather<2>(a, n_sm, stream);
+    case 4: return launch_bwd_gather<4>(a, n_sm, stream);
+    default: return launch_bwd_gather<8>(a, n_sm, stream);
+  }
+}
+
 template <bool kBackward>
 static int dispatch_stream(int cg, const StreamArgs& a, int n_sm, cudaStream_t stream) {
   switch (cg) {
@@ -620,6 +790,9 @@ extern "C" int mf_interpolate_voxel_grid_bwd(const float* gvalues, const float* 
     StreamArgs a;
     a.grid_in = nullptr; a.grid_out = gvoxelized; a.rows_in = gvalues; a.rows_out = nullptr;
     a.points = points; a.bi = batch_indices; a.P = P; a.B = B; a.C = C; a.X = X; a.Y = Y; a.Z = Z;
+    if ((long long)(X + 1) * (Y + 1) * (Z + 1) <= GB_MAX_CELLS &&
+        bwd_gather_smem(X, Y, Z, 1) <= 220 * 1024)
+      return dispatch_bwd_gather(stream_cg(V, C, B), a, sm_count(), stream);
     return dispatch_stream<true>(stream_cg(V, C, B), a, sm_count(), stream);
   }
   if (!channels_last && P > 0 && planes_per_cta(V) > 0 && P <= (1LL << 22) && B <= 65535) {
