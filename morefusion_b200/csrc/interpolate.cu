@@ -281,8 +281,8 @@ k_interp_bwd_planes(const float* __restrict__ gvalues, const float* __restrict__
 //     together) and kept in shared memory (index + coordinates) for every item of that batch.
 // Arithmetic per (point, channel) is unchanged (corner order j = 0..7, explicit _rn ops): the
 // forward stays bit-identical.
-constexpr int ST_THREADS = 256;
-constexpr int ST_CHUNK = ST_THREADS * 8;   // batch indices scanned per step (all loads in flight)
+constexpr int ST_THREADS = 512;
+constexpr int ST_CHUNK = 2048;             // batch indices scanned per step (all loads in flight)
 constexpr int ST_MAXP = 2 * ST_CHUNK;      // cached points per pass (index + xyz = 16 B each): a batch
                                            // of <= ST_CHUNK points is always cached whole
 
@@ -365,28 +365,43 @@ __device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a
   __syncthreads();
 }
 
-// ---- voxel-centric backward --------------------------------------------------------------
+// ---- cell-owner backward -----------------------------------------------------------------
 // Scattering 8 P C products needs atomics, and shared-memory float atomics are CAS loops on this
 // architecture (ATOMS.CAST.SPIN in the SASS; measured 115 / 290 us with the planes in shared
-// memory, worse than the global-atomic kernel).  Inverted here: per batch the points are binned
-// by their base cell (counting sort in shared memory, each cell's list ordered by point index),
-// then every VOXEL of an item's planes sums the contributions of the <= 8 cells whose corners
-// land on it -- no atomics, deterministic order (corner j = 0..7, then point index), every output
-// element written exactly once with coalesced stores, no memset.
+// memory, worse than the global-atomic kernel).  A per-voxel gather over cell lists has no atomics
+// but wastes the warp (measured 151 / 186 us at 5.6 active threads per instruction: most lists are
+// empty or one point long).  Here, per batch, the points are binned by their base cell (counting
+// sort in shared memory, each cell's list in ascending point index) and the NON-EMPTY cells are
+// listed; an item's planes live in shared memory and are filled in 8 phases, one per corner: in
+// phase j a thread owns one non-empty cell and adds its points' w_j g products to the voxel
+// (cell + offset_j) -- distinct cells hit distinct voxels within a phase, so plain read-modify-
+// write is race-free; block barriers separate the phases.  No atomics, deterministic order
+// (corner j = 0..7, then point index), every output element written exactly once, no memset.
 constexpr int GB_THREADS = 512;
+constexpr int GB_MAXP = 2048;            // cached points per pass
+constexpr int GB_CHUNK = 1024;           // batch indices scanned per step: <= 1024 points per batch
+                                         // are always cached whole
 constexpr int GB_MAX_CELLS = 8192;       // (X+1)(Y+1)(Z+1) base cells that can touch the grid
+
+struct GbCache {
+  int n[GB_MAXP];
+  float x[GB_MAXP], y[GB_MAXP], z[GB_MAXP];
+  int perm[GB_MAXP];                     // cache slots in (cell, point index) order
+  int nz[GB_MAXP];                       // non-empty cells
+  int count, next, n_nz;
+};
 
 template <int CG>
 __global__ void __launch_bounds__(GB_THREADS, 1)
-k_interp_bwd_gather(StreamArgs a) {
+k_interp_bwd_cells(StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int X = a.X, Y = a.Y, Z = a.Z, V = X * Y * Z;
   const int NC = (X + 1) * (Y + 1) * (Z + 1);
-  PointCache& pc = *reinterpret_cast<PointCache*>(smem_raw);
-  int* cell_start = reinterpret_cast<int*>(&pc + 1);       // [NC + 1]
-  int* cursor = cell_start + NC + 1;                        // [NC]
-  int* perm = cursor + NC;                                  // [ST_MAXP] cache slots in cell order
-  float* rows = reinterpret_cast<float*>(perm + ST_MAXP);   // [ST_MAXP][CG] staged gradient rows
+  float* planes = reinterpret_cast<float*>(smem_raw);             // [CG][V]
+  float* rows = planes + (size_t)CG * V;                          // [GB_MAXP][CG] staged gradient rows
+  GbCache& pc = *reinterpret_cast<GbCache*>(rows + (size_t)GB_MAXP * CG);
+  int* cell_start = reinterpret_cast<int*>(&pc + 1);              // [NC + 1]
+  int* cursor = cell_start + NC + 1;                              // [NC]
   __shared__ int warp_tot[GB_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = (a.n_items + gridDim.x - 1) / gridDim.x;
@@ -398,15 +413,51 @@ k_interp_bwd_gather(StreamArgs a) {
     const int b = item / a.n_groups;
     const int c0 = (item - b * a.n_groups) * CG;
     const int cg = min(CG, a.C - c0);
+    for (int e = tid; e < cg * (V >> 2); e += GB_THREADS)
+      reinterpret_cast<float4*>(planes)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     long long from = 0;
-    int pass = 0;
     for (;;) {
       if (!(cached_b == b && cache_whole)) {
-        cache_points<GB_THREADS>(pc, a, b, from);
+        // ---- points of batch b from index `from` on (all batch-index loads of a step in flight)
+        __syncthreads();
+        if (tid == 0) { pc.count = 0; pc.next = (int)a.P; pc.n_nz = 0; }
+        __syncthreads();
+        for (long long base = from; base < a.P; base += GB_CHUNK) {
+          if (pc.count + GB_CHUNK > GB_MAXP) {               // uniform (read after a barrier)
+            if (tid == 0) pc.next = (int)base;
+            break;
+          }
+          constexpr int PER = GB_CHUNK / GB_THREADS;
+          int bb[PER];
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            const long long n = base + u * GB_THREADS + tid;
+            bb[u] = (n < a.P) ? __ldg(a.bi + n) : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            const bool m = bb[u] == b;
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (bal) {
+              int pos = 0;
+              if (lane == 0) pos = atomicAdd(&pc.count, __popc(bal));
+              pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+              if (m) {
+                const long long n = base + u * GB_THREADS + tid;
+                pc.n[pos] = (int)n;
+                pc.x[pos] = __ldg(a.points + 3 * n);
+                pc.y[pos] = __ldg(a.points + 3 * n + 1);
+                pc.z[pos] = __ldg(a.points + 3 * n + 2);
+              }
+            }
+          }
+          __syncthreads();
+        }
+        __syncthreads();
         cached_b = b;
         cache_whole = (from == 0 && pc.next >= (int)a.P);
         // ---- bin the cached points by base cell
-        const int count = min(pc.count, ST_MAXP);
+        const int count = pc.count;
         for (int c = tid; c < NC; c += GB_THREADS) cursor[c] = 0;
         __syncthreads();
         for (int e = tid; e < count; e += GB_THREADS) {
@@ -435,50 +486,53 @@ k_interp_bwd_gather(StreamArgs a) {
             cell_start[c] = off;
             cursor[c] = off;
             off += n_c;
+            if (n_c > 0) pc.nz[atomicAdd(&pc.n_nz, 1)] = c;      // any order: cells are independent
           }
-          if (tid == GB_THREADS - 1) cell_start[NC] = off;   // chunk * GB_THREADS >= NC: last thread ends at NC
+          if (tid == GB_THREADS - 1) cell_start[NC] = off;
           __syncthreads();
         }
         for (int e = tid; e < count; e += GB_THREADS) {
           const int x0 = (int)pc.x[e], y0 = (int)pc.y[e], z0 = (int)pc.z[e];
           if (x0 >= -1 && x0 < X && y0 >= -1 && y0 < Y && z0 >= -1 && z0 < Z)
-            perm[atomicAdd(cursor + ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1), 1)] = e;
+            pc.perm[atomicAdd(cursor + ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1), 1)] = e;
         }
         __syncthreads();
         // each cell's list in ascending point index: the sum order is then fixed
-        for (int c = tid; c < NC; c += GB_THREADS) {
+        for (int i0 = tid; i0 < pc.n_nz; i0 += GB_THREADS) {
+          const int c = pc.nz[i0];
           const int s0 = cell_start[c], s1 = cell_start[c + 1];
           for (int i = s0 + 1; i < s1; ++i) {
-            const int e = perm[i], key = pc.n[e];
+            const int e = pc.perm[i], key = pc.n[e];
             int j = i - 1;
-            while (j >= s0 && pc.n[perm[j]] > key) { perm[j + 1] = perm[j]; --j; }
-            perm[j + 1] = e;
+            while (j >= s0 && pc.n[pc.perm[j]] > key) { pc.perm[j + 1] = pc.perm[j]; --j; }
+            pc.perm[j + 1] = e;
           }
         }
-        __syncthreads();
       }
+      __syncthreads();
       // ---- stage the gradient rows of the cached points for this item's channels
-      const int count = min(pc.count, ST_MAXP);
+      const int count = pc.count;
       for (int i = tid; i < count * CG; i += GB_THREADS) {
         const int e = i / CG, kk = i - e * CG;
         rows[i] = (kk < cg) ? __ldg(a.rows_in + (long long)pc.n[e] * a.C + c0 + kk) : 0.f;
       }
       __syncthreads();
-      // ---- one voxel per thread and step
-      for (int v = tid; v < V; v += GB_THREADS) {
-        const int iz = v % Z, iy = (v / Z) % Y, ix = v / (Z * Y);
-        float acc[CG];
+      // ---- 8 phases, one per corner (reference order w000 w100 w010 w001 w110 w011 w101 w111)
+      const int n_nz = pc.n_nz;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        const int dx = (0xD2 >> j) & 1, dy = (0xB4 >> j) & 1, dz = (0xE8 >> j) & 1;
+        for (int i0 = tid; i0 < n_nz; i0 += GB_THREADS) {
+          const int c = pc.nz[i0];
+          const int z0 = c % (Z + 1) - 1, y0 = (c / (Z + 1)) % (Y + 1) - 1, x0 = c / ((Z + 1) * (Y + 1)) - 1;
+          const int ix = x0 + dx, iy = y0 + dy, iz = z0 + dz;
+          if (ix < 0 || ix >= X || iy < 0 || iy >= Y || iz < 0 || iz >= Z) continue;
+          float acc[CG];
 #pragma unroll
-        for (int kk = 0; kk < CG; ++kk) acc[kk] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // corner order of the reference: w000 w100 w010 w001 w110 w011 w101 w111
-          const int dx = (0xD2 >> j) & 1, dy = (0xB4 >> j) & 1, dz = (0xE8 >> j) & 1;
-          const int x0 = ix - dx, y0 = iy - dy, z0 = iz - dz;
-          const int c = ((x0 + 1) * (Y + 1) + (y0 + 1)) * (Z + 1) + (z0 + 1);
+          for (int kk = 0; kk < CG; ++kk) acc[kk] = 0.f;
           const int s0 = cell_start[c], s1 = cell_start[c + 1];
           for (int i = s0; i < s1; ++i) {
-            const int e = perm[i];
+            const int e = pc.perm[i];
             const float lx = __fsub_rn(pc.x[e], (float)x0), ly = __fsub_rn(pc.y[e], (float)y0),
                         lz = __fsub_rn(pc.z[e], (float)z0);
             const float wx = dx ? lx : __fsub_rn(1.f, lx), wy = dy ? ly : __fsub_rn(1.f, ly),
@@ -488,18 +542,22 @@ k_interp_bwd_gather(StreamArgs a) {
             for (int kk = 0; kk < CG; ++kk)
               acc[kk] = __fadd_rn(acc[kk], __fmul_rn(w, rows[e * CG + kk]));
           }
-        }
-        float* dst = a.grid_out + ((long long)b * a.C + c0) * V + v;
+          float* dst = planes + (ix * Y + iy) * Z + iz;
 #pragma unroll
-        for (int kk = 0; kk < CG; ++kk)
-          if (kk < cg) dst[(long long)kk * V] = pass == 0 ? acc[kk] : __fadd_rn(dst[(long long)kk * V], acc[kk]);
+          for (int kk = 0; kk < CG; ++kk)
+            if (kk < cg) dst[kk * V] = __fadd_rn(dst[kk * V], acc[kk]);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       if (pc.next >= (int)a.P) break;
       from = pc.next;
       cached_b = -1;
-      ++pass;
     }
+    // ---- the item's planes are contiguous in the output: coalesced 16-byte stores
+    float4* d4 = reinterpret_cast<float4*>(a.grid_out + ((long long)b * a.C + c0) * V);
+    for (int e = tid; e < cg * (V >> 2); e += GB_THREADS)
+      __stcs(d4 + e, reinterpret_cast<const float4*>(planes)[e]);
+    __syncthreads();
   }
 }
 
@@ -672,8 +730,8 @@ static int launch_stream(const StreamArgs& a0, int n_sm, cudaStream_t stream) {
 }
 
 static size_t bwd_gather_smem(int X, int Y, int Z, int cg) {
-  const size_t NC = (size_t)(X + 1) * (Y + 1) * (Z + 1);
-  return sizeof(PointCache) + (2 * NC + 1 + ST_MAXP) * 4 + (size_t)ST_MAXP * cg * 4 + 128;
+  const size_t NC = (size_t)(X + 1) * (Y + 1) * (Z + 1), V = (size_t)X * Y * Z;
+  return (size_t)cg * V * 4 + (size_t)GB_MAXP * cg * 4 + sizeof(GbCache) + (2 * NC + 1) * 4 + 128;
 }
 
 template <int CG>
@@ -682,9 +740,9 @@ static int launch_bwd_gather(const StreamArgs& a0, int n_sm, cudaStream_t stream
   a.n_groups = (a.C + CG - 1) / CG;
   a.n_items = a.n_groups * a.B;
   const size_t smem = bwd_gather_smem(a.X, a.Y, a.Z, CG);
-  MF_ENSURE_DYN_SMEM((k_interp_bwd_gather<CG>), smem);
+  MF_ENSURE_DYN_SMEM((k_interp_bwd_cells<CG>), smem);
   const int grid = a.n_items < n_sm ? a.n_items : n_sm;
-  k_interp_bwd_gather<CG><<<grid, GB_THREADS, smem, stream>>>(a);
+  k_interp_bwd_cells<CG><<<grid, GB_THREADS, smem, stream>>>(a);
   MF_LAUNCH_CHECK();
   return MF_OK;
 }
