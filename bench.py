@@ -464,6 +464,61 @@ def bench_chain(dev, model, runner, rank, world, quick):
     barrier(world)
     ms_f = max_over_ranks(e0.elapsed_time(e1), world, dev)
     per_frame_f = ms_f / (n_groups * F)
+
+    # ---- the same with the map front end in every frame: depth + instance
+    # label H2D (2 x 1.2 MB), depth -> point image, labelled OctoMap scan into the persistent device
+    # map, the 3 x 8 target grids, grid_nontarget_empty composed as the evaluation transform does
+    # (train.py:50-54,92-105).  The synthetic generators are not ONE consistent scene: the map
+    # stage runs on its own 640x480 frames and its grids are produced and combined every frame,
+    # while the CNN / ICC consume the scene's precomputed grids (same sizes, same work).
+    from morefusion_b200 import geometry as mgeo
+    from morefusion_b200.contrib import MultiInstanceOctreeMapping
+    fr = [synthetic.make_depth_frame(seed=40 + j) for j in range(2)]
+    pitches = fr[0][3]
+    ids = sorted(i for i in pitches if i != 0) + [0]
+    mp = MultiInstanceOctreeMapping(device=dev)
+    for ins in ids:
+        mp.initialize(ins, pitch=pitches[ins])
+    h_depth = [torch.from_numpy(np.ascontiguousarray(f[0][..., 2])).pin_memory() for f in fr]
+    h_label = [torch.from_numpy(np.ascontiguousarray(f[1])).pin_memory() for f in fr]
+    d_depth = torch.empty(tuple(h_depth[0].shape), dtype=torch.float32, device=dev)
+    d_label = torch.empty(tuple(h_label[0].shape), dtype=torch.int32, device=dev)
+    Hh, Ww = h_depth[0].shape
+    tids = [i for i in ids if i != 0]
+    t_orig = [np.nanmedian(fr[0][0][fr[0][1] == t], axis=0) - 15.5 * pitches[t] for t in tids]
+    t_pit = [pitches[t] for t in tids]
+
+    def frontend(i):
+        k = i % 2
+        d_depth.copy_(h_depth[k], non_blocking=True)
+        d_label.copy_(h_label[k], non_blocking=True)
+        pcd = mgeo.pointcloud_from_depth(d_depth, fx=600.0, fy=600.0, cx=Ww / 2, cy=Hh / 2)
+        mp.integrate_labels(d_label, pcd)
+        gt, gn, ge = mp.get_target_grids_batch(tids, dimensions=(32, 32, 32), pitches=t_pit, origins=t_orig)
+        tgt = gt > 0.5
+        return ((gn > 0.5) ^ tgt) | ((ge > 0.5) ^ tgt)               # grid_nontarget_empty [8,32,32,32]
+
+    def frames_full(i0):
+        keep = [frontend(i0 + j) for j in range(F)]
+        frames(i0)
+        return keep
+
+    frames_full(0)
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for g in range(n_groups):
+        frames_full(g * F)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_full = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    with_map = dict(value=n_groups * F * world * 8 / (ms_full * 1e-3), ms_per_frame=ms_full / (n_groups * F),
+                    extra_h2d_bytes_per_frame=int(h_depth[0].numel() * 4 + h_label[0].numel() * 4),
+                    map_cells=mp.n_cells(),
+                    stages="depth+label H2D -> k_pointcloud_from_depth -> k_map_scan_hits/free (all "
+                           "instances) -> k_map_query_grids (8 targets) -> gne -> [CNN -> ICC as above]")
     return dict(metric="objects/sec per-frame chain voxelise->3D-CNN->ICC",
                 value=n_groups * F * world * 8 / (ms_f * 1e-3), unit="objects/s",
                 frames=n_groups * F * world, objects_per_frame=8, icc_iterations=icc_iter,
@@ -471,6 +526,7 @@ def bench_chain(dev, model, runner, rank, world, quick):
                 latency_of_a_frame_group_ms=ms_f / n_groups,
                 single_frame_mode=dict(value=len(my) * world * 8 / (ms * 1e-3), ms_per_frame=ms / len(my),
                                        frames=len(my) * world, frames_per_icc_launch=1),
+                with_map_frontend=with_map,
                 h2d_bytes_per_frame=int(h2d), d2h_bytes_per_frame=int(out_pose.numel() * 4),
                 n_gpus=world,
                 timed="CUDA events around the frame loop incl. H2D/D2H, max over ranks; `value` = "
