@@ -76,9 +76,13 @@ __device__ __forceinline__ MapCell map_load(const MapCell* c) {
 // slot of `key`, inserting it when absent; -1 when the table is full (overflow flag raised).
 // *seen = the cell as loaded (stamp 0 for a cell this call inserted or lost the race for: a stale
 // stamp only costs a redundant atomicMax, never an update).
+// Probe sequences are bounded (MAP_MAX_PROBES): a table that is (nearly) full reports overflow
+// instead of walking millions of slots per thread.
+static constexpr unsigned MAP_MAX_PROBES = 4096;
 __device__ __forceinline__ int map_find_or_insert(const MapTable& t, u64 key, MapCell* seen) {
   unsigned s = map_hash(key) & t.mask;
-  for (unsigned n = 0; n <= t.mask; ++n) {
+  const unsigned limit = t.mask < MAP_MAX_PROBES ? t.mask : MAP_MAX_PROBES;
+  for (unsigned n = 0; n <= limit; ++n) {
     const MapCell c = map_load(t.cells + s);
     if (c.key == key) { *seen = c; return (int)s; }
     if (c.key == MAP_EMPTY) {
@@ -97,7 +101,8 @@ __device__ __forceinline__ int map_find_or_insert(const MapTable& t, u64 key, Ma
 
 __device__ __forceinline__ int map_find(const MapTable& t, u64 key, MapCell* seen) {
   unsigned s = map_hash(key) & t.mask;
-  for (unsigned n = 0; n <= t.mask; ++n) {
+  const unsigned limit = t.mask < MAP_MAX_PROBES ? t.mask : MAP_MAX_PROBES;
+  for (unsigned n = 0; n <= limit; ++n) {
     const MapCell c = map_load(t.cells + s);
     if (c.key == key) { *seen = c; return (int)s; }
     if (c.key == MAP_EMPTY) return -1;
