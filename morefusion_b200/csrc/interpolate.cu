@@ -333,7 +333,10 @@ __device__ __forceinline__ void cache_points(PointCache& pc, const StreamArgs& a
   const int lane = threadIdx.x & 31;
   // chunks of ST_CHUNK indices; a chunk is only taken if it is certain to fit
   for (long long base = from; base < a.P; base += ST_CHUNK) {
-    if (pc.count + ST_CHUNK > cap && pc.count > 0) {   // uniform: read after the barrier below
+    // every thread reads the count, THEN the block votes (barrier): nobody can be past the vote
+    // and already appending while another thread still reads, and the decision is uniform
+    const int cnt = pc.count;
+    if (__syncthreads_or(cnt + ST_CHUNK > cap && cnt > 0)) {
       if (threadIdx.x == 0) pc.next = (int)base;
       break;
     }
@@ -426,7 +429,9 @@ k_interp_bwd_cells(StreamArgs a) {
         if (tid == 0) { pc.count = 0; pc.next = (int)a.P; pc.n_nz = 0; }
         __syncthreads();
         for (long long base = from; base < a.P; base += GB_CHUNK) {
-          if (pc.count + GB_CHUNK > GB_MAXP) {               // uniform (read after a barrier)
+          // read, then vote with a barrier: uniform decision, no thread appends while another reads
+          const int cnt = pc.count;
+          if (__syncthreads_or(cnt + GB_CHUNK > GB_MAXP)) {
             if (tid == 0) pc.next = (int)base;
             break;
           }
@@ -445,7 +450,7 @@ k_interp_bwd_cells(StreamArgs a) {
               int pos = 0;
               if (lane == 0) pos = atomicAdd(&pc.count, __popc(bal));
               pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-              if (m) {
+              if (m && pos < GB_MAXP) {
                 const long long n = base + u * GB_THREADS + tid;
                 pc.n[pos] = (int)n;
                 pc.x[pos] = __ldg(a.points + 3 * n);
