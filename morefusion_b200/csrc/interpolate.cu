@@ -742,7 +742,7 @@ k_interp_stream(StreamArgs a) {
 static int stream_planes(long long V, int C, int B, int n_sm) {
   if ((V & 3) != 0 || V * 4 > 64 * 1024) return 0;
   int cg = 16;
-  while (cg > 1 && (cg * V * 4 > 64 * 1024 || (long long)((C + cg - 1) / cg) * B < 3LL * n_sm)) cg >>= 1;
+  while (cg > 1 && (cg * V * 4 > 64 * 1024 || (long long)((C + cg - 1) / cg) * B * 2 < 3LL * n_sm)) cg >>= 1;
   return cg;
 }
 

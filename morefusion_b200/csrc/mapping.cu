@@ -205,7 +205,7 @@ k_map_scan_hits(ScanParams p, MapTable t) {
 // The key ray of computeRayKeys (oracle/octomap.py::OcTree.computeRayKeys has the line-by-line
 // commentary): first cell included, end cell excluded; every cell of the ray that this scan has not
 // hit gets the miss update.  Runs after k_map_scan_hits of the same scan (stream order).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_map_scan_free(ScanParams p, MapTable t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
