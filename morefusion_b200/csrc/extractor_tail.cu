@@ -14,7 +14,7 @@
 // pix [B, P] int64 = row-major index into the H x W = 2Hs x 2Ws image; out [B, 32, P] fp32 (the
 // `values` layout of the 3-D section).  One persistent CTA per SM: 147 KB of transposed up3
 // weights + the 1x1 weights staged once, then tiles of 8 points: gather (coalesced over channels)
-// -> [576 x 8] operand in shared memory -> 128 threads = 64 output channels x 2 K-halves with 8
+// -> [576 x 8] operand in shared memory -> 512 threads = 64 output channels x 8 K-slices with 8
 // accumulators each (every weight read from shared memory feeds 8 FMAs).
 #include "common.cuh"
 
@@ -24,7 +24,8 @@ constexpr int TAIL_C = 64;          // channels of up2 / up3
 constexpr int TAIL_K = TAIL_C * 9;  // 576
 constexpr int TAIL_O = 32;          // output features
 constexpr int TAIL_PT = 8;          // points per tile
-constexpr int TAIL_THREADS = 128;
+constexpr int TAIL_THREADS = 512;      // 64 channels x 8 slices (gather pairs / K ranges)
+constexpr int TAIL_SLICES = TAIL_THREADS / TAIL_C;   // 8
 
 struct TailParams {
   const float* up2;   // [B,Hs,Ws,64]
@@ -44,8 +45,8 @@ k_psp_tail_sampled(TailParams p) {
   float* sW3 = smem;                          // [576][64]
   float* sW1 = sW3 + TAIL_K * TAIL_C;         // [64][32]
   float* sU = sW1 + TAIL_C * TAIL_O;          // [576][8]
-  float* sPart = sU + TAIL_K * TAIL_PT;       // [2][8][64]
-  float* sO = sPart + 2 * TAIL_PT * TAIL_C;   // [8][64]
+  float* sPart = sU + TAIL_K * TAIL_PT;       // [8 slices][8][64]
+  float* sO = sPart + TAIL_SLICES * TAIL_PT * TAIL_C;   // [8][64]
   const int tid = threadIdx.x;
   for (int i = tid; i < TAIL_K * TAIL_C / 4; i += TAIL_THREADS)
     reinterpret_cast<float4*>(sW3)[i] = __ldg(reinterpret_cast<const float4*>(p.w3t) + i);
@@ -64,41 +65,58 @@ k_psp_tail_sampled(TailParams p) {
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TAIL_PT;
-    // ---- gather: U[ci*9 + tap][q] = resized up2 at the tap's pixel (0 outside the image)
-    for (int pair = sub; pair < TAIL_PT * 9; pair += 2) {
-      const int q = pair / 9, tap = pair - q * 9;
-      const long long n = n0 + q;
-      float v = 0.f;
-      if (n < NP) {
-        const int b = (int)(n / p.P);
-        const long long px = p.pix[n];
-        const int r = (int)(px / W) + tap / 3 - 1, c = (int)(px % W) + tap % 3 - 1;
-        if (r >= 0 && r < H && c >= 0 && c < W) {
-          const float fy = sy * (float)r, fx = sx * (float)c;
-          const int y0 = (int)fy, x0 = (int)fx;
-          const int y1 = y0 + (y0 < p.Hs - 1), x1 = x0 + (x0 < p.Ws - 1);
-          const float wy1 = fy - (float)y0, wx1 = fx - (float)x0;
-          const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-          const float* base = p.up2 + (size_t)b * p.Hs * p.Ws * TAIL_C + ci;
-          const float a = __ldg(base + ((size_t)y0 * p.Ws + x0) * TAIL_C);
-          const float bb = __ldg(base + ((size_t)y0 * p.Ws + x1) * TAIL_C);
-          const float cc = __ldg(base + ((size_t)y1 * p.Ws + x0) * TAIL_C);
-          const float d = __ldg(base + ((size_t)y1 * p.Ws + x1) * TAIL_C);
-          v = wy0 * (wx0 * a + wx1 * bb) + wy1 * (wx0 * cc + wx1 * d);
+    // ---- gather: U[ci*9 + tap][q] = resized up2 at the tap's pixel (0 outside the image).
+    // 72 (point, tap) pairs x 64 channels = 9 values per thread; the 36 loads of a thread are all
+    // requested before the first is used (the first version walked them one pair at a time with
+    // 4 warps per SM: 219 us, all of it L2 latency)
+    {
+      constexpr int NPAIR = TAIL_PT * 9 / TAIL_SLICES;     // 9
+      float a[NPAIR], bb[NPAIR], cc[NPAIR], d[NPAIR], wy1[NPAIR], wx1[NPAIR];
+      bool ok[NPAIR];
+#pragma unroll
+      for (int i = 0; i < NPAIR; ++i) {
+        const int pair = sub + TAIL_SLICES * i;
+        const int q = pair / 9, tap = pair - q * 9;
+        const long long n = n0 + q;
+        ok[i] = false;
+        a[i] = bb[i] = cc[i] = d[i] = wy1[i] = wx1[i] = 0.f;
+        if (n < NP) {
+          const int b = (int)(n / p.P);
+          const long long px = __ldg(p.pix + n);
+          const int r = (int)(px / W) + tap / 3 - 1, c = (int)(px % W) + tap % 3 - 1;
+          if (r >= 0 && r < H && c >= 0 && c < W) {
+            const float fy = sy * (float)r, fx = sx * (float)c;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = y0 + (y0 < p.Hs - 1), x1 = x0 + (x0 < p.Ws - 1);
+            wy1[i] = fy - (float)y0; wx1[i] = fx - (float)x0;
+            const float* base = p.up2 + (size_t)b * p.Hs * p.Ws * TAIL_C + ci;
+            a[i] = __ldg(base + ((size_t)y0 * p.Ws + x0) * TAIL_C);
+            bb[i] = __ldg(base + ((size_t)y0 * p.Ws + x1) * TAIL_C);
+            cc[i] = __ldg(base + ((size_t)y1 * p.Ws + x0) * TAIL_C);
+            d[i] = __ldg(base + ((size_t)y1 * p.Ws + x1) * TAIL_C);
+            ok[i] = true;
+          }
         }
       }
-      sU[(ci * 9 + tap) * TAIL_PT + q] = v;
+#pragma unroll
+      for (int i = 0; i < NPAIR; ++i) {
+        const int pair = sub + TAIL_SLICES * i;
+        const int q = pair / 9, tap = pair - q * 9;
+        const float wy0 = 1.f - wy1[i], wx0 = 1.f - wx1[i];
+        const float v = ok[i] ? wy0 * (wx0 * a[i] + wx1[i] * bb[i]) + wy1[i] * (wx0 * cc[i] + wx1[i] * d[i]) : 0.f;
+        sU[(ci * 9 + tap) * TAIL_PT + q] = v;
+      }
     }
     __syncthreads();
-    // ---- up3 conv: o[q][co] = sum_k W3t[k][co] * U[k][q], two K-halves
+    // ---- up3 conv: o[q][co] = sum_k W3t[k][co] * U[k][q], 8 K-slices of 72
     {
       const int co = ci, h = sub;
       float acc[TAIL_PT];
 #pragma unroll
       for (int q = 0; q < TAIL_PT; ++q) acc[q] = 0.f;
-      const int k0 = h * (TAIL_K / 2);
+      const int k0 = h * (TAIL_K / TAIL_SLICES);
 #pragma unroll 4
-      for (int k = k0; k < k0 + TAIL_K / 2; ++k) {
+      for (int k = k0; k < k0 + TAIL_K / TAIL_SLICES; ++k) {
         const float w = sW3[k * TAIL_C + co];
         const float4 u0 = *reinterpret_cast<const float4*>(sU + k * TAIL_PT);
         const float4 u1 = *reinterpret_cast<const float4*>(sU + k * TAIL_PT + 4);
@@ -114,11 +132,13 @@ k_psp_tail_sampled(TailParams p) {
     // ---- bias + PReLU
     for (int e = tid; e < TAIL_PT * TAIL_C; e += TAIL_THREADS) {
       const int co = e & 63;
-      const float o = __ldg(p.b3 + co) + sPart[e] + sPart[TAIL_PT * TAIL_C + e];
+      float o = __ldg(p.b3 + co);
+#pragma unroll
+      for (int h = 0; h < TAIL_SLICES; ++h) o += sPart[h * TAIL_PT * TAIL_C + e];
       sO[e] = o > 0.f ? o : slope * o;
     }
     __syncthreads();
-    // ---- 1x1 conv + log-softmax over the 32 features: one warp per point (2 points per warp)
+    // ---- 1x1 conv + log-softmax over the 32 features: one warp per point
     {
       const int warp = tid >> 5, lane = tid & 31;
       for (int q = warp; q < TAIL_PT; q += TAIL_THREADS / 32) {
@@ -149,7 +169,7 @@ extern "C" int mf_psp_tail_sampled(const float* up2_nhwc, const int64_t* pix, in
       Ws <= 0 || (long long)Hs * Ws >= (1LL << 28))
     return MF_E_BADARG;
   const size_t smem = sizeof(float) * (TAIL_K * TAIL_C + TAIL_C * TAIL_O + TAIL_K * TAIL_PT +
-                                       2 * TAIL_PT * TAIL_C + TAIL_PT * TAIL_C);
+                                       TAIL_SLICES * TAIL_PT * TAIL_C + TAIL_PT * TAIL_C);
   MF_ENSURE_DYN_SMEM(k_psp_tail_sampled, smem);
   int dev = 0, n_sm = 0;
   MF_CUDA_TRY(cudaGetDevice(&dev));
