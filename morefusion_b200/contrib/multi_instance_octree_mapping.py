@@ -52,6 +52,7 @@ class MultiInstanceOctreeMapping:
         self._pending = None                     # event of the last asynchronous counter read-back
         self._res_factor = None                  # cached device array of 1 / pitch
         self._lut = None                         # cached (lut, lut_lo, resolutions) device arrays
+        self._query_cache = None                 # cached (key, targets, pitches, origins) device arrays
 
     # ------------------------------------------------------------------ table management
     def _alloc_table(self, cap):
@@ -223,9 +224,13 @@ class MultiInstanceOctreeMapping:
             self._res_factor = torch.as_tensor(1.0 / np.asarray(self._pitch, dtype=np.float64)).to(dev)
         X, Y, Z = (int(d) for d in dimensions)
         out = torch.empty((3, T, X, Y, Z), dtype=torch.float32, device=dev)
-        d_tix = torch.as_tensor(tix).to(dev)
-        d_pit = torch.as_tensor(pit).to(dev)
-        d_org = torch.as_tensor(org).to(dev)
+        # the per-frame path asks for the same targets frame after frame: their small device
+        # arrays are uploaded once per distinct (targets, pitches, origins)
+        key = (tix.tobytes(), pit.tobytes(), org.tobytes())
+        if self._query_cache is None or self._query_cache[0] != key:
+            self._query_cache = (key, torch.as_tensor(tix).to(dev), torch.as_tensor(pit).to(dev),
+                                 torch.as_tensor(org).to(dev))
+        _, d_tix, d_pit, d_org = self._query_cache
         with self._dev_ctx():
             _lib.check(_lib.lib().mf_map_query_grids(
                 _lib.ptr(d_tix), _lib.ptr(d_pit), _lib.ptr(d_org), T, X, Y, Z,
