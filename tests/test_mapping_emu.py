@@ -255,6 +255,38 @@ def _nan_rows(pcd):
     return pcd
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scans_negative_coordinates_and_odd_pitches(emu_mapping, seed):
+    """Random point sets on both sides of every axis, sensor origins off the lattice, pitches that
+    are not exactly representable: the cell keys, the DDA and the once-per-scan rule against the
+    oracle, bit for bit, after three scans per instance."""
+    rs = np.random.RandomState(100 + seed)
+    ours, ref = emu_mapping(device="cpu", capacity=1 << 15), oc.MultiInstanceOctreeMapping()
+    pitches = {4: float(rs.uniform(0.003, 0.02)), 9: 0.0075, 0: float(rs.uniform(0.01, 0.03))}
+    for ins, pitch in pitches.items():
+        ours.initialize(ins, pitch=pitch)
+        ref.initialize(ins, pitch=pitch)
+    for scan in range(3):
+        origin = rs.uniform(-0.05, 0.05, 3)
+        pcd = rs.uniform(-0.25, 0.25, (10, 12, 3)).astype(np.float32)
+        pcd[rs.rand(10, 12) < 0.1] = np.nan
+        if scan == 1:
+            pcd[0, 0] = origin.astype(np.float32)                # zero-length ray
+            pcd[0, 1] = [1e6, 0, 0]                              # end point outside the key range
+        label = rs.choice([4, 9, 0, 5], size=(10, 12))           # 5 is never initialised
+        for ins in pitches:
+            ours.integrate(ins, label == ins, pcd, origin)
+            ref.integrate(ins, label == ins, pcd, origin)
+    assert_cells_equal(ours, ref)
+    for tid in (4, 9):
+        org = rs.uniform(-0.2, -0.1, 3)
+        got = ours.get_target_grids(tid, dimensions=(12, 12, 12), pitch=0.02, origin=org)
+        want = ref.get_target_grids(tid, dimensions=(12, 12, 12), pitch=0.02, origin=org)
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g > 0, w > 0)
+            np.testing.assert_allclose(g, w, rtol=0, atol=1e-7)
+
+
 def test_ray_walk_against_oracle_dense(emu_mapping):
     """The DDA over many random rays, including axis-aligned, zero-length and far rays, from an
     origin that sits exactly on cell borders."""
