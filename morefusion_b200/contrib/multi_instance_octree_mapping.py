@@ -84,9 +84,16 @@ class MultiInstanceOctreeMapping:
         self._pending = torch.cuda.Event()
         self._pending.record(torch.cuda.current_stream(self.device))
 
-    def _check(self):
-        """Act on the counters of the previous operation: errors for dropped work, growth."""
+    def _check(self, wait=True):
+        """Act on the counters of the previous operation: errors for dropped work, growth.
+        `wait=False` (the per-frame calls integrate_labels / get_target_grids_batch) never blocks
+        the host: if the read-back of the previous operation has not landed yet it is looked at by
+        a later call (the table grows at a quarter full, so a decision that lags a scan is still
+        early; overflow is sticky and cannot be missed).  The reference-style calls wait, which
+        keeps growth decisions exact for small tables."""
         if self._pending is None:
+            return
+        if not wait and not self._pending.query():
             return
         self._pending.synchronize()
         self._pending = None
@@ -169,7 +176,7 @@ class MultiInstanceOctreeMapping:
         lab = lab.to(torch.int32).contiguous()
         n = pts.numel() // 3
         org = np.asarray(origin, dtype=np.float64).astype(np.float32)
-        self._check()
+        self._check(wait=False)
         if n == 0 or not self._ids:
             return
         if self._lut is None:
@@ -219,7 +226,7 @@ class MultiInstanceOctreeMapping:
         assert (pit > 0).all()
         tix = np.asarray([self._ids[t] for t in target_ids], dtype=np.int32)
         dev = self.device
-        self._check()
+        self._check(wait=False)
         if self._res_factor is None:
             self._res_factor = torch.as_tensor(1.0 / np.asarray(self._pitch, dtype=np.float64)).to(dev)
         X, Y, Z = (int(d) for d in dimensions)
@@ -243,6 +250,7 @@ class MultiInstanceOctreeMapping:
         (:35-94)."""
         assert not np.isnan(origin).any()
         assert pitch > 0
+        self._check()
         gt, gn, ge = self.get_target_grids_batch(
             [target_id], dimensions=dimensions, pitches=[pitch], origins=[origin])
         return gt[0].cpu().numpy(), gn[0].cpu().numpy(), ge[0].cpu().numpy()

@@ -74,6 +74,9 @@ def emu_mapping(emu, monkeypatch):
             class Done:
                 def synchronize(self):
                     pass
+
+                def query(self):
+                    return True
             self._pending = Done()
 
     return EmuMapping
