@@ -270,14 +270,13 @@ class MultiInstanceOctreeMapping:
         coords = ((kxyz - _TREE_MAX_VAL).to(torch.float64) + 0.5) * self._pitch[idx]
         coords = coords.to(torch.float32).to(torch.float64).cpu().numpy()   # point3d floats -> float64
         occ = (lo >= 0).cpu().numpy()
-        occupied, empty = coords[occ], coords[~occ]
+        # axis-aligned box [aabb_min, aabb_max): lower bound inclusive, upper exclusive (:124-131)
+        inside = np.ones(len(coords), dtype=bool)
         if aabb_min is not None:
-            occupied = occupied[(occupied >= aabb_min).all(axis=1)]
-            empty = empty[(empty >= aabb_min).all(axis=1)]
+            inside &= (coords >= np.asarray(aabb_min)).all(axis=1)
         if aabb_max is not None:
-            occupied = occupied[(occupied < aabb_max).all(axis=1)]
-            empty = empty[(empty < aabb_max).all(axis=1)]
-        return occupied, empty
+            inside &= (coords < np.asarray(aabb_max)).all(axis=1)
+        return coords[occ & inside], coords[~occ & inside]
 
     # ------------------------------------------------------------------ introspection (tests, bench)
     def n_cells(self):
