@@ -675,15 +675,18 @@ def run_ours(args, rank, world, local):
         except Exception as e:      # a sub-record must not take the headline line down
             records[name] = dict(error=f"{type(e).__name__}: {e}")
     # ---- CPU baseline: oracle port on the host cores, bounded sample
-    threads = pick_threads(weights, batches[0])
-    n_obj = 2
-    reps, t_cpu = 0, 0.0
-    while t_cpu < 8.0 and reps < 6:
-        t_cpu += cpu_port_step(weights, batches[0], n_obj)
-        reps += 1
-    cpu = dict(value=n_obj * reps / t_cpu, unit="objects/s", cores=threads, host_cores=os.cpu_count(),
-               kind="port",
-               sample=f"{n_obj} objects x {reps} passes of the oracle port (torch-CPU fp32 convs + NumPy kernels)")
+    if world == 1:
+        threads = pick_threads(weights, batches[0])
+        n_obj = 2
+        reps, t_cpu = 0, 0.0
+        while t_cpu < 8.0 and reps < 6:
+            t_cpu += cpu_port_step(weights, batches[0], n_obj)
+            reps += 1
+        cpu = dict(value=n_obj * reps / t_cpu, unit="objects/s", cores=threads, host_cores=os.cpu_count(),
+                   kind="port",
+                   sample=f"{n_obj} objects x {reps} passes of the oracle port (torch-CPU fp32 convs + NumPy kernels)")
+    else:       # the host-core baseline is a 1-GPU figure: N ranks would time each other's threads
+        cpu = dict(value=None, unit="objects/s", kind="port", sample="measured at N=1 only (see the 1-GPU line)")
     line = dict(
         metric=METRIC, value=value, unit="objects/s", n_gpus=world, steps=K, warmup=max(args.warmup, 3),
         ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
