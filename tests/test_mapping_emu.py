@@ -251,6 +251,26 @@ def test_labelled_frame_equals_per_instance_scans(emu_mapping):
     assert m._scan == 2 and ref._scan == 8                        # 2 launches pairs instead of 8
 
 
+def test_labelled_frame_with_negative_and_sparse_instance_ids(emu_mapping):
+    """Instance ids as the ROS node numbers them (-1 = background, arbitrary positive ids): the
+    label look-up table covers [min id, max id] and skips everything else."""
+    pcd, fg = make_scene(2)
+    label = np.where(fg, 41, -1).astype(np.int64)
+    label[:2] = -2                                            # "uncertain" pixels: never integrated
+    label[2, :4] = 17                                         # inside the table's range, not an instance
+    a, b = emu_mapping(device="cpu", capacity=1 << 14), emu_mapping(device="cpu", capacity=1 << 14)
+    for m in (a, b):
+        m.initialize(41, pitch=0.008)
+        m.initialize(-1, pitch=0.02)
+    a.integrate_labels(label, pcd)
+    b.integrate(41, label == 41, pcd)
+    b.integrate(-1, label == -1, pcd)
+    for ins in (41, -1):
+        assert a.cells(ins) == b.cells(ins) and len(a.cells(ins)) > 100
+    with pytest.raises(ValueError, match="integer"):
+        a.integrate_labels(label.astype(np.float32), pcd)
+
+
 def _nan_rows(pcd):
     pcd = pcd.copy()
     pcd[0, :5] = np.nan
