@@ -362,9 +362,35 @@ def gen_octree_mapping():
     _save("octree_mapping", **out)
 
 
+def gen_octree_mapping_update():
+    """The reference class's ``update`` (multi_instance_octree_mapping.py:29-34: updateNodes on
+    every row, then updateInnerOccupancy) after one scan, and the grids it leads to."""
+    shim.install()
+    mod = shim.ref_module("contrib.multi_instance_octree_mapping")
+    pcd, label, org = octree_mapping_scene(seed=33, H=24, W=32)[0]
+    mapping = mod.MultiInstanceOctreeMapping()
+    mapping.initialize(1, pitch=0.006)
+    mapping.initialize(0, pitch=0.012)
+    mapping.integrate(1, label == 1, pcd, origin=org)
+    mapping.integrate(0, label != 1, pcd, origin=org)
+    rs = np.random.RandomState(5)
+    centre = np.nanmedian(pcd[label == 1], axis=0).astype(np.float64)
+    occupied = centre + rs.uniform(-0.03, 0.03, (400, 3))
+    occupied[:12] = occupied[0]                     # 12 rows in one cell: the clamp is reached
+    mapping.update(1, occupied)
+    cells = mapping._octrees[1].cells
+    keys = np.array(sorted(cells), dtype=np.int32).reshape(-1, 3)
+    origin = centre - 7.5 * 0.006
+    gt, gn, ge = mapping.get_target_grids(1, dimensions=(16, 16, 16), pitch=0.006, origin=origin)
+    _save("octree_mapping_update", pcd=pcd, label=label, origin=org, occupied=occupied,
+          cells_keys_1=keys, cells_logodds_1=np.array([cells[tuple(k)] for k in keys], dtype=F32),
+          grid_origin=origin, ref_grid_target=gt, ref_grid_nontarget=gn, ref_grid_empty=ge)
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     gen_octree_mapping()
+    gen_octree_mapping_update()
     gen_average_distance()
     gen_voxelization()
     gen_interpolate()

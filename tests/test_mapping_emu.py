@@ -224,6 +224,34 @@ def check_golden(m, g, to_np=lambda a: a):
     np.testing.assert_array_equal(emp, g["ref_pcd_empty_2"])
 
 
+def run_golden_update(make, g):
+    m = make()
+    m.initialize(1, pitch=0.006)
+    m.initialize(0, pitch=0.012)
+    m.integrate(1, g["label"] == 1, g["pcd"], origin=g["origin"])
+    m.integrate(0, g["label"] != 1, g["pcd"], origin=g["origin"])
+    m.update(1, g["occupied"])
+    return m
+
+
+def test_golden_reference_update(emu_mapping):
+    """``update`` (updateNodes row by row, clamping after 12 hits on one cell) as the reference's
+    own class performs it over the restated OcTree (tests/golden/octree_mapping_update.npz)."""
+    from conftest import golden
+    g = golden("octree_mapping_update")
+    for m in (run_golden_update(lambda: emu_mapping(device="cpu", capacity=1 << 14), g),
+              run_golden_update(oc.MultiInstanceOctreeMapping, g)):
+        cells = m.cells(1) if hasattr(m, "cells") else m._octrees[1].cells
+        keys = g["cells_keys_1"]
+        assert len(cells) == len(keys)
+        assert np.array_equal(np.array([cells[tuple(k)] for k in keys], np.float32), g["cells_logodds_1"])
+        grids = m.get_target_grids(1, dimensions=(16, 16, 16), pitch=0.006, origin=g["grid_origin"])
+        for name, a in zip(("target", "nontarget", "empty"), grids):
+            np.testing.assert_array_equal(a > 0, g[f"ref_grid_{name}"] > 0)
+            np.testing.assert_allclose(a, g[f"ref_grid_{name}"], rtol=0, atol=1e-7)
+    assert g["cells_logodds_1"].max() == np.float32(oc.logodds(0.971))      # the clamp was reached
+
+
 def test_golden_reference_run(emu_mapping):
     from conftest import golden
     g = golden("octree_mapping")
